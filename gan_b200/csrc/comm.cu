@@ -1,0 +1,72 @@
+// comm.cu — data-parallel gradient exchange over NCCL (NVLink 5 / NVSwitch).
+//
+// The reference is single-device (base_gan.py:18-19 only prints the GPU count); data parallelism
+// is new work defined by BASELINE.json.  NCCL is resolved at run time with dlopen so that the
+// library links against nothing but cudart: one process per GPU loads the same libnccl that
+// torch.distributed already mapped; the unique id is exchanged by the Python host through
+// torch.distributed (plumbing only).
+#include <dlfcn.h>
+#include <cstring>
+#include "engine.h"
+
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void* ncclComm_t_;
+typedef int (*fn_getuid)(ncclUniqueId_t*);
+typedef int (*fn_initrank)(ncclComm_t_*, int, ncclUniqueId_t, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+typedef int (*fn_destroy)(ncclComm_t_);
+typedef const char* (*fn_errstr)(int);
+
+static struct {
+  void* lib = nullptr;
+  fn_getuid getuid = nullptr; fn_initrank initrank = nullptr; fn_allreduce allreduce = nullptr;
+  fn_destroy destroy = nullptr; fn_errstr errstr = nullptr;
+} g_nccl;
+
+static void nccl_load() {
+  if (g_nccl.lib) return;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.lib; ++i) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.lib) throw GanError(-4, std::string("cannot dlopen libnccl: ") + dlerror());
+  g_nccl.getuid = (fn_getuid)dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.initrank = (fn_initrank)dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.getuid || !g_nccl.initrank || !g_nccl.allreduce || !g_nccl.destroy)
+    throw GanError(-4, "libnccl is missing required symbols");
+}
+static void nccl_check(int r, const char* what) {
+  if (r != 0) throw GanError(-4, std::string(what) + ": " + (g_nccl.errstr ? g_nccl.errstr(r) : "nccl error"));
+}
+
+int comm_unique_id(void* out128) {
+  try { nccl_load(); } catch (...) { return -1; }
+  ncclUniqueId_t id;
+  if (g_nccl.getuid(&id) != 0) return -1;
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+void comm_init(gan_ctx* ctx, int rank, int world, const void* id128) {
+  GAN_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  ctx->rank = rank; ctx->world = world;
+  if (world == 1) return;
+  nccl_load();
+  ncclUniqueId_t id; memcpy(&id, id128, 128);
+  ncclComm_t_ c = nullptr;
+  nccl_check(g_nccl.initrank(&c, world, id, rank), "ncclCommInitRank");
+  ctx->comm = c;
+}
+
+void comm_destroy(gan_ctx* ctx) {
+  if (ctx->comm && g_nccl.destroy) g_nccl.destroy((ncclComm_t_)ctx->comm);
+  ctx->comm = nullptr;
+}
+
+// Sum-all-reduce of an fp32 buffer, enqueued on the ctx stream (ncclFloat32 = 7, ncclSum = 0).
+void comm_allreduce_sum(gan_ctx* ctx, float* buf, int64_t n) {
+  if (ctx->world <= 1) return;
+  GAN_REQUIRE(ctx->comm != nullptr, "communicator not initialised");
+  nccl_check(g_nccl.allreduce(buf, buf, (size_t)n, 7, 0, (ncclComm_t_)ctx->comm, ctx->stream), "ncclAllReduce");
+}

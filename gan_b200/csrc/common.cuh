@@ -1,0 +1,142 @@
+// common.cuh — shared types for the gan_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <stdexcept>
+
+typedef __nv_bfloat16 bf16;
+
+enum { DT_F32 = 0, DT_BF16 = 1 };
+enum { K_CONV_S2 = 0, K_CONV_S1P = 1, K_CONVT_S2 = 2 };
+enum { NORM_NONE = 0, NORM_BATCH = 1, NORM_INSTANCE = 2 };
+enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3 };
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2 };
+
+#define LEAKY_SLOPE 0.3f
+
+// A strided NHWC view: element (n,h,w,c) lives at p[((n*H+h)*W+w)*pitch + coff + c].
+struct View {
+  void* p;
+  int N, H, W, C;
+  int pitch;   // elements per pixel in the underlying buffer (>= coff + C)
+  int coff;    // channel offset inside the pixel
+  int64_t pixels() const { return (int64_t)N * H * W; }
+};
+
+static inline View make_view(void* p, int N, int H, int W, int C, int pitch = -1, int coff = 0) {
+  View v; v.p = p; v.N = N; v.H = H; v.W = W; v.C = C; v.pitch = pitch < 0 ? C : pitch; v.coff = coff; return v;
+}
+
+// One output class of a "tap GEMM" (see DESIGN.md §3): out pixel (mh*so+oa, mw*so+ob) of the
+// M-space point (n,mh,mw) accumulates, for every tap t, in[n, mh*si+dh[t], mw*si+dw[t], :] times
+// the packed weight slab [Nc][t*Kc .. t*Kc+Kc).
+struct ClassGeom {
+  int oa, ob, ntaps;
+  int8_t dh[16], dw[16], widx[16];   // widx = kh*4+kw of the master 4x4 kernel
+  int64_t b_off;                     // element offset of this class's packed weights
+};
+
+struct ConvOp {
+  const void* in; int in_pitch, in_coff, Hin, Win;
+  void* out;      int out_pitch, out_coff, Hout, Wout;
+  int N, Hm, Wm;                 // M-space extents
+  int si, so;                    // input / output pixel stride of the M-space
+  int Kc, Nc;                    // channels per tap (GEMM K = ntaps*Kc), output channels (GEMM N)
+  int ncls;
+  ClassGeom cls[4];
+  const void* B;                 // packed weights, dtype = activation dtype
+  const float* bias; int epi;    // forward epilogue
+  float* out_f32;                // optional fp32 copy of the epilogue output, compact [pix][Nc]
+  // wgrad: dW[widx*s_tap + kc*s_k + nc*s_n] += sum_m in(m,t,kc) * out(m,nc)
+  float* dW; int64_t s_tap, s_k, s_n;
+};
+
+// ---- error handling (host) -----------------------------------------------------------------
+struct GanError : public std::runtime_error {
+  int code;
+  GanError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      throw GanError(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +   \
+                             __FILE__ + ":" + std::to_string(__LINE__));                         \
+  } while (0)
+
+#define GAN_REQUIRE(cond, msg)                                                                   \
+  do {                                                                                           \
+    if (!(cond)) throw GanError(-1, std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +    \
+                                        std::to_string(__LINE__));                               \
+  } while (0)
+
+// ---- device helpers ------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <typename T> struct VecIO;
+
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <> struct VecIO<bf16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ static __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Philox-4x32-10 (same definition as oracle/gan_oracle.py:philox4x32_10).
+__device__ __forceinline__ uint32_t philox_word0(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+// Dropout(0.5) keep decision for element `elem` of global sample `sample` (base_gan.py:118).
+struct DropKey { uint32_t seed_lo, seed_hi, call, layer; int64_t sample0; int enabled; };
+__device__ __forceinline__ bool dropout_keep(const DropKey& k, int64_t sample_local, uint32_t elem) {
+  uint32_t w = philox_word0(elem, (uint32_t)(k.sample0 + sample_local), k.layer, k.call, k.seed_lo, k.seed_hi);
+  return (w >> 31) != 0u;
+}
+#else
+struct DropKey { uint32_t seed_lo, seed_hi, call, layer; int64_t sample0; int enabled; };
+#endif

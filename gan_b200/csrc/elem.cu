@@ -1,0 +1,556 @@
+// elem.cu — memory-bound kernels of the GAN train step: layout conversion, normalisation
+// statistics / apply / backward (BatchNorm base_gan.py:83,113,151 and InstanceNormalization
+// utils.py:6-30), activations (LeakyReLU 0.3 base_gan.py:87,155; ReLU :120; Dropout 0.5 :118),
+// losses (BCE-from-logits base_gan.py:227-245, L1 pix2pix.py:181 / cycle_gan.py:167,176),
+// Keras Adam (base_gan.py:252) and weight packing.
+//
+// All of them are HBM-bound: 128-bit loads/stores, grid sized as a multiple of the 148 SMs,
+// fp32 math with double-precision final reductions, no atomics on the value paths except the
+// tiny bias-gradient sums.
+#include "kernels.h"
+
+#define NSM 148
+
+template <typename F> static void dispatch_dt(int dt, F&& f) {
+  if (dt == DT_F32) f((float*)nullptr); else f((bf16*)nullptr);
+}
+#define KLAUNCH(L) (++*(L).count)
+
+static inline int grid_for(int64_t work, int threads, int max_waves = 8) {
+  int64_t b = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)NSM * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 NHWC (compact) <-> strided view of dtype T
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_convert(const float* __restrict__ src, int64_t total, int C, T* __restrict__ dst, int pitch,
+                          int coff) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C; int c = (int)(i - p * C);
+    dst[p * pitch + coff + c] = from_f<T>(src[i]);
+  }
+}
+void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* dst, int pitch, int coff) {
+  int64_t total = P * C;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_convert<T><<<grid_for(total, 256), 256, 0, L.s>>>(src, total, C, (T*)dst, pitch, coff);
+  });
+  KLAUNCH(L);
+}
+
+template <typename T>
+__global__ void k_export(const T* __restrict__ src, int pitch, int coff, int64_t total, int C, float* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C; int c = (int)(i - p * C);
+    dst[i] = to_f(src[p * pitch + coff + c]);
+  }
+}
+void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64_t P, int C, float* dst) {
+  int64_t total = P * C;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_export<T><<<grid_for(total, 256), 256, 0, L.s>>>((const T*)src, pitch, coff, total, C, dst);
+  });
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Normalisation statistics.  z is compact [G*Pg][C]; group g covers rows [g*Pg,(g+1)*Pg).
+// Stage 1: each block reduces a chunk of rows to per-channel (sum, sumsq) in fp32.
+// Stage 2: chunks are combined in double; mean / inv-std / fused scale+shift are emitted.
+// ---------------------------------------------------------------------------------------------
+int stats_chunks(int G, int64_t Pg) {
+  int64_t want = (STATS_MAX_CHUNKS + G - 1) / G;         // fill ~4 waves of 148 SMs across all groups
+  int64_t maxc = (Pg + 31) / 32;                         // at least 32 rows per chunk
+  int64_t c = want < maxc ? want : maxc;
+  return (int)(c < 1 ? 1 : c);
+}
+size_t stats_ws_floats(int G, int64_t Pg, int C) { return (size_t)G * stats_chunks(G, Pg) * 2 * C; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, int64_t Pg, int C, int nchunk,
+                                                       float* __restrict__ ws) {
+  constexpr int V = VecIO<T>::N;
+  __shared__ float sh_s[256 * V];
+  __shared__ float sh_q[256 * V];
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int cv = C / V;
+  const int rows_par = 256 / cv;
+  const int col = threadIdx.x % cv, r = threadIdx.x / cv;
+  const int64_t per = (Pg + nchunk - 1) / nchunk;
+  const int64_t p0 = chunk * per, p1 = (p0 + per < Pg) ? p0 + per : Pg;
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (r < rows_par) {
+    const T* base = z + ((int64_t)g * Pg) * C + col * V;
+    for (int64_t p = p0 + r; p < p1; p += rows_par) {
+      float v[V];
+      VecIO<T>::load(base + p * C, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sh_s[threadIdx.x * V + i] = s[i]; sh_q[threadIdx.x * V + i] = q[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float S = 0.f, Q = 0.f;
+    for (int rr = 0; rr < rows_par; ++rr) {
+      int t = rr * cv + c / V;
+      S += sh_s[t * V + c % V]; Q += sh_q[t * V + c % V];
+    }
+    float* o = ws + ((int64_t)(g * nchunk + chunk) * 2) * C;
+    o[c] = S; o[C + c] = Q;
+  }
+}
+
+__global__ void k_stats_finalize(const float* __restrict__ ws, int G, int nchunk, int C, double n, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* __restrict__ mean, float* __restrict__ inv, float* __restrict__ scale,
+                                 float* __restrict__ shift, float* mov_mean, float* mov_var, float momentum) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  int g = i / C, c = i - g * C;
+  double S = 0.0, Q = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float* o = ws + ((int64_t)(g * nchunk + k) * 2) * C;
+    S += (double)o[c]; Q += (double)o[C + c];
+  }
+  double m = S / n;
+  double var = Q / n - m * m;
+  if (var < 0.0) var = 0.0;
+  double iv = 1.0 / sqrt(var + (double)eps);
+  float sc = (float)((double)gamma[c] * iv);
+  mean[i] = (float)m; inv[i] = (float)iv;
+  scale[i] = sc; shift[i] = (float)((double)beta[c] - m * (double)gamma[c] * iv);
+  if (mov_mean != nullptr) {
+    // Keras BatchNormalization moving averages (momentum 0.99); the fused TF kernel feeds the
+    // Bessel-corrected variance.  Never read on the hot path (every call is training=True).
+    double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * (float)m;
+    mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)unbiased;
+  }
+}
+
+void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C, float* ws, float eps,
+                       const float* gamma, const float* beta, float* mean, float* inv, float* scale,
+                       float* shift, float* mov_mean, float* mov_var, float momentum) {
+  int nchunk = stats_chunks(G, Pg);
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_stats_partial<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, Pg, C, nchunk, ws);
+  });
+  KLAUNCH(L);
+  k_stats_finalize<<<(G * C + 127) / 128, 128, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, eps, gamma, beta, mean, inv,
+                                                        scale, shift, mov_mean, mov_var, momentum);
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = act(dropout(z*scale + shift)) written into the consumer's (concat-offset) view.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(float u, int act) {
+  if (act == ACT_LEAKY) return u > 0.f ? u : LEAKY_SLOPE * u;
+  if (act == ACT_RELU) return u > 0.f ? u : 0.f;
+  if (act == ACT_TANH) return tanhf(u);
+  return u;
+}
+__device__ __forceinline__ float act_bwd(float u, int act) {
+  if (act == ACT_LEAKY) return u > 0.f ? 1.f : LEAKY_SLOPE;
+  if (act == ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, int64_t nvec, int64_t Pg, int G, int HW,
+                                                    int C, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, int act, DropKey dk,
+                                                    T* __restrict__ out, int out_pitch, int out_coff) {
+  constexpr int V = VecIO<T>::N;
+  const int cv = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / cv; int c0 = (int)(i - p * cv) * V;
+    float v[V];
+    VecIO<T>::load(z + p * C + c0, v);
+    if (scale != nullptr) {
+      int g = (G == 1) ? 0 : (int)(p / Pg);
+      const float* sc = scale + (int64_t)g * C + c0; const float* sh = shift + (int64_t)g * C + c0;
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = fmaf(v[k], __ldg(sc + k), __ldg(sh + k));
+    }
+    if (dk.enabled) {
+      int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = dropout_keep(dk, smp, e0 + k) ? 2.f * v[k] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = act_fwd(v[k], act);
+    VecIO<T>::store(out + p * out_pitch + out_coff + c0, v);
+  }
+}
+
+void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, int G, int HW, int C,
+                       const float* scale, const float* shift, int act, DropKey dk, void* out, int out_pitch,
+                       int out_coff) {
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    int64_t nvec = P * (C / VecIO<T>::N);
+    k_norm_apply<T><<<grid_for(nvec, 256), 256, 0, L.s>>>((const T*)z, nvec, Pg, G, HW, C, scale, shift, act, dk,
+                                                          (T*)out, out_pitch, out_coff);
+  });
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of norm -> dropout -> activation.
+//   g    = (d1 + d2) * act'(.) * dropout'      (gradient w.r.t. the affine output u = gamma*xhat+beta)
+//   dbeta = sum g, dgamma = sum g*xhat,  dz = gamma*inv * (g - mean(g) - xhat*mean(g*xhat))
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__device__ __forceinline__ void load_grad(const GradSrc& d1, const GradSrc& d2, int64_t p, int c0, float (&g)[V]) {
+  VecIO<T>::load((const T*)d1.p + p * d1.pitch + d1.coff + c0, g);
+  if (d2.p != nullptr) {
+    float h[V];
+    VecIO<T>::load((const T*)d2.p + p * d2.pitch + d2.coff + c0, h);
+#pragma unroll
+    for (int k = 0; k < V; ++k) g[k] += h[k];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, GradSrc d1, GradSrc d2, int64_t Pg, int HW,
+                                                    int C, int nchunk, const float* __restrict__ mean,
+                                                    const float* __restrict__ inv, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, int act, DropKey dk,
+                                                    float* __restrict__ ws) {
+  constexpr int V = VecIO<T>::N;
+  __shared__ float sh_s[256 * V];
+  __shared__ float sh_q[256 * V];
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int cv = C / V;
+  const int rows_par = 256 / cv;
+  const int col = threadIdx.x % cv, r = threadIdx.x / cv;
+  const int c0 = col * V;
+  const int64_t per = (Pg + nchunk - 1) / nchunk;
+  const int64_t p0 = chunk * per, p1 = (p0 + per < Pg) ? p0 + per : Pg;
+  float s[V], q[V], mu[V], iv[V], sc[V], sf[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    s[i] = 0.f; q[i] = 0.f;
+    mu[i] = mean[(int64_t)g * C + c0 + i]; iv[i] = inv[(int64_t)g * C + c0 + i];
+    sc[i] = scale[(int64_t)g * C + c0 + i]; sf[i] = shift[(int64_t)g * C + c0 + i];
+  }
+  if (r < rows_par) {
+    for (int64_t pl = p0 + r; pl < p1; pl += rows_par) {
+      int64_t p = (int64_t)g * Pg + pl;
+      float v[V], gr[V];
+      VecIO<T>::load(z + p * C + c0, v);
+      load_grad<T, V>(d1, d2, p, c0, gr);
+      int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float u = fmaf(v[k], sc[k], sf[k]);
+        float gg = gr[k] * act_bwd(u, act);
+        if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+        float xh = (v[k] - mu[k]) * iv[k];
+        s[k] += gg; q[k] = fmaf(gg, xh, q[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sh_s[threadIdx.x * V + i] = s[i]; sh_q[threadIdx.x * V + i] = q[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float S = 0.f, Q = 0.f;
+    for (int rr = 0; rr < rows_par; ++rr) {
+      int t = rr * cv + c / V;
+      S += sh_s[t * V + c % V]; Q += sh_q[t * V + c % V];
+    }
+    float* o = ws + ((int64_t)(g * nchunk + chunk) * 2) * C;
+    o[c] = S; o[C + c] = Q;
+  }
+}
+
+__global__ void k_bwd_finalize(const float* __restrict__ ws, int G, int nchunk, int C, double n, float* __restrict__ c1,
+                               float* __restrict__ c2, float* dgamma, float* dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double SB = 0.0, SG = 0.0;
+  for (int g = 0; g < G; ++g) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+      const float* o = ws + ((int64_t)(g * nchunk + k) * 2) * C;
+      S += (double)o[c]; Q += (double)o[C + c];
+    }
+    c1[(int64_t)g * C + c] = (float)(S / n); c2[(int64_t)g * C + c] = (float)(Q / n);
+    SB += S; SG += Q;
+  }
+  dbeta[c] += (float)SB; dgamma[c] += (float)SG;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, GradSrc d1, GradSrc d2, int64_t nvec,
+                                                   int64_t Pg, int G, int HW, int C, int norm,
+                                                   const float* __restrict__ mean, const float* __restrict__ inv,
+                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                   const float* __restrict__ c1, const float* __restrict__ c2, int act,
+                                                   DropKey dk, T* __restrict__ dz) {
+  constexpr int V = VecIO<T>::N;
+  const int cv = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / cv; int c0 = (int)(i - p * cv) * V;
+    float v[V], gr[V], o[V];
+    VecIO<T>::load(z + p * C + c0, v);
+    load_grad<T, V>(d1, d2, p, c0, gr);
+    if (norm == NORM_NONE) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] = gr[k] * act_bwd(v[k], act);
+    } else {
+      int64_t gi = ((G == 1) ? 0 : (p / Pg)) * C + c0;
+      int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float sc = __ldg(scale + gi + k);
+        float u = fmaf(v[k], sc, __ldg(shift + gi + k));
+        float gg = gr[k] * act_bwd(u, act);
+        if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+        float xh = (v[k] - __ldg(mean + gi + k)) * __ldg(inv + gi + k);
+        o[k] = sc * (gg - __ldg(c1 + gi + k) - xh * __ldg(c2 + gi + k));
+      }
+    }
+    VecIO<T>::store(dz + p * C + c0, o);
+  }
+}
+
+void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
+                     int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
+                     int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz) {
+  int nchunk = stats_chunks(G, Pg);
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    if (norm != NORM_NONE) {
+      k_bwd_reduce<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, Pg, HW, C, nchunk, mean, inv, scale, shift,
+                                                       act, dk, ws);
+      KLAUNCH(L);
+      k_bwd_finalize<<<(C + 127) / 128, 128, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
+      KLAUNCH(L);
+    }
+    int64_t nvec = P * (C / VecIO<T>::N);
+    k_bwd_apply<T><<<grid_for(nvec, 256), 256, 0, L.s>>>((const T*)z, d1, d2, nvec, Pg, G, HW, C, norm, mean, inv, scale,
+                                                         shift, c1, c2, act, dk, (T*)dz);
+    KLAUNCH(L);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generator head backward (tanh output; L1 term pix2pix.py:181 / cycle_gan.py:167,176).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out, const float* __restrict__ ref, GradSrc d1,
+                                                   GradSrc d2, float l1_coef, int64_t total, int C, T* __restrict__ dz,
+                                                   float* dbias) {
+  __shared__ float sh[8];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // C <= 4
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C; int c = (int)(i - p * C);
+    float o = out[i];
+    float d = 0.f;
+    if (d1.p != nullptr) d += to_f(((const T*)d1.p)[p * d1.pitch + d1.coff + c]);
+    if (d2.p != nullptr) d += to_f(((const T*)d2.p)[p * d2.pitch + d2.coff + c]);
+    if (ref != nullptr) {
+      float df = o - ref[i];
+      d += l1_coef * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+    }
+    float g = d * (1.f - o * o);
+    T gq = from_f<T>(g);
+    dz[i] = gq;
+    float gf = to_f(gq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (c == k) bsum[k] += gf;
+  }
+  for (int k = 0; k < C && k < 4; ++k) {
+    float v = warp_sum(bsum[k]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+      atomicAdd(dbias + k, t);
+    }
+  }
+}
+void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
+                      float l1_coef, int64_t P, int C, void* dz, float* dbias) {
+  GAN_REQUIRE(C <= 4, "generator head supports up to 4 output channels");
+  int64_t total = P * C;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_ghead_bwd<T><<<grid_for(total, 256, 4), 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dbias);
+  });
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Losses.  Each loss kernel writes one fp32 partial per block into loss_ws[slot][blockIdx.x];
+// k_loss_finalize sums the partials in double and mixes them into the reported scalars.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_partial_store(float v, float* dst) {
+  __shared__ float sh[8];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    *dst = t;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_t n, float label, float coef_over_n,
+                                             T* dz, float* dbias, float* __restrict__ loss_slot) {
+  float acc = 0.f, bacc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    acc += fmaxf(v, 0.f) - v * label + log1pf(expf(-fabsf(v)));
+    if (dz != nullptr) {
+      float sg = 1.f / (1.f + expf(-v));
+      T q = from_f<T>(coef_over_n * (sg - label));
+      dz[i] = q;
+      bacc += to_f(q);
+    }
+  }
+  block_partial_store(acc, loss_slot + blockIdx.x);
+  if (dz != nullptr && dbias != nullptr) {
+    __syncthreads();
+    __shared__ float shb[8];
+    float v = warp_sum(bacc);
+    if ((threadIdx.x & 31) == 0) shb[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += shb[w];
+      atomicAdd(dbias, t);
+    }
+  }
+}
+void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, float* dbias,
+                float* loss_ws, int slot) {
+  int blocks = grid_for(n, 256, 1);
+  if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dbias, loss_ws + slot * LOSS_BLOCKS);
+  });
+  KLAUNCH(L);
+}
+
+__global__ void __launch_bounds__(256) k_l1(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                            float* __restrict__ loss_slot) {
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += fabsf(a[i] - b[i]);
+  block_partial_store(acc, loss_slot + blockIdx.x);
+}
+void launch_l1(Launch L, const float* a, const float* b, int64_t n, float* loss_ws, int slot) {
+  int blocks = grid_for(n, 256 * 8, 2);
+  if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+  k_l1<<<blocks, 256, 0, L.s>>>(a, b, n, loss_ws + slot * LOSS_BLOCKS);
+  KLAUNCH(L);
+}
+
+__global__ void k_loss_finalize(const float* __restrict__ ws, LossMix mix, float* __restrict__ out) {
+  __shared__ double raw[LOSS_SLOTS];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < mix.nraw) {
+    double s = 0.0;
+    for (int i = lane; i < LOSS_BLOCKS; i += 32) s += (double)ws[w * LOSS_BLOCKS + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) raw[w] = s / (double)mix.denom[w];
+  }
+  __syncthreads();
+  if (threadIdx.x < mix.nout) {
+    double v = 0.0;
+    for (int j = 0; j < mix.nraw; ++j) v += (double)mix.mix[threadIdx.x * mix.nraw + j] * raw[j];
+    out[threadIdx.x] = (float)v;
+  }
+}
+void launch_loss_finalize(Launch L, const float* loss_ws, LossMix mix, float* out) {
+  k_loss_finalize<<<1, 32 * LOSS_SLOTS, 0, L.s>>>(loss_ws, mix, out);
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras Adam: m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= lr_t*m/(sqrt(v)+eps)
+// One launch per network over the flat parameter buffer: 28 B/param of HBM traffic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, int64_t n4, int64_t n, float lr_t, float b1, float b2,
+                                              float eps, float gscale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], Gr = reinterpret_cast<const float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    float* pp = &P.x; float* gg = &Gr.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = gg[k] * gscale;
+      mm[k] += (gr - mm[k]) * (1.f - b1);
+      vv[k] += (gr * gr - vv[k]) * (1.f - b2);
+      pp[k] -= lr_t * mm[k] / (sqrtf(vv[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
+  }
+  // tail (n not a multiple of 4)
+  int64_t t = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) {
+    float gr = g[t] * gscale;
+    m[t] += (gr - m[t]) * (1.f - b1);
+    v[t] += (gr * gr - v[t]) * (1.f - b2);
+    p[t] -= lr_t * m[t] / (sqrtf(v[t]) + eps);
+  }
+}
+void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
+                 float eps, float gscale) {
+  int64_t n4 = n / 4;
+  k_adam<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, L.s>>>(p, g, m, v, n4, n, lr_t, b1, b2, eps, gscale);
+  KLAUNCH(L);
+}
+
+__global__ void k_scale(float* p, int64_t n, float s) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] *= s;
+}
+void launch_scale(Launch L, float* p, int64_t n, float s) {
+  k_scale<<<grid_for(n, 256), 256, 0, L.s>>>(p, n, s);
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: fp32 master (TF layout) -> [class][Nc][tap*Kc + kc] in the activation dtype.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack(const float* __restrict__ master, T* __restrict__ dst, PackOp op) {
+  const ClassGeom& cg = op.cls[blockIdx.y];
+  const int64_t K = (int64_t)cg.ntaps * op.Kc;
+  const int64_t total = K * op.Nc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = i / K; int64_t k = i - n * K;
+    int t = (int)(k / op.Kc); int kc = (int)(k - (int64_t)t * op.Kc);
+    dst[cg.b_off + i] = from_f<T>(master[(int64_t)cg.widx[t] * op.s_tap + (int64_t)kc * op.s_k + n * op.s_n]);
+  }
+}
+void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op) {
+  int64_t total = (int64_t)op.cls[0].ntaps * op.Kc * op.Nc;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_pack<T><<<dim3(grid_for(total, 256, 4), op.ncls), 256, 0, L.s>>>(master, (T*)dst, op);
+  });
+  KLAUNCH(L);
+}

@@ -1,0 +1,984 @@
+// engine.cu — host orchestration of the GAN train step and the C-ABI (include/gan_b200.h).
+//
+// Restates, as kernel launch sequences on one CUDA stream:
+//   GAN.Generator / GAN.Discriminator forward ........ base_gan.py:124-225
+//   Pix2Pix.train_step ................................ pix2pix.py:190-218
+//   CycleGAN.train_step ............................... cycle_gan.py:206-276
+// Autodiff (tf.GradientTape) is replaced by hand-derived backward sweeps over the saved raw
+// convolution outputs ("z") and normalisation statistics of each forward call (a Slot).
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include "engine.h"
+#include "../../include/gan_b200.h"
+
+static thread_local std::string g_last_error;
+
+#define API_BEGIN try {
+#define API_END                                                              \
+  return GAN_OK;                                                             \
+  } catch (const GanError& e) { g_last_error = e.what(); return e.code; }    \
+  catch (const std::exception& e) { g_last_error = e.what(); return GAN_ERR_INVALID; }
+
+static const int DOWN_F[8] = {64, 128, 256, 512, 512, 512, 512, 512};   // base_gan.py:179-188
+static const int UP_F[7] = {512, 512, 512, 512, 256, 128, 64};          // base_gan.py:190-198
+#define BN_EPS 1e-3f
+#define IN_EPS 1e-5f
+#define BN_MOMENTUM 0.99f
+
+enum { R_FWD = 0, R_DGRAD = 1, R_WGRAD = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Tap geometry (oracle/direct.py CONVT_TAPS)
+// ---------------------------------------------------------------------------------------------
+static ClassGeom geom_conv16(int sign) {
+  ClassGeom g; memset(&g, 0, sizeof(g));
+  g.ntaps = 16;
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      int t = kh * 4 + kw;
+      g.dh[t] = (int8_t)(sign * (kh - 1)); g.dw[t] = (int8_t)(sign * (kw - 1)); g.widx[t] = (int8_t)t;
+    }
+  return g;
+}
+static void geom_convT4(ClassGeom* cls) {
+  static const int KH_T[2][2] = {{1, 3}, {0, 2}};
+  static const int DH_T[2][2] = {{0, -1}, {1, 0}};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      ClassGeom g; memset(&g, 0, sizeof(g));
+      g.oa = a; g.ob = b; g.ntaps = 4;
+      for (int th = 0; th < 2; ++th)
+        for (int tw = 0; tw < 2; ++tw) {
+          int t = th * 2 + tw;
+          g.dh[t] = (int8_t)DH_T[a][th]; g.dw[t] = (int8_t)DH_T[b][tw];
+          g.widx[t] = (int8_t)(KH_T[a][th] * 4 + KH_T[b][tw]);
+        }
+      cls[a * 2 + b] = g;
+    }
+}
+static int fill_geometry(int kind, int role, ClassGeom* cls) {
+  bool conv_form = (kind != K_CONVT_S2 && role != R_DGRAD) || (kind == K_CONVT_S2 && role == R_DGRAD) ||
+                   (kind == K_CONV_S1P);
+  if (conv_form) { cls[0] = geom_conv16((kind == K_CONV_S1P && role == R_DGRAD) ? -1 : 1); return 1; }
+  geom_convT4(cls);
+  return 4;
+}
+
+// Master-weight strides for (tap, K-channel, N-channel) of a role.
+static void weight_strides(const Layer& ly, int role, int& Kc, int& Nc, int64_t& s_tap, int64_t& s_k, int64_t& s_n) {
+  s_tap = (int64_t)ly.Cin * ly.Cout;
+  bool transposed_master = (ly.kind == K_CONVT_S2);   // (kh,kw,out,in) instead of (kh,kw,in,out)
+  int64_t s_in = transposed_master ? 1 : ly.Cout, s_out = transposed_master ? ly.Cin : 1;
+  if (role == R_DGRAD) { Kc = ly.Cout; Nc = ly.Cin; s_k = s_out; s_n = s_in; }
+  else { Kc = ly.Cin; Nc = ly.Cout; s_k = s_in; s_n = s_out; }
+}
+
+// x: layer-input-side view (N,Hin,Win,Cin); y: layer-output-side view (N,Hout,Wout,Cout).
+static ConvOp make_op(const Layer& ly, int role, View x, View y, const void* wpack) {
+  ConvOp op; memset(&op, 0, sizeof(op));
+  op.ncls = fill_geometry(ly.kind, role, op.cls);
+  weight_strides(ly, role, op.Kc, op.Nc, op.s_tap, op.s_k, op.s_n);
+  View src = (role == R_DGRAD) ? y : x, dst = (role == R_DGRAD) ? x : y;
+  op.in = src.p; op.in_pitch = src.pitch; op.in_coff = src.coff; op.Hin = src.H; op.Win = src.W;
+  op.out = dst.p; op.out_pitch = dst.pitch; op.out_coff = dst.coff; op.Hout = dst.H; op.Wout = dst.W;
+  op.N = x.N;
+  if (role != R_DGRAD) {
+    if (ly.kind == K_CONVT_S2) { op.Hm = x.H; op.Wm = x.W; op.si = 1; op.so = 2; }
+    else { op.Hm = y.H; op.Wm = y.W; op.si = (ly.kind == K_CONV_S2) ? 2 : 1; op.so = 1; }
+  } else {
+    if (ly.kind == K_CONV_S2) { op.Hm = y.H; op.Wm = y.W; op.si = 1; op.so = 2; }
+    else if (ly.kind == K_CONV_S1P) { op.Hm = x.H; op.Wm = x.W; op.si = 1; op.so = 1; }
+    else { op.Hm = x.H; op.Wm = x.W; op.si = 2; op.so = 1; }
+  }
+  for (int c = 0; c < op.ncls; ++c) op.cls[c].b_off = (int64_t)c * op.Nc * op.cls[c].ntaps * op.Kc;
+  op.B = wpack;
+  return op;
+}
+
+static void out_dims(int kind, int Hin, int Win, int& Ho, int& Wo) {
+  if (kind == K_CONV_S2) { Ho = Hin / 2; Wo = Win / 2; }
+  else if (kind == K_CONV_S1P) { Ho = Hin - 1; Wo = Win - 1; }
+  else { Ho = Hin * 2; Wo = Win * 2; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv dispatch: tcgen05 where the op fits (bf16 mode), FFMA otherwise
+// ---------------------------------------------------------------------------------------------
+static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op) {
+  bool can = ctx->dt == DT_BF16 && umma_fwd_supported(op);
+  if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
+  if (can && ctx->engine != GAN_ENGINE_FFMA) launch_conv_fwd_umma(ctx->L(), op);
+  else launch_conv_fwd_ffma(ctx->L(), ctx->dt, op);
+}
+static void run_conv_wgrad(gan_ctx* ctx, const ConvOp& op) {
+  bool can = ctx->dt == DT_BF16 && umma_wgrad_supported(op);
+  if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
+  if (can && ctx->engine != GAN_ENGINE_FFMA) launch_conv_wgrad_umma(ctx->L(), op);
+  else launch_conv_wgrad_ffma(ctx->L(), ctx->dt, op);
+}
+
+// ---------------------------------------------------------------------------------------------
+// net construction
+// ---------------------------------------------------------------------------------------------
+static void add_tensor(gan_net* n, const std::string& name, std::initializer_list<int64_t> shape, int64_t& off,
+                       bool trainable) {
+  TensorInfo t; t.name = name; t.ndim = (int)shape.size(); t.numel = 1; t.trainable = trainable;
+  int i = 0;
+  for (auto s : shape) { t.shape[i++] = s; t.numel *= s; }
+  for (; i < 4; ++i) t.shape[i] = 1;
+  t.off = off; off += t.numel;
+  n->tensors.push_back(t);
+}
+
+static void add_layer(gan_net* n, const std::string& name, int kind, int Cin, int Cout, int norm, int act, bool bias,
+                      bool dropout, int tag, bool head) {
+  Layer ly; ly.name = name; ly.kind = kind; ly.Cin = Cin; ly.Cout = Cout; ly.norm = norm; ly.act = act;
+  ly.bias = bias; ly.dropout = dropout; ly.tag = tag; ly.head = head;
+  ly.w_off = n->nparams;
+  if (kind == K_CONVT_S2) add_tensor(n, name + ".kernel", {4, 4, Cout, Cin}, n->nparams, true);
+  else add_tensor(n, name + ".kernel", {4, 4, Cin, Cout}, n->nparams, true);
+  if (norm != NORM_NONE) {
+    ly.g_off = n->nparams; add_tensor(n, name + ".gamma", {Cout}, n->nparams, true);
+    ly.b_off = n->nparams; add_tensor(n, name + ".beta", {Cout}, n->nparams, true);
+  }
+  if (bias) { ly.bias_off = n->nparams; add_tensor(n, name + ".bias", {Cout}, n->nparams, true); }
+  n->layers.push_back(std::move(ly));
+}
+
+static void finish_net(gan_net* n) {
+  n->ntrain = (int)n->tensors.size();
+  // BatchNorm moving statistics (non-trainable; bookkeeping only — never read, every call is training=True)
+  if (n->norm == NORM_BATCH)
+    for (auto& ly : n->layers)
+      if (ly.norm != NORM_NONE) {
+        ly.mov_off = n->nmov;
+        add_tensor(n, ly.name + ".moving_mean", {ly.Cout}, n->nmov, false);
+        add_tensor(n, ly.name + ".moving_variance", {ly.Cout}, n->nmov, false);
+      }
+  n->params.ensure((size_t)(n->nparams + 4) * 4);
+  n->grads.ensure((size_t)(n->nparams + 4) * 4);
+  if (n->nmov > 0) {
+    n->mov.ensure((size_t)n->nmov * 4);
+    std::vector<float> init((size_t)n->nmov, 0.f);
+    for (auto& t : n->tensors)
+      if (!t.trainable && t.name.find("moving_variance") != std::string::npos)
+        for (int64_t i = 0; i < t.numel; ++i) init[(size_t)(t.off + i)] = 1.f;
+    CUDA_CHECK(cudaMemcpy(n->mov.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice));
+  }
+  n->slots.resize(3);
+  n->packed_dirty = true;
+}
+
+static void pack_weights(gan_net* n) {
+  if (!n->packed_dirty) return;
+  gan_ctx* ctx = n->ctx;
+  for (auto& ly : n->layers) {
+    for (int role = R_FWD; role <= R_DGRAD; ++role) {
+      if (role == R_DGRAD && !ly.need_dgrad) continue;
+      PackOp po; memset(&po, 0, sizeof(po));
+      po.ncls = fill_geometry(ly.kind, role, po.cls);
+      weight_strides(ly, role, po.Kc, po.Nc, po.s_tap, po.s_k, po.s_n);
+      for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
+      DevBuf& dst = role == R_FWD ? ly.wp_fwd : ly.wp_dgrad;
+      dst.ensure((size_t)16 * ly.Cin * ly.Cout * ctx->esize());
+      launch_pack(ctx->L(), ctx->dt, n->params.as<float>() + ly.w_off, dst.p, po);
+    }
+  }
+  n->packed_dirty = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one conv(+norm+act) layer, forward and backward
+// ---------------------------------------------------------------------------------------------
+static DropKey drop_key(gan_ctx* ctx, const Layer& ly, const Slot& s) {
+  DropKey k;
+  k.seed_lo = (uint32_t)(ctx->seed & 0xffffffffu); k.seed_hi = (uint32_t)(ctx->seed >> 32);
+  k.call = s.call_id; k.layer = (uint32_t)ly.tag; k.sample0 = s.sample0;
+  k.enabled = (ly.dropout && ctx->dropout_enabled) ? 1 : 0;
+  return k;
+}
+
+static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
+  gan_ctx* ctx = n->ctx;
+  Layer& ly = n->layers[li];
+  int Ho, Wo; out_dims(ly.kind, in.H, in.W, Ho, Wo);
+  const int B = in.N;
+  s.in_views[li] = in; s.out_views[li] = out;
+  if (ly.head) {
+    // generator head: bias + tanh -> fp32 image; discriminator head: bias -> fp32 logits
+    View y = make_view(nullptr, B, Ho, Wo, ly.Cout);
+    ConvOp op = make_op(ly, R_FWD, in, y, ly.wp_fwd.p);
+    op.bias = n->params.as<float>() + ly.bias_off;
+    op.epi = ly.act == ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS;
+    op.out_f32 = (float*)out.p;
+    launch_conv_fwd_ffma(ctx->L(), ctx->dt, op);
+    return;
+  }
+  int64_t P = (int64_t)B * Ho * Wo;
+  s.z[li].ensure((size_t)P * ly.Cout * ctx->esize());
+  View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
+  run_conv_fwd(ctx, make_op(ly, R_FWD, in, z, ly.wp_fwd.p));
+  DropKey dk = drop_key(ctx, ly, s);
+  if (ly.norm == NORM_NONE) {
+    launch_norm_apply(ctx->L(), ctx->dt, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, ly.act, dk, out.p,
+                      out.pitch, out.coff);
+    return;
+  }
+  const int G = ly.norm == NORM_BATCH ? 1 : B;
+  const int64_t Pg = P / G;
+  const size_t gc = (size_t)G * ly.Cout;
+  s.stats[li].ensure(gc * 6 * 4);
+  float* st = s.stats[li].as<float>();
+  ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
+  float* pr = n->params.as<float>();
+  float* mm = (ly.mov_off >= 0) ? n->mov.as<float>() + ly.mov_off : nullptr;
+  launch_norm_stats(ctx->L(), ctx->dt, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(),
+                    ly.norm == NORM_BATCH ? BN_EPS : IN_EPS, pr + ly.g_off, pr + ly.b_off, st, st + gc, st + 2 * gc,
+                    st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
+  launch_norm_apply(ctx->L(), ctx->dt, z.p, P, Pg, G, Ho * Wo, ly.Cout, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
+                    out.pitch, out.coff);
+}
+
+// d1/d2: gradient w.r.t. the layer's activated output.  din: where the gradient w.r.t. the layer
+// input goes (p == nullptr: not needed).  For head layers d1 is dz itself (already in d1.p, compact).
+static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, View din, bool want_wgrad) {
+  gan_ctx* ctx = n->ctx;
+  Layer& ly = n->layers[li];
+  View in = s.in_views[li];
+  int Ho, Wo; out_dims(ly.kind, in.H, in.W, Ho, Wo);
+  const int B = in.N;
+  const int64_t P = (int64_t)B * Ho * Wo;
+  View dz;
+  if (ly.head) {
+    dz = make_view((void*)d1.p, B, Ho, Wo, ly.Cout, d1.pitch, d1.coff);
+  } else {
+    ctx->dz_scratch.ensure((size_t)P * ly.Cout * ctx->esize());
+    dz = make_view(ctx->dz_scratch.p, B, Ho, Wo, ly.Cout);
+    const int G = ly.norm == NORM_BATCH ? 1 : (ly.norm == NORM_INSTANCE ? B : 1);
+    const int64_t Pg = P / G;
+    const size_t gc = (size_t)G * ly.Cout;
+    float* st = ly.norm != NORM_NONE ? s.stats[li].as<float>() : nullptr;
+    float* gr = want_wgrad ? n->grads.as<float>() : nullptr;
+    ctx->junk.ensure(2048 * 4);
+    float* dgamma = (gr && ly.norm != NORM_NONE) ? gr + ly.g_off : ctx->junk.as<float>();
+    float* dbeta = (gr && ly.norm != NORM_NONE) ? gr + ly.b_off : ctx->junk.as<float>() + 1024;
+    if (ly.norm != NORM_NONE) ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
+    launch_norm_bwd(ctx->L(), ctx->dt, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
+                    st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
+                    ctx->stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
+  }
+  if (want_wgrad) {
+    ConvOp op = make_op(ly, R_WGRAD, in, dz, nullptr);
+    op.dW = n->grads.as<float>() + ly.w_off;
+    run_conv_wgrad(ctx, op);
+  }
+  if (din.p != nullptr) {
+    GAN_REQUIRE(ly.need_dgrad, "dgrad weights not packed");
+    run_conv_fwd(ctx, make_op(ly, R_DGRAD, din, dz, ly.wp_dgrad.p));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generator / discriminator sweeps
+// ---------------------------------------------------------------------------------------------
+static void slot_prepare(gan_net* n, Slot& s, int B, int H, int W) {
+  size_t nl = n->layers.size();
+  if (s.z.size() != nl) {
+    s.z.resize(nl); s.stats.resize(nl); s.in_views.resize(nl); s.out_views.resize(nl);
+    if (n->is_gen) { s.cat.resize(7); s.dcat.resize(7); s.dskip.resize(8); }
+    else { s.act.resize(4); s.dact.resize(4); }
+  }
+  s.B = B; s.H = H; s.W = W;
+}
+
+// x_f32: device fp32 (B,H,W,C).  Output: s.out_f32 (B,H,W,C) fp32.
+static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, int H, int W) {
+  gan_ctx* ctx = g->ctx;
+  GAN_REQUIRE(H % 256 == 0 && W % 256 == 0 && H >= 256 && W >= 256, "generator needs H,W multiples of 256");
+  pack_weights(g);
+  Slot& s = g->slots[slot];
+  slot_prepare(g, s, B, H, W);
+  s.call_id = ctx->call_counter++;
+  s.sample0 = ctx->sample0_set ? ctx->sample0 : (int64_t)ctx->rank * B;
+  const size_t es = ctx->esize();
+  const int C = g->C;
+  s.xin.ensure((size_t)B * H * W * C * es);
+  launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, C, 0);
+  // concat buffers: cat[k-1] = [up_k output (UP_F[k-1]) | down_{8-k} output (DOWN_F[7-k])] at H/2^(8-k)
+  for (int k = 1; k <= 7; ++k) {
+    int hs = H >> (8 - k), ws = W >> (8 - k);
+    s.cat[k - 1].ensure((size_t)B * hs * ws * (UP_F[k - 1] + DOWN_F[7 - k]) * es);
+  }
+  s.d8.ensure((size_t)B * (H >> 8) * (W >> 8) * 512 * es);
+  View in = make_view(s.xin.p, B, H, W, C);
+  for (int j = 1; j <= 8; ++j) {
+    int hs = H >> j, ws = W >> j;
+    View out;
+    if (j < 8) { int k = 8 - j; out = make_view(s.cat[k - 1].p, B, hs, ws, DOWN_F[j - 1], UP_F[k - 1] + DOWN_F[j - 1], UP_F[k - 1]); }
+    else out = make_view(s.d8.p, B, hs, ws, 512);
+    layer_forward(g, s, j - 1, in, out);
+    in = out;
+  }
+  for (int k = 1; k <= 7; ++k) {
+    int hs = H >> (8 - k), ws = W >> (8 - k);
+    int pitch = UP_F[k - 1] + DOWN_F[7 - k];
+    View out = make_view(s.cat[k - 1].p, B, hs, ws, UP_F[k - 1], pitch, 0);
+    layer_forward(g, s, 7 + k, in, out);
+    in = make_view(s.cat[k - 1].p, B, hs, ws, pitch, pitch, 0);     // Concatenate([x, skip]) base_gan.py:221
+  }
+  s.out_f32.ensure((size_t)B * H * W * C * 4);
+  layer_forward(g, s, 15, in, make_view(s.out_f32.p, B, H, W, C));
+}
+
+// Backward through one generator call.  d1/d2: extra gradient sources w.r.t. the tanh output
+// (activation dtype); ref/l1_coef: + l1_coef*sign(out-ref).  Accumulates into g->grads.
+static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, const float* ref_f32, float l1_coef,
+                               bool want_input_grad) {
+  gan_ctx* ctx = g->ctx;
+  Slot& s = g->slots[slot];
+  const int B = s.B, H = s.H, W = s.W, C = g->C;
+  const size_t es = ctx->esize();
+  float* gr = g->grads.as<float>();
+  // head
+  s.dlogit.ensure((size_t)B * H * W * C * es);
+  launch_ghead_bwd(ctx->L(), ctx->dt, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p,
+                   gr + g->layers[15].bias_off);
+  for (int k = 1; k <= 7; ++k) {
+    int hs = H >> (8 - k), ws = W >> (8 - k);
+    s.dcat[k - 1].ensure((size_t)B * hs * ws * (UP_F[k - 1] + DOWN_F[7 - k]) * es);
+  }
+  {
+    int pitch = UP_F[6] + DOWN_F[0];
+    View din = make_view(s.dcat[6].p, B, H / 2, W / 2, pitch);
+    layer_backward(g, s, 15, GradSrc{s.dlogit.p, C, 0}, GradSrc{nullptr, 0, 0}, din, true);
+  }
+  s.dd8.ensure((size_t)B * (H >> 8) * (W >> 8) * 512 * es);
+  for (int k = 7; k >= 1; --k) {
+    int pitch = UP_F[k - 1] + DOWN_F[7 - k];
+    GradSrc src{s.dcat[k - 1].p, pitch, 0};
+    View din;
+    if (k == 1) din = make_view(s.dd8.p, B, H >> 8, W >> 8, 512);
+    else { int pp = UP_F[k - 2] + DOWN_F[8 - k]; din = make_view(s.dcat[k - 2].p, B, H >> (9 - k), W >> (9 - k), pp); }
+    layer_backward(g, s, 7 + k, src, GradSrc{nullptr, 0, 0}, din, true);
+  }
+  for (int j = 8; j >= 1; --j) {
+    GradSrc a, b{nullptr, 0, 0};
+    if (j == 8) a = GradSrc{s.dd8.p, 512, 0};
+    else {
+      int k = 8 - j;
+      a = GradSrc{s.dskip[j].p, DOWN_F[j - 1], 0};                              // from down_{j+1} dgrad
+      b = GradSrc{s.dcat[k - 1].p, UP_F[k - 1] + DOWN_F[j - 1], UP_F[k - 1]};   // skip half of the concat gradient
+    }
+    View din = make_view(nullptr, B, H >> (j - 1), W >> (j - 1), j > 1 ? DOWN_F[j - 2] : C);
+    if (j > 1) {
+      s.dskip[j - 1].ensure((size_t)B * din.H * din.W * din.C * es);
+      din.p = s.dskip[j - 1].p;
+    } else if (want_input_grad) {
+      s.dxin.ensure((size_t)B * H * W * C * es);
+      din.p = s.dxin.p;
+    }
+    layer_backward(g, s, j - 1, a, b, din, true);
+  }
+}
+
+// inp/tar: device fp32 (B,H,W,C); tar may be nullptr when target == false.
+static void discriminator_forward(gan_net* d, int slot, const float* inp, const float* tar, int B, int H, int W) {
+  gan_ctx* ctx = d->ctx;
+  GAN_REQUIRE(H % 8 == 0 && W % 8 == 0 && H >= 32 && W >= 32, "discriminator needs H,W multiples of 8");
+  GAN_REQUIRE((tar != nullptr) == d->target, "discriminator target input mismatch");
+  pack_weights(d);
+  Slot& s = d->slots[slot];
+  slot_prepare(d, s, B, H, W);
+  const size_t es = ctx->esize();
+  const int C = d->C, C0 = d->Cin0;
+  s.in0.ensure((size_t)B * H * W * C0 * es);
+  launch_convert(ctx->L(), ctx->dt, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
+  if (tar) launch_convert(ctx->L(), ctx->dt, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
+  View in = make_view(s.in0.p, B, H, W, C0);
+  int h = H, w = W;
+  for (int li = 0; li < 4; ++li) {
+    int ho, wo; out_dims(d->layers[li].kind, h, w, ho, wo);
+    s.act[li].ensure((size_t)B * ho * wo * d->layers[li].Cout * es);
+    View out = make_view(s.act[li].p, B, ho, wo, d->layers[li].Cout);
+    layer_forward(d, s, li, in, out);
+    in = out; h = ho; w = wo;
+  }
+  s.logits.ensure((size_t)B * (h - 1) * (w - 1) * 4);
+  layer_forward(d, s, 4, in, make_view(s.logits.p, B, h - 1, w - 1, 1));
+}
+
+// Backward from s.dlogit (already filled).  want_wgrad: accumulate into d->grads.
+static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool want_input_grad) {
+  gan_ctx* ctx = d->ctx;
+  Slot& s = d->slots[slot];
+  const size_t es = ctx->esize();
+  const int B = s.B;
+  for (int li = 4; li >= 0; --li) {
+    View in = s.in_views[li];
+    View din = make_view(nullptr, B, in.H, in.W, in.C);
+    if (li > 0) { s.dact[li - 1].ensure((size_t)B * in.H * in.W * in.C * es); din.p = s.dact[li - 1].p; }
+    else if (want_input_grad) { s.din0.ensure((size_t)B * in.H * in.W * in.C * es); din.p = s.din0.p; }
+    GradSrc src = (li == 4) ? GradSrc{s.dlogit.p, 1, 0} : GradSrc{s.dact[li].p, d->layers[li].Cout, 0};
+    layer_backward(d, s, li, src, GradSrc{nullptr, 0, 0}, din, want_wgrad);
+  }
+}
+
+static int64_t logits_count(const Slot& s) { return (int64_t)s.B * (s.H / 8 - 2) * (s.W / 8 - 2); }
+
+// BCE on a discriminator call's logits: loss partial into `slot_idx`; when dz: s.dlogit = coef*(sigmoid-label)/n
+static void disc_bce(gan_net* d, int slot, float label, float coef, bool make_dz, bool bias_grad, int loss_slot) {
+  gan_ctx* ctx = d->ctx;
+  Slot& s = d->slots[slot];
+  int64_t n = logits_count(s);
+  if (make_dz) s.dlogit.ensure((size_t)n * ctx->esize());
+  launch_bce(ctx->L(), ctx->dt, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr,
+             (make_dz && bias_grad) ? d->grads.as<float>() + d->layers[4].bias_off : nullptr, ctx->loss_ws.as<float>(),
+             loss_slot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers: staging of caller buffers, adam, all-reduce
+// ---------------------------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+static const float* stage_in(gan_ctx* ctx, int idx, const float* p, size_t bytes) {
+  if (is_device_ptr(p)) return p;
+  ctx->stage[idx].ensure(bytes);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->stage[idx].p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return ctx->stage[idx].as<float>();
+}
+static void copy_out(gan_ctx* ctx, float* dst, const float* src_dev, size_t bytes) {
+  if (is_device_ptr(dst)) CUDA_CHECK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  else {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+static void zero_grads(gan_net* n) {
+  CUDA_CHECK(cudaMemsetAsync(n->grads.p, 0, (size_t)n->nparams * 4, n->ctx->stream));
+}
+static void adam_apply(gan_adam* o) {
+  gan_net* n = o->net; gan_ctx* ctx = n->ctx;
+  if (ctx->world > 1) comm_allreduce_sum(ctx, n->grads.as<float>(), n->nparams);
+  o->t += 1;
+  double lr_t = o->lr * std::sqrt(1.0 - std::pow(o->b2, (double)o->t)) / (1.0 - std::pow(o->b1, (double)o->t));
+  launch_adam(ctx->L(), n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), n->nparams,
+              (float)lr_t, (float)o->b1, (float)o->b2, (float)o->eps, 1.f / (float)ctx->world);
+  n->packed_dirty = true;
+  pack_weights(n);
+}
+static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {
+  ctx->loss_out.ensure(16 * 4);
+  launch_loss_finalize(ctx->L(), ctx->loss_ws.as<float>(), mix, ctx->loss_out.as<float>());
+  if (ctx->world > 1) {
+    comm_allreduce_sum(ctx, ctx->loss_out.as<float>(), mix.nout);
+    launch_scale(ctx->L(), ctx->loss_out.as<float>(), mix.nout, 1.f / (float)ctx->world);
+  }
+  ctx->n_losses = mix.nout;
+  CUDA_CHECK(cudaMemcpyAsync(ctx->loss_host, ctx->loss_out.p, mix.nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (losses_host) {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(losses_host, ctx->loss_host, mix.nout * 4);
+  }
+}
+static void loss_ws_reset(gan_ctx* ctx) {
+  ctx->loss_ws.ensure((size_t)LOSS_SLOTS * LOSS_BLOCKS * 4);
+  CUDA_CHECK(cudaMemsetAsync(ctx->loss_ws.p, 0, (size_t)LOSS_SLOTS * LOSS_BLOCKS * 4, ctx->stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pix2Pix.train_step (pix2pix.py:190-218)
+// ---------------------------------------------------------------------------------------------
+static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, const float* x_in, const float* y_in, int B,
+                         float lambda, int training, float* losses) {
+  gan_ctx* ctx = g->ctx;
+  GAN_REQUIRE(d->ctx == ctx, "nets belong to different contexts");
+  GAN_REQUIRE(g->is_gen && !d->is_gen && d->target, "pix2pix needs a generator and a target=True discriminator");
+  GAN_REQUIRE(B >= 1, "batch must be >= 1");
+  const int H = g->H, W = g->W, C = g->C;
+  const size_t img_bytes = (size_t)B * H * W * C * 4;
+  const float* x = stage_in(ctx, 0, x_in, img_bytes);
+  const float* y = stage_in(ctx, 1, y_in, img_bytes);
+  loss_ws_reset(ctx);
+  if (training) { zero_grads(g); zero_grads(d); }
+
+  generator_forward(g, 0, x, B, H, W);                                   // gen_output           (:200)
+  const float* gen_out = g->slots[0].out_f32.as<float>();
+  discriminator_forward(d, 0, x, y, B, H, W);                            // disc_real_output     (:202)
+  discriminator_forward(d, 1, x, gen_out, B, H, W);                      // disc_generated_output(:203)
+
+  const int64_t n_img = (int64_t)B * H * W * C;
+  launch_l1(ctx->L(), y, gen_out, n_img, ctx->loss_ws.as<float>(), 1);   // gan_loss2 = mean|target-gen_output| (:181)
+  // raw slots: 0 BCE(1,fake)  1 L1  2 BCE(1,real)  3 BCE(0,fake)
+  disc_bce(d, 0, 1.f, 0.5f, training, true, 2);
+  if (training) discriminator_backward(d, 0, true, false);
+  disc_bce(d, 1, 0.f, 0.5f, training, true, 3);
+  if (training) discriminator_backward(d, 1, true, false);
+  disc_bce(d, 1, 1.f, 1.0f, training, false, 0);
+  if (training) {
+    discriminator_backward(d, 1, false, true);                           // dL_G/d(gen_output) through D (:210)
+    GradSrc dgan{d->slots[1].din0.p, 2 * C, C};
+    generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, lambda / (float)n_img, false);
+    adam_apply(go);                                                      // (:213)
+    adam_apply(dopt);                                                    // (:215)
+  }
+  LossMix mix; memset(&mix, 0, sizeof(mix));
+  mix.nraw = 4; mix.nout = 4;
+  const float nlog = (float)logits_count(d->slots[0]);
+  mix.denom[0] = nlog; mix.denom[1] = (float)n_img; mix.denom[2] = nlog; mix.denom[3] = nlog;
+  auto M = [&](int i, int j) -> float& { return mix.mix[i * mix.nraw + j]; };
+  M(0, 0) = 1.f; M(0, 1) = lambda;        // gen_total_loss = gan_loss + lambda*l1   (:186)
+  M(1, 0) = 1.f;                          // gen_gan_loss
+  M(2, 1) = 1.f;                          // gen_gan_loss2 (L1)
+  M(3, 2) = 0.5f; M(3, 3) = 0.5f;         // disc_loss = (real+generated)*0.5         (:206)
+  finish_losses(ctx, mix, losses);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CycleGAN.train_step (cycle_gan.py:206-276), single backward sweep
+// ---------------------------------------------------------------------------------------------
+static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_adam* og, gan_adam* of, gan_adam* odx,
+                          gan_adam* ody, const float* x_in, const float* y_in, int B, float lambda, int training,
+                          float* losses) {
+  gan_ctx* ctx = g->ctx;
+  GAN_REQUIRE(g->is_gen && f->is_gen && !dx->is_gen && !dy->is_gen && !dx->target && !dy->target,
+              "cyclegan needs two generators and two target=False discriminators");
+  GAN_REQUIRE(B >= 1, "batch must be >= 1");
+  const int C = g->C;
+  int H = g->H, W = g->W;
+  const size_t img_bytes = (size_t)B * H * W * C * 4;
+  const float* x = stage_in(ctx, 0, x_in, img_bytes);
+  const float* y = stage_in(ctx, 1, y_in, img_bytes);
+  loss_ws_reset(ctx);
+  if (training) { zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy); }
+  for (gan_net* n : {g, f}) for (auto& ly : n->layers) ly.need_dgrad = true;
+
+  generator_forward(g, 0, x, B, H, W);  const float* fake_y = g->slots[0].out_f32.as<float>();     // (:220)
+  generator_forward(f, 0, fake_y, B, H, W); const float* cycled_x = f->slots[0].out_f32.as<float>(); // (:221)
+  generator_forward(f, 1, y, B, H, W);  const float* fake_x = f->slots[1].out_f32.as<float>();     // (:223)
+  generator_forward(g, 1, fake_x, B, H, W); const float* cycled_y = g->slots[1].out_f32.as<float>(); // (:224)
+  generator_forward(f, 2, x, B, H, W);  const float* same_x = f->slots[2].out_f32.as<float>();     // (:227)
+  generator_forward(g, 2, y, B, H, W);  const float* same_y = g->slots[2].out_f32.as<float>();     // (:228)
+  discriminator_forward(dx, 0, x, nullptr, B, H, W);        // disc_real_x (:230)
+  discriminator_forward(dy, 0, y, nullptr, B, H, W);        // disc_real_y (:231)
+  discriminator_forward(dx, 1, fake_x, nullptr, B, H, W);   // disc_fake_x (:233)
+  discriminator_forward(dy, 1, fake_y, nullptr, B, H, W);   // disc_fake_y (:234)
+
+  const int64_t n_img = (int64_t)B * H * W * C;
+  float* lw = ctx->loss_ws.as<float>();
+  // raw: 0 BCE(1,fake_y) 1 BCE(1,fake_x) 2 L1(x,cyc_x) 3 L1(y,cyc_y) 4 L1(y,same_y) 5 L1(x,same_x)
+  //      6 BCE(1,real_x) 7 BCE(0,fake_x) 8 BCE(1,real_y) 9 BCE(0,fake_y)
+  launch_l1(ctx->L(), x, cycled_x, n_img, lw, 2);
+  launch_l1(ctx->L(), y, cycled_y, n_img, lw, 3);
+  launch_l1(ctx->L(), y, same_y, n_img, lw, 4);
+  launch_l1(ctx->L(), x, same_x, n_img, lw, 5);
+  disc_bce(dx, 0, 1.f, 0.5f, training, true, 6); if (training) discriminator_backward(dx, 0, true, false);
+  disc_bce(dx, 1, 0.f, 0.5f, training, true, 7); if (training) discriminator_backward(dx, 1, true, false);
+  disc_bce(dy, 0, 1.f, 0.5f, training, true, 8); if (training) discriminator_backward(dy, 0, true, false);
+  disc_bce(dy, 1, 0.f, 0.5f, training, true, 9); if (training) discriminator_backward(dy, 1, true, false);
+  disc_bce(dy, 1, 1.f, 1.0f, training, false, 0); if (training) discriminator_backward(dy, 1, false, true);
+  disc_bce(dx, 1, 1.f, 1.0f, training, false, 1); if (training) discriminator_backward(dx, 1, false, true);
+  if (training) {
+    const GradSrc none{nullptr, 0, 0};
+    const float lc = lambda / (float)n_img;
+    generator_backward(f, 0, none, none, x, lc, true);                                   // cycle x: through F into fake_y
+    generator_backward(g, 1, none, none, y, lc, true);                                   // cycle y: through G into fake_x
+    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, C, 0}, GradSrc{f->slots[0].dxin.p, C, 0}, nullptr, 0.f, false);
+    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, C, 0}, GradSrc{g->slots[1].dxin.p, C, 0}, nullptr, 0.f, false);
+    generator_backward(f, 2, none, none, x, 0.5f * lc, false);                           // identity x (:244)
+    generator_backward(g, 2, none, none, y, 0.5f * lc, false);                           // identity y (:243)
+    adam_apply(og); adam_apply(of); adam_apply(odx); adam_apply(ody);                    // (:263-273)
+  }
+  LossMix mix; memset(&mix, 0, sizeof(mix));
+  mix.nraw = 10; mix.nout = 7;
+  const float nlog = (float)logits_count(dx->slots[0]);
+  for (int j = 0; j < 10; ++j) mix.denom[j] = (j >= 2 && j <= 5) ? (float)n_img : nlog;
+  auto M = [&](int i, int j) -> float& { return mix.mix[i * mix.nraw + j]; };
+  M(0, 0) = 1.f;                                                       // gen_g_loss
+  M(1, 1) = 1.f;                                                       // gen_f_loss
+  M(2, 2) = lambda; M(2, 3) = lambda;                                  // total_cycle_loss (:240)
+  M(3, 0) = 1.f; M(3, 2) = lambda; M(3, 3) = lambda; M(3, 4) = 0.5f * lambda;   // total_gen_g_loss (:243)
+  M(4, 1) = 1.f; M(4, 2) = lambda; M(4, 3) = lambda; M(4, 5) = 0.5f * lambda;   // total_gen_f_loss (:244)
+  M(5, 6) = 0.5f; M(5, 7) = 0.5f;                                      // disc_x_loss (:246)
+  M(6, 8) = 0.5f; M(6, 9) = 0.5f;                                      // disc_y_loss (:247)
+  finish_losses(ctx, mix, losses);
+}
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+const char* gan_last_error(void) { return g_last_error.c_str(); }
+int gan_version(void) { return 100; }
+
+int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
+  API_BEGIN
+  GAN_REQUIRE(out != nullptr, "null out");
+  GAN_REQUIRE(precision == GAN_FP32 || precision == GAN_BF16, "bad precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw GanError(GAN_ERR_NO_DEVICE, "no CUDA device: libgan_b200 has no CPU fallback");
+  }
+  GAN_REQUIRE(device >= 0 && device < ndev, "bad device index");
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) throw GanError(GAN_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) +
+                                                              std::to_string(prop.minor) + ", this library is sm_100a only");
+  gan_ctx* c = new gan_ctx();
+  c->device = device; c->dt = precision == GAN_FP32 ? DT_F32 : DT_BF16; c->seed = seed;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaMallocHost((void**)&c->loss_host, 16 * 4));
+  umma_init();
+  *out = c;
+  API_END
+}
+int gan_ctx_destroy(gan_ctx* ctx) {
+  API_BEGIN
+  if (!ctx) return GAN_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  cudaFreeHost(ctx->loss_host);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  API_END
+}
+int gan_ctx_sync(gan_ctx* ctx) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  CUDA_CHECK(cudaGetLastError());
+  API_END
+}
+int gan_ctx_set_dropout(gan_ctx* ctx, int enabled) { ctx->dropout_enabled = enabled ? 1 : 0; return GAN_OK; }
+int gan_ctx_set_rng(gan_ctx* ctx, uint64_t seed, uint32_t call_counter) { ctx->seed = seed; ctx->call_counter = call_counter; return GAN_OK; }
+int gan_ctx_get_call_counter(gan_ctx* ctx, uint32_t* out) { *out = ctx->call_counter; return GAN_OK; }
+int gan_ctx_set_engine(gan_ctx* ctx, int engine) { ctx->engine = engine; return GAN_OK; }
+int gan_ctx_set_graphs(gan_ctx* ctx, int enabled) { ctx->graphs = enabled; return GAN_OK; }
+int gan_ctx_launch_count(gan_ctx* ctx, uint64_t* out) { *out = ctx->launches; return GAN_OK; }
+int gan_ctx_stream(gan_ctx* ctx, void** out) { *out = (void*)ctx->stream; return GAN_OK; }
+int gan_ctx_set_sample_offset(gan_ctx* ctx, int64_t sample0) { ctx->sample0 = sample0; ctx->sample0_set = true; return GAN_OK; }
+
+int gan_comm_unique_id(void* out128) {
+  API_BEGIN
+  int r = comm_unique_id(out128);
+  if (r != 0) throw GanError(GAN_ERR_COMM, "ncclGetUniqueId failed");
+  API_END
+}
+int gan_ctx_comm_init(gan_ctx* ctx, int rank, int world, const void* unique_id128) {
+  API_BEGIN
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  comm_init(ctx, rank, world, unique_id128);
+  API_END
+}
+
+int gan_generator_create(gan_ctx* ctx, int norm_type, int height, int width, int channels, gan_net** out) {
+  API_BEGIN
+  GAN_REQUIRE(ctx && out, "null argument");
+  GAN_REQUIRE(norm_type == GAN_NORM_BATCH || norm_type == GAN_NORM_INSTANCE, "bad norm type");
+  GAN_REQUIRE(channels >= 1 && channels <= 4, "channels must be 1..4");
+  GAN_REQUIRE(height >= 256 && width >= 256 && height % 256 == 0 && width % 256 == 0, "image size must be a multiple of 256");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  gan_net* n = new gan_net();
+  n->ctx = ctx; n->is_gen = true; n->norm = norm_type; n->H = height; n->W = width; n->C = channels; n->Cin0 = channels;
+  int cin = channels;
+  for (int j = 1; j <= 8; ++j) {            // downsample blocks, first without norm (base_gan.py:179-188)
+    add_layer(n, "down" + std::to_string(j), K_CONV_S2, cin, DOWN_F[j - 1], j == 1 ? NORM_NONE : norm_type, ACT_LEAKY, false,
+              false, 0, false);
+    cin = DOWN_F[j - 1];
+  }
+  for (int k = 1; k <= 7; ++k) {            // upsample blocks, first three with dropout (base_gan.py:190-198)
+    add_layer(n, "up" + std::to_string(k), K_CONVT_S2, cin, UP_F[k - 1], norm_type, ACT_RELU, false, k <= 3, k, false);
+    cin = UP_F[k - 1] + DOWN_F[7 - k];
+  }
+  add_layer(n, "last", K_CONVT_S2, cin, channels, NORM_NONE, ACT_TANH, true, false, 0, true);   // base_gan.py:201-204
+  finish_net(n);
+  *out = n;
+  API_END
+}
+
+int gan_discriminator_create(gan_ctx* ctx, int norm_type, int channels, int target, gan_net** out) {
+  API_BEGIN
+  GAN_REQUIRE(ctx && out, "null argument");
+  GAN_REQUIRE(norm_type == GAN_NORM_BATCH || norm_type == GAN_NORM_INSTANCE, "bad norm type");
+  GAN_REQUIRE(channels >= 1 && channels <= 4, "channels must be 1..4");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  gan_net* n = new gan_net();
+  n->ctx = ctx; n->is_gen = false; n->norm = norm_type; n->C = channels; n->target = target != 0;
+  n->Cin0 = target ? 2 * channels : channels;
+  add_layer(n, "down1", K_CONV_S2, n->Cin0, 64, NORM_NONE, ACT_LEAKY, false, false, 0, false);   // base_gan.py:141
+  add_layer(n, "down2", K_CONV_S2, 64, 128, norm_type, ACT_LEAKY, false, false, 0, false);       // :142
+  add_layer(n, "down3", K_CONV_S2, 128, 256, norm_type, ACT_LEAKY, false, false, 0, false);      // :143
+  add_layer(n, "conv512", K_CONV_S1P, 256, 512, norm_type, ACT_LEAKY, false, false, 0, false);   // :145-155
+  n->tensors[n->tensors.size() - 2].name = "norm.gamma"; n->tensors[n->tensors.size() - 1].name = "norm.beta";
+  add_layer(n, "last", K_CONV_S1P, 512, 1, NORM_NONE, ACT_NONE, true, false, 0, true);           // :157-161
+  finish_net(n);
+  *out = n;
+  API_END
+}
+
+int gan_net_destroy(gan_net* net) {
+  API_BEGIN
+  if (net) { cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); delete net; }
+  API_END
+}
+
+int gan_net_num_tensors(gan_net* net, int* trainable, int* total) {
+  if (trainable) *trainable = net->ntrain;
+  if (total) *total = (int)net->tensors.size();
+  return GAN_OK;
+}
+int gan_net_tensor_info(gan_net* net, int idx, char* name, int name_cap, int* ndim, int64_t shape[4], int64_t* numel) {
+  API_BEGIN
+  GAN_REQUIRE(idx >= 0 && idx < (int)net->tensors.size(), "tensor index out of range");
+  const TensorInfo& t = net->tensors[idx];
+  if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ndim) *ndim = t.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = t.shape[i];
+  if (numel) *numel = t.numel;
+  API_END
+}
+static float* tensor_dev(gan_net* net, int idx, DevBuf* alt = nullptr) {
+  GAN_REQUIRE(idx >= 0 && idx < (int)net->tensors.size(), "tensor index out of range");
+  const TensorInfo& t = net->tensors[idx];
+  if (t.trainable) return (alt ? alt->as<float>() : net->params.as<float>()) + t.off;
+  GAN_REQUIRE(alt == nullptr, "non-trainable tensor has no gradient");
+  return net->mov.as<float>() + t.off;
+}
+int gan_net_get_tensor(gan_net* net, int idx, float* host_dst) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(host_dst, tensor_dev(net, idx), net->tensors[idx].numel * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+int gan_net_set_tensor(gan_net* net, int idx, const float* host_src) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(tensor_dev(net, idx), host_src, net->tensors[idx].numel * 4, cudaMemcpyHostToDevice));
+  net->packed_dirty = true;
+  API_END
+}
+int gan_net_get_grad(gan_net* net, int idx, float* host_dst) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(host_dst, tensor_dev(net, idx, &net->grads), net->tensors[idx].numel * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+int gan_net_num_params(gan_net* net, int64_t* out) { *out = net->nparams; return GAN_OK; }
+int gan_net_get_params(gan_net* net, float* host_dst) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(host_dst, net->params.p, net->nparams * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+int gan_net_set_params(gan_net* net, const float* host_src) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(net->params.p, host_src, net->nparams * 4, cudaMemcpyHostToDevice));
+  net->packed_dirty = true;
+  API_END
+}
+int gan_net_get_grads(gan_net* net, float* host_dst) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(host_dst, net->grads.p, net->nparams * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+
+int gan_net_debug_tensor(gan_net* net, int slot, const char* name, float* host_dst, int64_t cap, int64_t* numel) {
+  API_BEGIN
+  gan_ctx* ctx = net->ctx;
+  GAN_REQUIRE(slot >= 0 && slot < (int)net->slots.size(), "bad slot");
+  Slot& s = net->slots[slot];
+  GAN_REQUIRE(s.B > 0, "slot has no forward call yet");
+  std::string nm(name);
+  const void* src = nullptr; int pitch = 0, coff = 0, C = 0; int64_t P = 0; bool is_f32 = false;
+  if (nm == "out" && net->is_gen) { src = s.out_f32.p; C = net->C; P = (int64_t)s.B * s.H * s.W; pitch = C; is_f32 = true; }
+  else if (nm == "logits" && !net->is_gen) { src = s.logits.p; C = 1; P = logits_count(s); pitch = 1; is_f32 = true; }
+  else if (nm == "din0" && !net->is_gen) { src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = C; }
+  else {
+    size_t dot = nm.rfind('.');
+    GAN_REQUIRE(dot != std::string::npos, "debug tensor name must be <layer>.z or <layer>.a");
+    std::string lname = nm.substr(0, dot), what = nm.substr(dot + 1);
+    int li = -1;
+    for (size_t i = 0; i < net->layers.size(); ++i) if (net->layers[i].name == lname) li = (int)i;
+    GAN_REQUIRE(li >= 0 && !net->layers[li].head, "unknown layer");
+    View ov = s.out_views[li];
+    P = ov.pixels(); C = ov.C;
+    if (what == "z") { src = s.z[li].p; pitch = C; coff = 0; }
+    else if (what == "a") { src = ov.p; pitch = ov.pitch; coff = ov.coff; }
+    else GAN_REQUIRE(false, "debug tensor kind must be z or a");
+  }
+  if (numel) *numel = P * C;
+  GAN_REQUIRE(cap >= P * C, "destination too small");
+  if (is_f32) {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaMemcpy(host_dst, src, P * C * 4, cudaMemcpyDeviceToHost));
+  } else {
+    DevBuf tmp; tmp.ensure((size_t)P * C * 4);
+    launch_export(ctx->L(), ctx->dt, src, pitch, coff, P, C, tmp.as<float>());
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaMemcpy(host_dst, tmp.p, P * C * 4, cudaMemcpyDeviceToHost));
+  }
+  API_END
+}
+
+int gan_generator_forward(gan_net* g, const float* x, int batch, float* out) {
+  API_BEGIN
+  GAN_REQUIRE(g && g->is_gen && x && out && batch >= 1, "bad argument");
+  gan_ctx* ctx = g->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t bytes = (size_t)batch * g->H * g->W * g->C * 4;
+  const float* xd = stage_in(ctx, 0, x, bytes);
+  generator_forward(g, 0, xd, batch, g->H, g->W);
+  copy_out(ctx, out, g->slots[0].out_f32.as<float>(), bytes);
+  API_END
+}
+
+int gan_discriminator_forward(gan_net* d, const float* inp, const float* tar, int batch, int height, int width,
+                              float* logits) {
+  API_BEGIN
+  GAN_REQUIRE(d && !d->is_gen && inp && logits && batch >= 1, "bad argument");
+  gan_ctx* ctx = d->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t bytes = (size_t)batch * height * width * d->C * 4;
+  const float* id = stage_in(ctx, 0, inp, bytes);
+  const float* td = tar ? stage_in(ctx, 1, tar, bytes) : nullptr;
+  discriminator_forward(d, 0, id, td, batch, height, width);
+  copy_out(ctx, logits, d->slots[0].logits.as<float>(), (size_t)logits_count(d->slots[0]) * 4);
+  API_END
+}
+
+int gan_adam_create(gan_net* net, double lr, double beta1, double beta2, double eps, gan_adam** out) {
+  API_BEGIN
+  GAN_REQUIRE(net && out, "null argument");
+  CUDA_CHECK(cudaSetDevice(net->ctx->device));
+  gan_adam* o = new gan_adam();
+  o->net = net; o->lr = lr; o->b1 = beta1; o->b2 = beta2; o->eps = eps;
+  o->m.ensure((size_t)(net->nparams + 4) * 4); o->v.ensure((size_t)(net->nparams + 4) * 4);
+  *out = o;
+  API_END
+}
+int gan_adam_destroy(gan_adam* opt) {
+  API_BEGIN
+  if (opt) { cudaSetDevice(opt->net->ctx->device); cudaStreamSynchronize(opt->net->ctx->stream); delete opt; }
+  API_END
+}
+int gan_adam_get_step(gan_adam* opt, int64_t* t) { *t = opt->t; return GAN_OK; }
+int gan_adam_set_step(gan_adam* opt, int64_t t) { opt->t = t; return GAN_OK; }
+int gan_adam_get_state(gan_adam* opt, int which, float* host_dst) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(opt->net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(host_dst, which == 0 ? opt->m.p : opt->v.p, opt->net->nparams * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+int gan_adam_set_state(gan_adam* opt, int which, const float* host_src) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(opt->net->ctx->stream));
+  CUDA_CHECK(cudaMemcpy(which == 0 ? opt->m.p : opt->v.p, host_src, opt->net->nparams * 4, cudaMemcpyHostToDevice));
+  API_END
+}
+
+int gan_pix2pix_train_step(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_opt, const float* input_image,
+                           const float* target, int batch, float lambda, int training, float losses[4]) {
+  API_BEGIN
+  GAN_REQUIRE(g && d && input_image && target, "null argument");
+  GAN_REQUIRE(!training || (g_opt && d_opt && g_opt->net == g && d_opt->net == d), "optimizers do not match the nets");
+  CUDA_CHECK(cudaSetDevice(g->ctx->device));
+  pix2pix_step(g, d, g_opt, d_opt, input_image, target, batch, lambda, training, losses);
+  API_END
+}
+
+int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_adam* g_opt, gan_adam* f_opt,
+                            gan_adam* dx_opt, gan_adam* dy_opt, const float* real_x, const float* real_y, int batch,
+                            float lambda, int training, float losses[7]) {
+  API_BEGIN
+  GAN_REQUIRE(g && f && dx && dy && real_x && real_y, "null argument");
+  GAN_REQUIRE(!training || (g_opt && f_opt && dx_opt && dy_opt && g_opt->net == g && f_opt->net == f &&
+                            dx_opt->net == dx && dy_opt->net == dy), "optimizers do not match the nets");
+  CUDA_CHECK(cudaSetDevice(g->ctx->device));
+  cyclegan_step(g, f, dx, dy, g_opt, f_opt, dx_opt, dy_opt, real_x, real_y, batch, lambda, training, losses);
+  API_END
+}
+
+int gan_ctx_last_losses(gan_ctx* ctx, float* out, int n) {
+  API_BEGIN
+  GAN_REQUIRE(n >= 0 && n <= ctx->n_losses, "more losses requested than the last step produced");
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->loss_host, (size_t)n * 4);
+  API_END
+}
+
+int gan_op_conv(gan_ctx* ctx, int kind, int role, int engine, const float* a, const float* b, float* out, int batch,
+                int height, int width, int cin, int cout) {
+  API_BEGIN
+  GAN_REQUIRE(ctx && a && b && out, "null argument");
+  GAN_REQUIRE(kind >= 0 && kind <= 2 && role >= 0 && role <= 2, "bad kind/role");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  Layer ly; ly.name = "op"; ly.kind = kind; ly.Cin = cin; ly.Cout = cout; ly.norm = NORM_NONE; ly.act = ACT_NONE;
+  int Ho, Wo; out_dims(kind, height, width, Ho, Wo);
+  const int64_t nx = (int64_t)batch * height * width * cin, ny = (int64_t)batch * Ho * Wo * cout, nw = 16LL * cin * cout;
+  const size_t es = ctx->esize();
+  DevBuf fa, fb, fo, xa, ya, wp;
+  Launch L = ctx->L();
+  int saved = ctx->engine; ctx->engine = engine;
+  try {
+    auto up = [&](DevBuf& stage, const float* h, int64_t n) {
+      stage.ensure((size_t)n * 4);
+      CUDA_CHECK(cudaMemcpyAsync(stage.p, h, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    };
+    View x = make_view(nullptr, batch, height, width, cin), y = make_view(nullptr, batch, Ho, Wo, cout);
+    xa.ensure((size_t)nx * es); ya.ensure((size_t)ny * es);
+    x.p = xa.p; y.p = ya.p;
+    if (role != R_WGRAD) {
+      // pack the kernel for this role
+      up(fb, b, nw);
+      PackOp po; memset(&po, 0, sizeof(po));
+      po.ncls = fill_geometry(kind, role, po.cls);
+      weight_strides(ly, role, po.Kc, po.Nc, po.s_tap, po.s_k, po.s_n);
+      for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
+      wp.ensure((size_t)nw * es);
+      launch_pack(L, ctx->dt, fb.as<float>(), wp.p, po);
+      if (role == R_FWD) {
+        up(fa, a, nx);
+        launch_convert(L, ctx->dt, fa.as<float>(), nx / cin, cin, x.p, cin, 0);
+        run_conv_fwd(ctx, make_op(ly, R_FWD, x, y, wp.p));
+        fo.ensure((size_t)ny * 4);
+        launch_export(L, ctx->dt, y.p, cout, 0, ny / cout, cout, fo.as<float>());
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CUDA_CHECK(cudaMemcpy(out, fo.p, ny * 4, cudaMemcpyDeviceToHost));
+      } else {
+        up(fa, a, ny);
+        launch_convert(L, ctx->dt, fa.as<float>(), ny / cout, cout, y.p, cout, 0);
+        run_conv_fwd(ctx, make_op(ly, R_DGRAD, x, y, wp.p));
+        fo.ensure((size_t)nx * 4);
+        launch_export(L, ctx->dt, x.p, cin, 0, nx / cin, cin, fo.as<float>());
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CUDA_CHECK(cudaMemcpy(out, fo.p, nx * 4, cudaMemcpyDeviceToHost));
+      }
+    } else {
+      up(fa, a, nx); up(fb, b, ny);
+      launch_convert(L, ctx->dt, fa.as<float>(), nx / cin, cin, x.p, cin, 0);
+      launch_convert(L, ctx->dt, fb.as<float>(), ny / cout, cout, y.p, cout, 0);
+      fo.ensure((size_t)nw * 4);
+      CUDA_CHECK(cudaMemsetAsync(fo.p, 0, nw * 4, ctx->stream));
+      ConvOp op = make_op(ly, R_WGRAD, x, y, nullptr);
+      op.dW = fo.as<float>();
+      run_conv_wgrad(ctx, op);
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      CUDA_CHECK(cudaMemcpy(out, fo.p, nw * 4, cudaMemcpyDeviceToHost));
+    }
+    CUDA_CHECK(cudaGetLastError());
+  } catch (...) { ctx->engine = saved; throw; }
+  ctx->engine = saved;
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// engine.h — host-side objects behind the C-ABI handles (gan_ctx / gan_net / gan_adam).
+#pragma once
+#include <string>
+#include <vector>
+#include <map>
+#include "kernels.h"
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  // grows only; contents are NOT preserved on growth
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    release();
+    CUDA_CHECK(cudaMalloc(&p, n));
+    CUDA_CHECK(cudaMemset(p, 0, n));
+    bytes = n;
+  }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct CommApi;   // dlopen'ed NCCL entry points (comm.cu)
+
+struct gan_ctx {
+  int device = 0;
+  int dt = DT_F32;
+  cudaStream_t stream = nullptr;
+  uint64_t seed = 0;
+  uint32_t call_counter = 0;
+  int dropout_enabled = 1;
+  int engine = -1;
+  int graphs = 0;
+  int64_t sample0 = 0;
+  bool sample0_set = false;
+  uint64_t launches = 0;
+  DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk;
+  DevBuf stage[4];
+  float* loss_host = nullptr;   // pinned
+  int n_losses = 0;
+  // data parallel
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  Launch L() { return Launch{stream, &launches}; }
+  size_t esize() const { return dt == DT_F32 ? 4 : 2; }
+};
+
+struct TensorInfo {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+  int64_t numel;
+  int64_t off;        // float offset in params (trainable) or mov (moving stats)
+  bool trainable;
+};
+
+struct Layer {
+  std::string name;
+  int kind, Cin, Cout, norm, act;
+  bool bias = false, dropout = false, need_dgrad = true, head = false;
+  int tag = 0;
+  int64_t w_off = -1, g_off = -1, b_off = -1, bias_off = -1, mov_off = -1;
+  DevBuf wp_fwd, wp_dgrad;
+};
+
+// Saved state of one forward call of a net (the "tape" of that call).
+struct Slot {
+  int B = 0, H = 0, W = 0;
+  uint32_t call_id = 0;
+  int64_t sample0 = 0;
+  std::vector<DevBuf> z;        // raw conv outputs per layer
+  std::vector<DevBuf> stats;    // per layer: mean, inv, scale, shift, c1, c2  ([G][C] each)
+  std::vector<View> in_views, out_views;   // per layer: input activation view, activated output view
+  // generator
+  DevBuf xin, d8, out_f32, dd8, dxin;
+  std::vector<DevBuf> cat, dcat, dskip;
+  // discriminator
+  DevBuf in0, logits, dlogit, din0;
+  std::vector<DevBuf> act, dact;
+};
+
+struct gan_net {
+  gan_ctx* ctx = nullptr;
+  bool is_gen = false;
+  int norm = NORM_BATCH, H = 0, W = 0, C = 0, Cin0 = 0;
+  bool target = false;
+  std::vector<Layer> layers;
+  std::vector<TensorInfo> tensors;
+  int ntrain = 0;
+  int64_t nparams = 0, nmov = 0;
+  DevBuf params, grads, mov;
+  std::vector<Slot> slots;
+  bool packed_dirty = true;
+};
+
+struct gan_adam {
+  gan_net* net = nullptr;
+  double lr, b1, b2, eps;
+  int64_t t = 0;
+  DevBuf m, v;
+};
+
+// comm.cu
+int comm_unique_id(void* out128);
+void comm_init(gan_ctx* ctx, int rank, int world, const void* id128);
+void comm_destroy(gan_ctx* ctx);
+void comm_allreduce_sum(gan_ctx* ctx, float* buf, int64_t n);

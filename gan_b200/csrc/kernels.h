@@ -1,0 +1,60 @@
+// kernels.h — host-side launchers of every CUDA kernel in libgan_b200.so.
+#pragma once
+#include "common.cuh"
+
+struct Launch {
+  cudaStream_t s;
+  uint64_t* count;   // incremented once per kernel launch (bench: gpu_launches)
+};
+
+#define STATS_MAX_CHUNKS 592   // 4 x 148 SMs
+#define LOSS_SLOTS 16
+#define LOSS_BLOCKS 256
+
+// ---- elem.cu --------------------------------------------------------------------------------
+void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* dst, int pitch, int coff);
+void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64_t P, int C, float* dst);
+
+int stats_chunks(int G, int64_t Pg);
+size_t stats_ws_floats(int G, int64_t Pg, int C);
+// Per-channel (G==1, BatchNorm) or per-(sample,channel) (G==N, InstanceNorm) moments of z, then
+// mean/inv/scale/shift (each [G][C]); BN moving statistics updated when mov_mean != nullptr.
+void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C, float* ws, float eps,
+                       const float* gamma, const float* beta, float* mean, float* inv, float* scale,
+                       float* shift, float* mov_mean, float* mov_var, float momentum);
+// out = act(dropout(z*scale+shift)); scale == nullptr => identity affine (no-norm layers).
+void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, int G, int HW, int C,
+                       const float* scale, const float* shift, int act, DropKey dk, void* out, int out_pitch,
+                       int out_coff);
+struct GradSrc { const void* p; int pitch, coff; };
+// Backward of (norm -> dropout -> activation): dz, plus dgamma/dbeta accumulated into the grad buffer.
+void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
+                     int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
+                     int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz);
+// Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
+void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
+                      float l1_coef, int64_t P, int C, void* dz, float* dbias);
+// BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
+void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, float* dbias,
+                float* loss_ws, int slot);
+void launch_l1(Launch L, const float* a, const float* b, int64_t n, float* loss_ws, int slot);
+// raw[j] = sum(slot j)/denom[j]; out[i] = sum_j mix[i*nraw+j]*raw[j]
+struct LossMix { int nraw, nout; float denom[LOSS_SLOTS]; float mix[8 * LOSS_SLOTS]; };
+void launch_loss_finalize(Launch L, const float* loss_ws, LossMix mix, float* out);
+void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
+                 float eps, float gscale);
+struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc; int64_t s_tap, s_k, s_n; };
+void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op);
+void launch_scale(Launch L, float* p, int64_t n, float s);
+
+// ---- conv_ffma.cu ---------------------------------------------------------------------------
+void launch_conv_fwd_ffma(Launch L, int dt, const ConvOp& op);
+void launch_conv_wgrad_ffma(Launch L, int dt, const ConvOp& op);
+
+// ---- conv_umma.cu ---------------------------------------------------------------------------
+struct UmmaPlan;   // opaque: tensor maps + tiling for one (op, batch) pair
+bool umma_fwd_supported(const ConvOp& op);
+bool umma_wgrad_supported(const ConvOp& op);
+void launch_conv_fwd_umma(Launch L, const ConvOp& op);
+void launch_conv_wgrad_umma(Launch L, const ConvOp& op);
+void umma_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes

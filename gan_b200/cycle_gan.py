@@ -1,0 +1,91 @@
+"""Host-side mirror of the reference's ``CycleGAN`` (reference cycle_gan.py:26-376), hot path only."""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _ffi
+from .base_gan import GAN, LossValue, _as_f32
+from .utils import cyclegan_losses
+
+
+class CycleGAN(GAN):
+    def __init__(self, config):
+        """Reference cycle_gan.py:28-37: two InstanceNorm generators, two target=False PatchGANs, four Adams."""
+        super().__init__(config)
+        ch = int(self.config['channels'])
+        self.generator_g = super().Generator(norm_type='instancenorm', shape=(None, None, ch))
+        self.generator_f = super().Generator(norm_type='instancenorm', shape=(None, None, ch))
+        self.discriminator_x = super().Discriminator(norm_type='instancenorm', target=False)
+        self.discriminator_y = super().Discriminator(norm_type='instancenorm', target=False)
+        kw = dict(learning_rate=self.config.get('learning_rate', 2e-4), beta_1=self.config.get('beta_1', 0.5),
+                  beta_2=self.config.get('beta_2', 0.999))
+        self.generator_g_optimizer = super().optimizer(**kw)
+        self.generator_f_optimizer = super().optimizer(**kw)
+        self.discriminator_x_optimizer = super().optimizer(**kw)
+        self.discriminator_y_optimizer = super().optimizer(**kw)
+
+    def generator_loss(self, generated):
+        """Reference cycle_gan.py:154-159 (host arrays)."""
+        return self.loss_obj(np.ones_like(generated), generated)
+
+    def calc_cycle_loss(self, real_image, cycled_image):
+        """Reference cycle_gan.py:161-168."""
+        return float(np.mean(np.abs(np.asarray(real_image, np.float64) - np.asarray(cycled_image, np.float64)))) \
+            * self.config.get('lambda', 10)
+
+    def identity_loss(self, real_image, same_image):
+        """Reference cycle_gan.py:170-177."""
+        return self.config.get('lambda', 10) * 0.5 * float(
+            np.mean(np.abs(np.asarray(real_image, np.float64) - np.asarray(same_image, np.float64))))
+
+    def train_step(self, real_x, real_y, training: bool = True, sync: bool = True):
+        """Reference cycle_gan.py:206-276: six generator and four discriminator forwards, seven
+        losses, one fused backward sweep that yields the reference's four gradient sets, four
+        Keras-Adam updates.  Returns the seven losses in the reference's order."""
+        x, y = _as_f32(real_x), _as_f32(real_y)
+        b = int(x.shape[0])
+        h = [self.generator_g_optimizer.bind(self.generator_g), self.generator_f_optimizer.bind(self.generator_f),
+             self.discriminator_x_optimizer.bind(self.discriminator_x),
+             self.discriminator_y_optimizer.bind(self.discriminator_y)]
+        losses = np.zeros(7, dtype=np.float32) if sync else None
+        _ffi.check(_ffi.lib().gan_cyclegan_train_step(
+            self.generator_g.handle, self.generator_f.handle, self.discriminator_x.handle, self.discriminator_y.handle,
+            h[0], h[1], h[2], h[3], _ffi.ptr_of(x), _ffi.ptr_of(y), b, C.c_float(float(self.config.get('lambda', 10))),
+            int(bool(training)), _ffi.ptr_of(losses)))
+        if not sync:
+            return None
+        return tuple(LossValue(v) for v in losses)
+
+    def generate_images(self, model, test_input, path_filename: str = None):
+        """Forward call of reference cycle_gan.py:179-186."""
+        prediction = model(test_input, training=True)
+        if path_filename:
+            np.save(path_filename, prediction)
+        return prediction
+
+    def fit(self, train_X, train_Y, val_X, val_Y, test=None, output_path: str = None, checkpoint_manager=None):
+        """Reference cycle_gan.py:278-358 (zip of the X and Y batch iterables)."""
+        start = time.time()
+        train_cost_functions, val_cost_functions = cyclegan_losses(), cyclegan_losses()
+        keys = list(train_cost_functions.keys())
+        for epoch in range(self.config['epochs']):
+            train_losses, val_losses = cyclegan_losses(), cyclegan_losses()
+            for image_x, image_y in zip(train_X, train_Y):
+                for k, v in zip(keys, self.train_step(image_x, image_y)):
+                    train_losses[k].append(v.numpy().tolist())
+            for k in keys:
+                train_cost_functions[k].append(sum(train_losses[k]) / len(train_losses[k]))
+            for image_x, image_y in zip(val_X, val_Y):
+                for k, v in zip(keys, self.train_step(image_x, image_y, False)):
+                    val_losses[k].append(v.numpy().tolist())
+            for k in keys:
+                val_cost_functions[k].append(sum(val_losses[k]) / len(val_losses[k]))
+            print(f'\nCumulative training duration at end of epoch {epoch + 1}: {(time.time() - start) / 60:.2f} min')
+        return train_cost_functions, val_cost_functions
+
+    def predict(self, predict_ds, output_path: str = None):
+        """Reference cycle_gan.py:360-376."""
+        return [self.generate_images(self.generator_g, np.expand_dims(np.asarray(i), axis=0)) for i in predict_ds]

@@ -1,0 +1,137 @@
+"""GPU parity of the fused Pix2Pix train step (reference pix2pix.py:190-218) against the CPU oracle:
+identical host-generated weights, synthetic U[-1,1) images and Philox dropout masks."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, make_pix2pix, load_model
+from oracle import gan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SEED = 123
+
+
+def _build(precision, channels=3, size=256, lam=100):
+    from gan_b200 import Pix2Pix
+    cfg = dict(img_size=size, channels=str(channels), learning_rate=2e-4, beta_1=0.5, beta_2=0.999,
+               generator_loss='l1', seed=SEED, precision=precision, epochs=1, batch_size=1)
+    cfg['lambda'] = lam
+    m = Pix2Pix(cfg)
+    g_np, d_np = make_pix2pix(SEED + 1, channels, None)
+    load_model(m.generator, g_np)
+    load_model(m.discriminator, d_np)
+    return m, g_np, d_np
+
+
+def _oracle_state(g_np, d_np, dtype=torch.float64):
+    gp, dp = O.to_torch(g_np, dtype), O.to_torch(d_np, dtype)
+    return gp, dp, O.KerasAdam(gp), O.KerasAdam(dp)
+
+
+def _inputs(b, size, c, seed=SEED):
+    rng = np.random.default_rng(seed)
+    return O.synthetic_images(rng, b, size, size, c), O.synthetic_images(rng, b, size, size, c)
+
+
+def _check_tensors(names, dev, ref, tol, what):
+    worst = 0.0
+    for n, a, r in zip(names, dev, ref):
+        r = r.detach().numpy() if hasattr(r, "detach") else np.asarray(r)
+        if np.abs(r).max() == 0.0:
+            assert np.abs(a).max() < 1e-10, f"{what} {n}: oracle is exactly zero, device is not"
+            continue
+        e = rel_err(a, r)
+        worst = max(worst, e)
+        assert e < tol, f"{what} {n}: rel err {e:.3e} >= {tol}"
+    return worst
+
+
+@pytest.mark.parametrize("batch,channels", [(1, 3), (2, 3), (2, 1)])
+def test_fp32_step_matches_oracle(batch, channels):
+    m, g_np, d_np = _build("fp32", channels)
+    gp, dp, go, do = _oracle_state(g_np, d_np)
+    x, y = _inputs(batch, 256, channels)
+    names_g = [v.name for v in m.generator.trainable_variables]
+    names_d = [v.name for v in m.discriminator.trainable_variables]
+    for step in range(2):
+        masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, batch, 256)
+        losses = m.train_step(x, y, True)
+        ref_losses, gg, dg = O.pix2pix_train_step(gp, dp, go, do, torch.tensor(x, dtype=torch.float64),
+                                                  torch.tensor(y, dtype=torch.float64), 100.0, True, masks)
+        for a, r in zip(losses, ref_losses):
+            assert abs(float(a) - r) <= 1e-4 * max(1.0, abs(r)), (step, list(map(float, losses)), ref_losses)
+        _check_tensors(names_g, [v.grad() for v in m.generator.trainable_variables], gg, 1e-4, f"step{step} dG")
+        _check_tensors(names_d, [v.grad() for v in m.discriminator.trainable_variables], dg, 1e-4, f"step{step} dD")
+        _check_tensors(names_g, m.generator.get_weights(), gp, 1e-4, f"step{step} G")
+        _check_tensors(names_d, m.discriminator.get_weights(), dp, 1e-4, f"step{step} D")
+    assert m.generator_optimizer.iterations == 2 and m.discriminator_optimizer.iterations == 2
+    m.ctx.close()
+
+
+def test_fp32_generator_forward_and_validation_step():
+    m, g_np, d_np = _build("fp32", 3)
+    gp, dp, go, do = _oracle_state(g_np, d_np)
+    x, y = _inputs(2, 256, 3, seed=7)
+    # model(x, training=True): predict semantics (pix2pix.py:228) — batch stats + dropout
+    masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, 2, 256)
+    out = m.generator(x, training=True)
+    ref = O.generator_forward(gp, torch.tensor(x, dtype=torch.float64), "batchnorm", masks).detach().numpy()
+    assert rel_err(out, ref) < 1e-4
+    # discriminator([inp, tar], training=True)
+    logits = m.discriminator([x, y], training=True)
+    ref_l = O.discriminator_forward(dp, torch.tensor(x, dtype=torch.float64), torch.tensor(y, dtype=torch.float64)).detach().numpy()
+    assert logits.shape == (2, 30, 30, 1) and rel_err(logits, ref_l) < 1e-4
+    # train_step(..., training=False): same forward, no update, Adam t not advanced (pix2pix.py:208,292)
+    w_before = m.generator.get_flat_params().copy()
+    masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, 2, 256)
+    losses = m.train_step(x, y, False)
+    ref_losses, _, _ = O.pix2pix_train_step(gp, dp, go, do, torch.tensor(x, dtype=torch.float64),
+                                            torch.tensor(y, dtype=torch.float64), 100.0, False, masks)
+    for a, r in zip(losses, ref_losses):
+        assert abs(float(a) - r) <= 1e-4 * max(1.0, abs(r))
+    assert np.array_equal(w_before, m.generator.get_flat_params())
+    assert m.generator_optimizer.iterations == 0
+    # ragged tail batch (tf.data batch() without drop_remainder, pix2pix.py:163): B smaller than before
+    masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, 1, 256)
+    losses = m.train_step(x[:1], y[:1], False)
+    ref_losses, _, _ = O.pix2pix_train_step(gp, dp, go, do, torch.tensor(x[:1], dtype=torch.float64),
+                                            torch.tensor(y[:1], dtype=torch.float64), 100.0, False, masks)
+    for a, r in zip(losses, ref_losses):
+        assert abs(float(a) - r) <= 1e-4 * max(1.0, abs(r))
+    m.ctx.close()
+
+
+def test_fp32_intermediate_activations():
+    """Per-layer localisation: raw conv outputs and activations of one generator forward."""
+    m, g_np, d_np = _build("fp32", 3)
+    gp = O.to_torch(g_np, torch.float64)
+    x, _ = _inputs(2, 256, 3, seed=11)
+    masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, 2, 256)
+    m.generator(x)
+    taps = {}
+    O.generator_forward(gp, torch.tensor(x, dtype=torch.float64), "batchnorm", masks, taps=taps)
+    for name in ["down1.a", "down2.z", "down2.a", "down5.a", "down8.a", "up1.a", "up3.a", "up4.z", "up7.a"]:
+        dev = m.generator.debug_tensor(name)
+        ref = taps[name].detach().numpy().reshape(-1)
+        assert rel_err(dev, ref) < 1e-4, name
+    m.ctx.close()
+
+
+def test_bf16_step_tracks_oracle():
+    """bf16/tcgen05 path: <=1e-2 relative on generator output and losses after N=3 steps."""
+    m, g_np, d_np = _build("bf16", 3)
+    gp, dp, go, do = _oracle_state(g_np, d_np)
+    x, y = _inputs(4, 256, 3)
+    xt, yt = torch.tensor(x, dtype=torch.float64), torch.tensor(y, dtype=torch.float64)
+    for step in range(3):
+        masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, 4, 256)
+        losses = m.train_step(x, y, True)
+        ref_losses, _, _ = O.pix2pix_train_step(gp, dp, go, do, xt, yt, 100.0, True, masks)
+        for a, r in zip(losses, ref_losses):
+            assert abs(float(a) - r) <= 1e-2 * max(1.0, abs(r)), (step, list(map(float, losses)), ref_losses)
+    masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, 4, 256)
+    out = m.generator(x)
+    ref = O.generator_forward(gp, xt, "batchnorm", masks).detach().numpy()
+    assert rel_err(out, ref) < 1e-2
+    m.ctx.close()
