@@ -34,6 +34,8 @@ SIGNATURES = {
     "gan_ctx_set_engine": (C.c_int, [_vp, C.c_int]),
     "gan_ctx_set_graphs": (C.c_int, [_vp, C.c_int]),
     "gan_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "gan_ctx_set_profile": (C.c_int, [_vp, C.c_int]),
+    "gan_ctx_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "gan_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "gan_comm_unique_id": (C.c_int, [_vp]),
     "gan_ctx_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

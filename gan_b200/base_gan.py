@@ -73,6 +73,17 @@ class Context:
         _ffi.check(_ffi.lib().gan_ctx_launch_count(self._h, C.byref(v)))
         return v.value
 
+    PROFILE_FAMILIES = ("umma_fwd", "umma_wgrad", "ffma_fwd", "ffma_wgrad", "norm", "adam", "pack", "other")
+
+    def set_profile(self, enabled: bool):
+        _ffi.check(_ffi.lib().gan_ctx_set_profile(self._h, int(bool(enabled))))
+
+    def profile_read(self):
+        """{family: (total ms, algorithmic work, launches)} since the last read (synchronises)."""
+        ms, work, cnt = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_int64 * 8)()
+        _ffi.check(_ffi.lib().gan_ctx_profile_read(self._h, ms, work, cnt))
+        return {n: (ms[i], work[i], cnt[i]) for i, n in enumerate(self.PROFILE_FAMILIES)}
+
     def stream(self) -> int:
         v = C.c_void_p()
         _ffi.check(_ffi.lib().gan_ctx_stream(self._h, C.byref(v)))

@@ -102,19 +102,39 @@ static void out_dims(int kind, int Hin, int Win, int& Ho, int& Wo) {
   else { Ho = Hin * 2; Wo = Win * 2; }
 }
 
+// Scoped CUDA-event timer around a group of launches of one kernel family (only when profiling).
+struct ProfScope {
+  gan_ctx* ctx; ProfEntry e; bool on;
+  ProfScope(gan_ctx* c, int fam, double work) : ctx(c), on(c->profile != 0) {
+    if (!on) return;
+    e.fam = fam; e.work = work; e.a = c->ev_get(); e.b = c->ev_get();
+    cudaEventRecord(e.a, c->stream);
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(e.b, ctx->stream); ctx->prof.push_back(e); } }
+};
+static double conv_flops(const ConvOp& op) {
+  double f = 0;
+  for (int c = 0; c < op.ncls; ++c) f += 2.0 * op.N * op.Hm * op.Wm * (double)op.Nc * op.cls[c].ntaps * op.Kc;
+  return f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // conv dispatch: tcgen05 where the op fits (bf16 mode), FFMA otherwise
 // ---------------------------------------------------------------------------------------------
 static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op) {
   bool can = ctx->dt == DT_BF16 && umma_fwd_supported(op);
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
-  if (can && ctx->engine != GAN_ENGINE_FFMA) launch_conv_fwd_umma(ctx->L(), op);
+  const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
+  ProfScope ps(ctx, um ? FAM_UMMA_FWD : FAM_FFMA_FWD, conv_flops(op));
+  if (um) launch_conv_fwd_umma(ctx->L(), op);
   else launch_conv_fwd_ffma(ctx->L(), ctx->dt, op);
 }
 static void run_conv_wgrad(gan_ctx* ctx, const ConvOp& op) {
   bool can = ctx->dt == DT_BF16 && umma_wgrad_supported(op);
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
-  if (can && ctx->engine != GAN_ENGINE_FFMA) launch_conv_wgrad_umma(ctx->L(), op);
+  const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
+  ProfScope ps(ctx, um ? FAM_UMMA_WGRAD : FAM_FFMA_WGRAD, conv_flops(op));
+  if (um) launch_conv_wgrad_umma(ctx->L(), op);
   else launch_conv_wgrad_ffma(ctx->L(), ctx->dt, op);
 }
 
@@ -212,6 +232,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     op.bias = n->params.as<float>() + ly.bias_off;
     op.epi = ly.act == ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS;
     op.out_f32 = (float*)out.p;
+    ProfScope ps(ctx, FAM_FFMA_FWD, conv_flops(op));
     launch_conv_fwd_ffma(ctx->L(), ctx->dt, op);
     return;
   }
@@ -220,6 +241,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
   run_conv_fwd(ctx, make_op(ly, R_FWD, in, z, ly.wp_fwd.p));
   DropKey dk = drop_key(ctx, ly, s);
+  ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 2 : 3));
   if (ly.norm == NORM_NONE) {
     launch_norm_apply(ctx->L(), ctx->dt, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, ly.act, dk, out.p,
                       out.pitch, out.coff);
@@ -264,6 +286,7 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
     float* dgamma = (gr && ly.norm != NORM_NONE) ? gr + ly.g_off : ctx->junk.as<float>();
     float* dbeta = (gr && ly.norm != NORM_NONE) ? gr + ly.b_off : ctx->junk.as<float>() + 1024;
     if (ly.norm != NORM_NONE) ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
+    ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 3 : 5));
     launch_norm_bwd(ctx->L(), ctx->dt, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
                     st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
                     ctx->stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
@@ -467,9 +490,13 @@ static void adam_apply(gan_adam* o) {
   if (ctx->world > 1) comm_allreduce_sum(ctx, n->grads.as<float>(), n->nparams);
   o->t += 1;
   double lr_t = o->lr * std::sqrt(1.0 - std::pow(o->b2, (double)o->t)) / (1.0 - std::pow(o->b1, (double)o->t));
-  launch_adam(ctx->L(), n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), n->nparams,
-              (float)lr_t, (float)o->b1, (float)o->b2, (float)o->eps, 1.f / (float)ctx->world);
+  {
+    ProfScope ps(ctx, FAM_ADAM, 28.0 * (double)n->nparams);
+    launch_adam(ctx->L(), n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), n->nparams,
+                (float)lr_t, (float)o->b1, (float)o->b2, (float)o->eps, 1.f / (float)ctx->world);
+  }
   n->packed_dirty = true;
+  ProfScope ps(ctx, FAM_PACK, (double)n->nparams * (4.0 + 2.0 * ctx->esize()));
   pack_weights(n);
 }
 static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {
@@ -664,6 +691,27 @@ int gan_ctx_set_engine(gan_ctx* ctx, int engine) { ctx->engine = engine; return 
 int gan_ctx_set_graphs(gan_ctx* ctx, int enabled) { ctx->graphs = enabled; return GAN_OK; }
 int gan_ctx_launch_count(gan_ctx* ctx, uint64_t* out) { *out = ctx->launches; return GAN_OK; }
 int gan_ctx_stream(gan_ctx* ctx, void** out) { *out = (void*)ctx->stream; return GAN_OK; }
+int gan_ctx_set_profile(gan_ctx* ctx, int enabled) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (auto& e : ctx->prof) { ctx->ev_pool.push_back(e.a); ctx->ev_pool.push_back(e.b); }
+  ctx->prof.clear();
+  ctx->profile = enabled;
+  API_END
+}
+int gan_ctx_profile_read(gan_ctx* ctx, double ms[8], double work[8], int64_t count[8]) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < FAM_COUNT; ++i) { ms[i] = 0; work[i] = 0; count[i] = 0; }
+  for (auto& e : ctx->prof) {
+    float t = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&t, e.a, e.b));
+    ms[e.fam] += t; work[e.fam] += e.work; count[e.fam] += 1;
+    ctx->ev_pool.push_back(e.a); ctx->ev_pool.push_back(e.b);
+  }
+  ctx->prof.clear();
+  API_END
+}
 int gan_ctx_set_sample_offset(gan_ctx* ctx, int64_t sample0) { ctx->sample0 = sample0; ctx->sample0_set = true; return GAN_OK; }
 
 int gan_comm_unique_id(void* out128) {

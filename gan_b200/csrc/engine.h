@@ -27,6 +27,11 @@ struct DevBuf {
 
 struct CommApi;   // dlopen'ed NCCL entry points (comm.cu)
 
+// Optional per-kernel-family timing with CUDA events on the ctx stream (bench.py roofline).
+enum { FAM_UMMA_FWD = 0, FAM_UMMA_WGRAD = 1, FAM_FFMA_FWD = 2, FAM_FFMA_WGRAD = 3, FAM_NORM = 4, FAM_ADAM = 5,
+       FAM_PACK = 6, FAM_OTHER = 7, FAM_COUNT = 8 };
+struct ProfEntry { cudaEvent_t a, b; int fam; double work; };
+
 struct gan_ctx {
   int device = 0;
   int dt = DT_F32;
@@ -43,6 +48,14 @@ struct gan_ctx {
   DevBuf stage[4];
   float* loss_host = nullptr;   // pinned
   int n_losses = 0;
+  // profiling
+  int profile = 0;
+  std::vector<ProfEntry> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t ev_get() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); return e;
+  }
   // data parallel
   void* comm = nullptr;
   int rank = 0, world = 1;

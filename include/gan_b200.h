@@ -68,6 +68,11 @@ GAN_API int gan_ctx_set_engine(gan_ctx* ctx, int engine);
 GAN_API int gan_ctx_set_graphs(gan_ctx* ctx, int enabled);
 /* Number of kernels this library launched on ctx since creation (bench: gpu_launches). */
 GAN_API int gan_ctx_launch_count(gan_ctx* ctx, uint64_t* out);
+/* Per-kernel-family timing with CUDA events on the ctx stream (bench.py roofline).  Families:
+ * 0 tcgen05 fwd/dgrad conv, 1 tcgen05 wgrad, 2 FFMA fwd/dgrad conv, 3 FFMA wgrad, 4 norm/activation
+ * fwd+bwd, 5 Adam, 6 weight packing, 7 other.  work[] is algorithmic FLOPs (0-3) or bytes (4-6). */
+GAN_API int gan_ctx_set_profile(gan_ctx* ctx, int enabled);
+GAN_API int gan_ctx_profile_read(gan_ctx* ctx, double ms[8], double work[8], int64_t count[8]);
 /* The stream every call of this ctx is enqueued on (cudaStream_t as void*), for event timing. */
 GAN_API int gan_ctx_stream(gan_ctx* ctx, void** out);
 
