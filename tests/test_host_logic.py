@@ -1,0 +1,88 @@
+"""CPU tests of the host-side logic, including the world_size-2 data-parallel path over gloo."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_and_loss_value():
+    from gan_b200 import shard_bounds, LossValue
+    assert [shard_bounds(64, r, 8) for r in (0, 7)] == [(0, 8), (56, 64)]
+    with pytest.raises(ValueError):
+        shard_bounds(10, 0, 4)
+    v = LossValue(1.5)
+    assert v.numpy().tolist() == 1.5 and isinstance(v.numpy(), np.float32)
+
+
+def test_loss_dict_keys_match_reference():
+    from gan_b200.utils import pix2pix_losses, cyclegan_losses
+    assert list(pix2pix_losses()) == ['Generator Total Loss', 'Generator Loss (Primary)',
+                                      'Generator Loss (Secondary)', 'Discriminator Loss']
+    assert len(cyclegan_losses()) == 7 and 'Total Cycle Loss' in cyclegan_losses()
+
+
+def test_host_bce_matches_oracle():
+    from gan_b200.base_gan import BinaryCrossentropyFromLogits
+    from oracle import gan_oracle as O
+    x = np.random.default_rng(0).normal(size=(2, 30, 30, 1)) * 4
+    f = BinaryCrossentropyFromLogits()
+    assert abs(f(np.ones_like(x), x) - float(O.bce_from_logits(torch.tensor(x), 1.0))) < 1e-12
+    assert abs(f(np.zeros_like(x), x) - float(O.bce_from_logits(torch.tensor(x), 0.0))) < 1e-12
+
+
+def _dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from gan_b200 import exchange_unique_id, shard_bounds
+    from oracle import gan_oracle as O
+    # 1. unique-id plumbing: rank 0's id reaches every rank
+    r, w, uid = exchange_unique_id(make_id=lambda: bytes(range(128)))
+    assert (r, w) == (rank, world) and uid == bytes(range(128))
+    # 2. data-parallel definition: per-shard reference step with identical weights,
+    #    gradients and losses averaged with an all-reduce == oracle's world=2 restatement.
+    rng = np.random.default_rng(5)
+    d_np = O.init_params(O.discriminator_spec(1, True), rng, "batchnorm")
+    B = 4
+    x = O.synthetic_images(rng, B, 32, 32, 1); y = O.synthetic_images(rng, B, 32, 32, 1)
+    lo, hi = shard_bounds(B, rank, world)
+    dp = O.to_torch(d_np)
+    logits = O.discriminator_forward(dp, torch.tensor(x[lo:hi], dtype=torch.float64), torch.tensor(y[lo:hi], dtype=torch.float64))
+    loss = O.bce_from_logits(logits, 1.0)
+    grads = torch.autograd.grad(loss, dp)
+    flat = torch.cat([g.flatten() for g in grads] + [loss.detach().reshape(1)])
+    dist.all_reduce(flat)            # the exchange step of the path: sum over ranks ...
+    flat /= world                    # ... divided by world before Adam
+    if rank == 0:
+        ref_flat = []
+        dp2 = O.to_torch(d_np)
+        acc = None
+        for s in range(world):
+            l2 = O.bce_from_logits(O.discriminator_forward(dp2, torch.tensor(x[s * 2:(s + 1) * 2], dtype=torch.float64),
+                                                           torch.tensor(y[s * 2:(s + 1) * 2], dtype=torch.float64)), 1.0)
+            g2 = torch.autograd.grad(l2, dp2)
+            v = torch.cat([g.flatten() for g in g2] + [l2.detach().reshape(1)])
+            acc = v if acc is None else acc + v
+        q.put(float((flat - acc / world).abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_path_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) < 1e-12
