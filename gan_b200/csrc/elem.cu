@@ -129,7 +129,7 @@ __global__ void k_stats_finalize(const float* __restrict__ ws, int G, int nchunk
   double iv = 1.0 / sqrt(var + (double)eps);
   float sc = (float)((double)gamma[c] * iv);
   mean[i] = (float)m; inv[i] = (float)iv;
-  scale[i] = sc; shift[i] = (float)((double)beta[c] - m * (double)gamma[c] * iv);
+  scale[i] = sc; shift[i] = beta[c];     // u = (z - mean)*scale + beta: exactly beta when z == mean (n == 1)
   if (mov_mean != nullptr) {
     // Keras BatchNormalization moving averages (momentum 0.99); the fused TF kernel feeds the
     // Bessel-corrected variance.  Never read on the hot path (every call is training=True).
@@ -170,7 +170,8 @@ __device__ __forceinline__ float act_bwd(float u, int act) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, int64_t nvec, int64_t Pg, int G, int HW,
-                                                    int C, const float* __restrict__ scale,
+                                                    int C, const float* __restrict__ mean,
+                                                    const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int act, DropKey dk,
                                                     T* __restrict__ out, int out_pitch, int out_coff) {
   constexpr int V = VecIO<T>::N;
@@ -182,8 +183,9 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, int
     if (scale != nullptr) {
       int g = (G == 1) ? 0 : (int)(p / Pg);
       const float* sc = scale + (int64_t)g * C + c0; const float* sh = shift + (int64_t)g * C + c0;
+      const float* mu = mean + (int64_t)g * C + c0;
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] = fmaf(v[k], __ldg(sc + k), __ldg(sh + k));
+      for (int k = 0; k < V; ++k) v[k] = fmaf(v[k] - __ldg(mu + k), __ldg(sc + k), __ldg(sh + k));
     }
     if (dk.enabled) {
       int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
@@ -197,12 +199,12 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, int
 }
 
 void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, int G, int HW, int C,
-                       const float* scale, const float* shift, int act, DropKey dk, void* out, int out_pitch,
-                       int out_coff) {
+                       const float* mean, const float* scale, const float* shift, int act, DropKey dk, void* out,
+                       int out_pitch, int out_coff) {
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     int64_t nvec = P * (C / VecIO<T>::N);
-    k_norm_apply<T><<<grid_for(nvec, 256), 256, 0, L.s>>>((const T*)z, nvec, Pg, G, HW, C, scale, shift, act, dk,
+    k_norm_apply<T><<<grid_for(nvec, 256), 256, 0, L.s>>>((const T*)z, nvec, Pg, G, HW, C, mean, scale, shift, act, dk,
                                                           (T*)out, out_pitch, out_coff);
   });
   KLAUNCH(L);
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
       int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float u = fmaf(v[k], sc[k], sf[k]);
+        float u = fmaf(v[k] - mu[k], sc[k], sf[k]);
         float gg = gr[k] * act_bwd(u, act);
         if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
         float xh = (v[k] - mu[k]) * iv[k];
@@ -318,10 +320,11 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         float sc = __ldg(scale + gi + k);
-        float u = fmaf(v[k], sc, __ldg(shift + gi + k));
+        float xc = v[k] - __ldg(mean + gi + k);
+        float u = fmaf(xc, sc, __ldg(shift + gi + k));
         float gg = gr[k] * act_bwd(u, act);
         if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
-        float xh = (v[k] - __ldg(mean + gi + k)) * __ldg(inv + gi + k);
+        float xh = xc * __ldg(inv + gi + k);
         o[k] = sc * (gg - __ldg(c1 + gi + k) - xh * __ldg(c2 + gi + k));
       }
     }

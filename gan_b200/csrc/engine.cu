@@ -243,7 +243,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   DropKey dk = drop_key(ctx, ly, s);
   ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 2 : 3));
   if (ly.norm == NORM_NONE) {
-    launch_norm_apply(ctx->L(), ctx->dt, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, ly.act, dk, out.p,
+    launch_norm_apply(ctx->L(), ctx->dt, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, nullptr, ly.act, dk, out.p,
                       out.pitch, out.coff);
     return;
   }
@@ -258,7 +258,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   launch_norm_stats(ctx->L(), ctx->dt, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(),
                     ly.norm == NORM_BATCH ? BN_EPS : IN_EPS, pr + ly.g_off, pr + ly.b_off, st, st + gc, st + 2 * gc,
                     st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
-  launch_norm_apply(ctx->L(), ctx->dt, z.p, P, Pg, G, Ho * Wo, ly.Cout, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
+  launch_norm_apply(ctx->L(), ctx->dt, z.p, P, Pg, G, Ho * Wo, ly.Cout, st, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
                     out.pitch, out.coff);
 }
 

@@ -20,6 +20,7 @@ struct DevBuf {
     release();
     CUDA_CHECK(cudaMalloc(&p, n));
     CUDA_CHECK(cudaMemset(p, 0, n));
+    CUDA_CHECK(cudaDeviceSynchronize());   // the memset runs on the legacy stream; ctx streams are non-blocking
     bytes = n;
   }
   template <typename T> T* as() const { return (T*)p; }

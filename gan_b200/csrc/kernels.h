@@ -24,8 +24,8 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
                        float* shift, float* mov_mean, float* mov_var, float momentum);
 // out = act(dropout(z*scale+shift)); scale == nullptr => identity affine (no-norm layers).
 void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, int G, int HW, int C,
-                       const float* scale, const float* shift, int act, DropKey dk, void* out, int out_pitch,
-                       int out_coff);
+                       const float* mean, const float* scale, const float* shift, int act, DropKey dk, void* out,
+                       int out_pitch, int out_coff);
 struct GradSrc { const void* p; int pitch, coff; };
 // Backward of (norm -> dropout -> activation): dz, plus dgamma/dbeta accumulated into the grad buffer.
 void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
