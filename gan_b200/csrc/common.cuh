@@ -43,7 +43,9 @@ struct ConvOp {
   void* out;      int out_pitch, out_coff, Hout, Wout;
   int N, Hm, Wm;                 // M-space extents
   int si, so;                    // input / output pixel stride of the M-space
-  int Kc, Nc;                    // channels per tap (GEMM K = ntaps*Kc), output channels (GEMM N)
+  int Kc, Nc;                    // channels per tap (GEMM K = ntaps*Kc), output channels (GEMM N); may be
+                                 // zero-padded to 16 in bf16 mode so that small-channel layers fit a tcgen05 tile
+  int Kr, Nr;                    // real (unpadded) channel counts: wgrad scatter / bias / fp32 output masks
   int ncls;
   ClassGeom cls[4];
   const void* B;                 // packed weights, dtype = activation dtype

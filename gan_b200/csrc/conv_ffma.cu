@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(256) k_conv_fwd(ConvOp op) {
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n < op.Nc) {
-        float v = epilogue(acc[i][j], op, n);
-        out[pix * op.out_pitch + op.out_coff + n] = from_f<T>(v);
-        if (op.out_f32 != nullptr) op.out_f32[pix * op.Nc + n] = v;
+        float v = n < op.Nr ? epilogue(acc[i][j], op, n) : 0.f;
+        if (out != nullptr) out[pix * op.out_pitch + op.out_coff + n] = from_f<T>(v);
+        if (op.out_f32 != nullptr && n < op.Nr) op.out_f32[pix * op.Nr + n] = v;
       }
     }
   }
@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(256) k_conv_fwd_skinny(ConvOp op) {
 #pragma unroll
       for (int n = 0; n < 8; ++n)
         if (n < op.Nc) {
-          float v = epilogue(acc[n], op, n);
+          float v = n < op.Nr ? epilogue(acc[n], op, n) : 0.f;
           if (out != nullptr) out[pix * op.out_pitch + op.out_coff + n] = from_f<T>(v);
-          if (op.out_f32 != nullptr) op.out_f32[pix * op.Nc + n] = v;
+          if (op.out_f32 != nullptr && n < op.Nr) op.out_f32[pix * op.Nr + n] = v;
         }
     }
   }
@@ -263,10 +263,11 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
     int k = k0 + ty * 4 + i;
     if (k >= K) continue;
     int t = k / op.Kc, c = k - t * op.Kc;
+    if (c >= op.Kr) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
-      if (n < op.Nc) atomicAdd(op.dW + (int64_t)cg.widx[t] * op.s_tap + (int64_t)c * op.s_k + (int64_t)n * op.s_n, acc[i][j]);
+      if (n < op.Nr) atomicAdd(op.dW + (int64_t)cg.widx[t] * op.s_tap + (int64_t)c * op.s_k + (int64_t)n * op.s_n, acc[i][j]);
     }
   }
 }
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits
       }
     }
   }
-  if (c_ok) {
+  if (c_ok && c < op.Kr) {
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll

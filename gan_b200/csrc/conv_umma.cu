@@ -36,31 +36,31 @@ static PFN_encodeTiled g_encode = nullptr;
 // A bf16 NHWC view sampled with pixel stride `s` starting at pixel offset (a,b):
 // dims (C, W/s, H/s, N), box (64, bw, bh, bn), SWIZZLE_128B, OOB -> 0.
 static CUtensorMap make_map4(const void* base, int pitch, int coff, int C, int H, int W, int N, int s, int a, int b,
-                             int bw, int bh, int bn) {
+                             int bw, int bh, int bn, int bc = 64) {
   GAN_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled unavailable");
   CUtensorMap m;
   const char* p = (const char*)base + ((int64_t)(a * W + b) * pitch + coff) * 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)((W - b + s - 1) / s), (cuuint64_t)((H - a + s - 1) / s), (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)s * pitch * 2, (cuuint64_t)s * W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, bc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string((int)r));
   return m;
 }
 // Packed weights [rows][K] K-major: dims (K, rows), box (64, bn).
-static CUtensorMap make_map2(const void* base, int64_t K, int64_t rows, int bn) {
+static CUtensorMap make_map2(const void* base, int64_t K, int64_t rows, int bn, int bk = 64) {
   GAN_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled unavailable");
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
   cuuint32_t es[2] = {1, 1};
   CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(2d) failed: " + std::to_string((int)r));
   return m;
 }
@@ -128,6 +128,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -135,16 +144,23 @@ __device__ __forceinline__ bool elect_one() {
 }
 }  // namespace ptx
 
-// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout).
-// K-major SWIZZLE_128B: rows of 128 B, 8-row atoms of 1024 B => SBO = 1024, LBO unused (1).
-__device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout):
+// start address [0,14) (>>4), LBO [16,30) (>>4), SBO [32,46) (>>4), version=1 [46,48),
+// layout type [61,64): 2 = SWIZZLE_128B, 6 = SWIZZLE_32B.
+//
+// K-major swizzled tile: rows of SW bytes (SW = 128 or 32), 8-row atoms => SBO = 8*SW; LBO unused.
+template <int SW>
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  constexpr uint64_t layout = (SW == 128) ? 2ull : 6ull;
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((8 * SW) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
-// MN-major SWIZZLE_128B: 64 MN elements (128 B) contiguous, 8 k-rows per 1024-B atom => SBO = 1024
-// (next 8 k), LBO = byte distance between consecutive 64-element MN blocks.
-__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+// MN-major swizzled tile: SW bytes of MN contiguous per k-row, 8 k-rows per atom => SBO = 8*SW
+// (next 8 k), LBO = byte distance between consecutive MN blocks of SW bytes.
+template <int SW>
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+  constexpr uint64_t layout = (SW == 128) ? 2ull : 6ull;
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((8 * SW) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16 (InstrDescriptor bit layout).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -153,27 +169,41 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 }
 
 // =============================================================================================
-// forward-type kernel
+// forward-type kernel.  Template: BN = N tile (128 | 64 | 16), KC = channels per TMA box
+// (64: one 128-byte-swizzled box per 64-channel k-block; 16: channel-padded small-Cin layers,
+// four 32-byte-swizzled boxes = four taps per k-block).
 // =============================================================================================
 struct alignas(64) UmmaFwdParams {
   CUtensorMap amap[4];
   CUtensorMap bmap;
   int8_t tap_map[4][16], tap_dw[4][16], tap_dh[4][16];
   int ntaps[4], oa[4], ob[4];
-  int kchunks;                 // Kc / 64
+  int kchunks;                 // Kc / 64 (KC == 64)
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;
   bf16* out; int out_pitch, out_coff, Hout, Wout, so;
   int N, Hm, Wm, Nc;
+  const float* bias; float* out_f32; int epi, Nr;
 };
 
 constexpr int FWD_STAGES = 3;
 constexpr int FWD_THREADS = 192;     // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 
-template <int BN>
+__device__ __forceinline__ float epi_apply(float v, int epi, const float* bias, int n) {
+  if (epi != EPI_NONE) v += __ldg(bias + n);
+  if (epi == EPI_BIAS_TANH) v = tanhf(v);
+  return v;
+}
+
+template <int BN, int KC>
 __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_constant__ UmmaFwdParams p) {
-  constexpr uint32_t A_BYTES = 128 * 128;          // 128 rows x 64 bf16
+  constexpr int SW = (KC == 64) ? 128 : 32;
+  constexpr int SUB = 64 / KC;                       // TMA boxes (taps) per 64-element k-block
+  constexpr uint32_t A_SUB = 128 * KC * 2;           // bytes of one A box
+  constexpr uint32_t B_SUB = BN * KC * 2;
+  constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + FWD_STAGES * STAGE_BYTES);
@@ -189,7 +219,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   const int th_i = tm % p.tiles_h; tm /= p.tiles_h;
   const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tm * p.TN;
   const int ntaps = p.ntaps[cls];
-  const int nk = ntaps * p.kchunks;
+  const int nk = (KC == 64) ? ntaps * p.kchunks : ntaps / SUB;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.bmap);
@@ -200,7 +230,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
     ptx::mbar_init(tmem_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, BN);
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -212,11 +242,21 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
         const int s = kb % FWD_STAGES;
         const uint32_t ph = (kb / FWD_STAGES) & 1;
         ptx::mbar_wait(&empty[s], ph ^ 1);
-        const int t = kb / p.kchunks, kc = kb - t * p.kchunks;
         uint8_t* sa = smem + s * STAGE_BYTES;
         ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
-        ptx::tma_load_4d(sa, &p.amap[p.tap_map[cls][t]], &full[s], kc * 64, w0 + p.tap_dw[cls][t], h0 + p.tap_dh[cls][t], b0);
-        ptx::tma_load_2d(sa + A_BYTES, &p.bmap, &full[s], kb * 64, cls * p.Nc + n0);
+        if (KC == 64) {
+          const int t = kb / p.kchunks, kc = kb - t * p.kchunks;
+          ptx::tma_load_4d(sa, &p.amap[p.tap_map[cls][t]], &full[s], kc * 64, w0 + p.tap_dw[cls][t], h0 + p.tap_dh[cls][t], b0);
+          ptx::tma_load_2d(sa + A_BYTES, &p.bmap, &full[s], kb * 64, cls * p.Nc + n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < SUB; ++j) {
+            const int t = kb * SUB + j;
+            ptx::tma_load_4d(sa + j * A_SUB, &p.amap[p.tap_map[cls][t]], &full[s], 0, w0 + p.tap_dw[cls][t],
+                             h0 + p.tap_dh[cls][t], b0);
+            ptx::tma_load_2d(sa + A_BYTES + j * B_SUB, &p.bmap, &full[s], t * KC, cls * p.Nc + n0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -228,10 +268,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t ad = desc_kmajor_sw128(sa), bd = desc_kmajor_sw128(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)     // 4 x (K=16) per 64-channel block: +32 B inside the swizzle atom
-          ptx::umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k) {
+          // KC==64: +32 B inside the 128-byte swizzle atom per K=16; KC==16: one 32-byte-swizzled box per K=16
+          const uint64_t ad = (KC == 64) ? desc_kmajor<SW>(sa) + 2 * k : desc_kmajor<SW>(sa + k * A_SUB);
+          const uint64_t bd = (KC == 64) ? desc_kmajor<SW>(sa + A_BYTES) + 2 * k : desc_kmajor<SW>(sa + A_BYTES + k * B_SUB);
+          ptx::umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+        }
         ptx::umma_commit(&empty[s]);
         if (kb == nk - 1) ptx::umma_commit(tmem_full);
       }
@@ -244,29 +287,52 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
     const int mw = w0 + wl, mh = h0 + hl, nb = b0 + nl;
     const int oh = mh * p.so + p.oa[cls], ow = mw * p.so + p.ob[cls];
     const bool valid = nb < p.N && mh < p.Hm && mw < p.Wm && oh < p.Hout && ow < p.Wout;
-    bf16* dst = p.out + (((int64_t)nb * p.Hout + oh) * p.Wout + ow) * p.out_pitch + p.out_coff + n0;
+    const int64_t pix = ((int64_t)nb * p.Hout + oh) * p.Wout + ow;
+    bf16* dst = p.out + pix * p.out_pitch + p.out_coff + n0;
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
+    if (BN >= 32) {
 #pragma unroll
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(dst + c + j * 8) = o;
+          }
+        }
+      }
+    } else {
+      // N = 16 tile: channel-padded heads (fp32 output with bias / tanh) and padded data gradients
+      uint32_t v[16];
+      ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), v);
       if (valid) {
+        if (p.out_f32 != nullptr) {
+          for (int n = 0; n < p.Nr; ++n) p.out_f32[pix * p.Nr + n] = epi_apply(__uint_as_float(v[n]), p.epi, p.bias, n);
+        }
+        if (p.out != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+          for (int j = 0; j < 2; ++j) {
+            uint4 o;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
-          *reinterpret_cast<uint4*>(dst + c + j * 8) = o;
+            for (int e = 0; e < 4; ++e)
+              h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(dst + j * 8) = o;
+          }
         }
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, BN);
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 static size_t fwd_smem_bytes(int BN) { return (size_t)FWD_STAGES * (128 * 128 + BN * 128) + 1024 + 128; }
@@ -274,84 +340,113 @@ static size_t fwd_smem_bytes(int BN) { return (size_t)FWD_STAGES * (128 * 128 + 
 static bool view_ok(int pitch, int coff, const void* p) {
   return pitch % 8 == 0 && coff % 8 == 0 && ((uintptr_t)p % 16) == 0;
 }
+static bool chan_ok(int c) { return c == 16 || (c >= 64 && c % 64 == 0); }
 
 bool umma_fwd_supported(const ConvOp& op) {
   if (g_encode == nullptr) return false;
-  if (op.Kc % 64 != 0 || op.Nc % 64 != 0) return false;
-  if (!view_ok(op.in_pitch, op.in_coff, op.in) || !view_ok(op.out_pitch, op.out_coff, op.out)) return false;
-  if (op.epi != EPI_NONE || op.out_f32 != nullptr) return false;
+  if (!chan_ok(op.Kc) || !chan_ok(op.Nc)) return false;
+  if (op.Kc == 16 && op.Nc == 16) return false;
+  if (op.Kc == 16 && op.cls[0].ntaps % 4 != 0) return false;
+  if (!view_ok(op.in_pitch, op.in_coff, op.in)) return false;
+  if (op.out != nullptr && !view_ok(op.out_pitch, op.out_coff, op.out)) return false;
+  if (op.out == nullptr && op.out_f32 == nullptr) return false;
+  if ((op.epi != EPI_NONE || op.out_f32 != nullptr) && op.Nc != 16) return false;
   if (op.si == 2 && (op.Hin % 2 != 0 || op.Win % 2 != 0)) return false;
   return true;
 }
 
-static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile) {
+static void fill_tap_tables(const ConvOp& op, int8_t (*tap_map)[16], int8_t (*tap_dw)[16], int8_t (*tap_dh)[16]) {
+  for (int c = 0; c < op.ncls; ++c) {
+    const ClassGeom& g = op.cls[c];
+    for (int t = 0; t < g.ntaps; ++t) {
+      if (op.si == 1) { tap_map[c][t] = 0; tap_dh[c][t] = g.dh[t]; tap_dw[c][t] = g.dw[t]; }
+      else {
+        int a = ((g.dh[t] % 2) + 2) % 2, b = ((g.dw[t] % 2) + 2) % 2;
+        tap_map[c][t] = (int8_t)(a * 2 + b);
+        tap_dh[c][t] = (int8_t)((g.dh[t] - a) / 2); tap_dw[c][t] = (int8_t)((g.dw[t] - b) / 2);
+      }
+    }
+  }
+}
+static void fill_in_maps(CUtensorMap* maps, const ConvOp& op, int bw, int bh, int bn, int bc) {
+  if (op.si == 1) {
+    maps[0] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 1, 0, 0, bw, bh, bn, bc);
+    for (int i = 1; i < 4; ++i) maps[i] = maps[0];
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        maps[a * 2 + b] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 2, a, b, bw, bh, bn, bc);
+  }
+}
+
+static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile, int kc) {
   memset(&P, 0, sizeof(P));
   int TW = pow2ceil(op.Wm); if (TW > 128) TW = 128;
   int TH = pow2ceil(op.Hm); if (TH > 128 / TW) TH = 128 / TW;
   int TN = 128 / (TW * TH);
   P.TW = TW; P.TH = TH; P.TN = TN;
   P.tiles_w = (op.Wm + TW - 1) / TW; P.tiles_h = (op.Hm + TH - 1) / TH; P.tiles_n = (op.N + TN - 1) / TN;
-  if (op.si == 1) {
-    P.amap[0] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 1, 0, 0, TW, TH, TN);
-    for (int i = 1; i < 4; ++i) P.amap[i] = P.amap[0];
-  } else {
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b)
-        P.amap[a * 2 + b] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 2, a, b, TW, TH, TN);
-  }
+  fill_in_maps(P.amap, op, TW, TH, TN, kc);
   int64_t Ktot = (int64_t)op.cls[0].ntaps * op.Kc;
-  P.bmap = make_map2(op.B, Ktot, (int64_t)op.ncls * op.Nc, bn_tile);
-  for (int c = 0; c < op.ncls; ++c) {
-    const ClassGeom& g = op.cls[c];
-    P.ntaps[c] = g.ntaps; P.oa[c] = g.oa; P.ob[c] = g.ob;
-    for (int t = 0; t < g.ntaps; ++t) {
-      if (op.si == 1) { P.tap_map[c][t] = 0; P.tap_dh[c][t] = g.dh[t]; P.tap_dw[c][t] = g.dw[t]; }
-      else {
-        int a = ((g.dh[t] % 2) + 2) % 2, b = ((g.dw[t] % 2) + 2) % 2;
-        P.tap_map[c][t] = (int8_t)(a * 2 + b);
-        P.tap_dh[c][t] = (int8_t)((g.dh[t] - a) / 2); P.tap_dw[c][t] = (int8_t)((g.dw[t] - b) / 2);
-      }
-    }
-  }
+  P.bmap = make_map2(op.B, Ktot, (int64_t)op.ncls * op.Nc, bn_tile, kc);
+  fill_tap_tables(op, P.tap_map, P.tap_dw, P.tap_dh);
+  for (int c = 0; c < op.ncls; ++c) { P.ntaps[c] = op.cls[c].ntaps; P.oa[c] = op.cls[c].oa; P.ob[c] = op.cls[c].ob; }
   P.kchunks = op.Kc / 64;
   P.out = (bf16*)op.out; P.out_pitch = op.out_pitch; P.out_coff = op.out_coff; P.Hout = op.Hout; P.Wout = op.Wout; P.so = op.so;
   P.N = op.N; P.Hm = op.Hm; P.Wm = op.Wm; P.Nc = op.Nc;
+  P.bias = op.bias; P.out_f32 = op.out_f32; P.epi = op.epi; P.Nr = op.Nr;
 }
 
 void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
-  const int BN = (op.Nc % 128 == 0) ? 128 : 64;
+  const int BN = (op.Nc % 128 == 0) ? 128 : (op.Nc % 64 == 0 ? 64 : 16);
+  const int KC = op.Kc == 16 ? 16 : 64;
   UmmaFwdParams P;
-  fill_fwd_params(P, op, BN);
+  fill_fwd_params(P, op, BN, KC);
   dim3 grid(P.tiles_w * P.tiles_h * P.tiles_n, op.Nc / BN, op.ncls);
-  if (BN == 128) k_conv_fwd_umma<128><<<grid, FWD_THREADS, fwd_smem_bytes(128), L.s>>>(P);
-  else k_conv_fwd_umma<64><<<grid, FWD_THREADS, fwd_smem_bytes(64), L.s>>>(P);
+  const size_t sm = fwd_smem_bytes(BN);
+  if (KC == 64) {
+    if (BN == 128) k_conv_fwd_umma<128, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
+    else if (BN == 64) k_conv_fwd_umma<64, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
+    else k_conv_fwd_umma<16, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
+  } else {
+    if (BN == 128) k_conv_fwd_umma<128, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
+    else k_conv_fwd_umma<64, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
+  }
   KLAUNCH(L);
 }
 
 // =============================================================================================
-// weight-gradient kernel
+// weight-gradient kernel.  Template: BN = N tile over dY channels (128 | 64 | 16),
+// KCA = channels per A box (64 | 16).  A rows = 128 consecutive entries of the (tap, channel)
+// index space = 128/KCA boxes; both operands MN-major, GEMM-K = pixels.
 // =============================================================================================
 struct alignas(64) UmmaWgradParams {
-  CUtensorMap amap[4];     // input activation boxes (64 ch x PW x PH x PN), parity sub-lattices when si == 2
+  CUtensorMap amap[4];     // input activation boxes (KCA ch x PW x PH x PN), parity sub-lattices when si == 2
   CUtensorMap dmap[4];     // dY boxes, parity sub-lattices when so == 2
   int8_t tap_map[4][16], tap_dw[4][16], tap_dh[4][16], widx[4][16];
   int ntaps[4], dy_map[4];
-  int Kc, kc_blocks;       // channels per tap, Kc/64
+  int Kc;                  // (padded) channels per tap
   int PW, PH, PN, tiles_w, tiles_h, tiles_n;   // 64-pixel boxes over the M-space
   int splits;
   float* dW; long long s_tap, s_k, s_n;
-  int Nc;
+  int Nc, Kr, Nr;
 };
 
 constexpr int WG_STAGES = 3;
 constexpr int WG_PIX = 64;            // pixels (GEMM-K) per stage
 
-template <int BN>
+template <int BN, int KCA>
 __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_constant__ UmmaWgradParams p) {
-  constexpr uint32_t BOX_BYTES = WG_PIX * 128;            // 64 pixels x 64 channels bf16
-  constexpr uint32_t A_BYTES = 2 * BOX_BYTES;             // 128 (tap,kc) rows
-  constexpr uint32_t B_BYTES = (BN / 64) * BOX_BYTES;
+  constexpr int SWA = (KCA == 64) ? 128 : 32;
+  constexpr int SWB = (BN >= 64) ? 128 : 32;
+  constexpr int NA = 128 / KCA;                               // A boxes per stage
+  constexpr int NB = (BN >= 64) ? BN / 64 : 1;                // dY boxes per stage
+  constexpr uint32_t A_BOX = WG_PIX * KCA * 2;
+  constexpr uint32_t B_BOX = WG_PIX * ((BN >= 64) ? 64 : 16) * 2;
+  constexpr uint32_t A_BYTES = NA * A_BOX;                    // 16 KB
+  constexpr uint32_t B_BYTES = NB * B_BOX;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + WG_STAGES * STAGE_BYTES);
@@ -363,7 +458,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
   const int cls = (int)(blockIdx.z / p.splits);
   const int split = blockIdx.z % p.splits;
   const int n0 = blockIdx.y * BN;
-  const int kblk0 = blockIdx.x * 2;                        // two 64-row blocks of the (tap,kc) index space
+  const int kbase = blockIdx.x * 128;                         // first (tap,channel) index of this M tile
   const int total_boxes = p.tiles_w * p.tiles_h * p.tiles_n;
   const int per = (total_boxes + p.splits - 1) / p.splits;
   const int box_beg = split * per;
@@ -378,7 +473,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
     ptx::mbar_init(tmem_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, BN);
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -387,8 +482,9 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
   if (nk > 0) {
     if (warp == 0) {
       if (lane == 0) {
-        int t_[2], c_[2];
-        for (int i = 0; i < 2; ++i) { int k = (kblk0 + i) * 64; t_[i] = k / p.Kc; c_[i] = k - t_[i] * p.Kc; }
+        int t_[NA], c_[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) { int k = kbase + i * KCA; t_[i] = k / p.Kc; c_[i] = k - t_[i] * p.Kc; }
         for (int kb = 0; kb < nk; ++kb) {
           const int s = kb % WG_STAGES;
           const uint32_t ph = (kb / WG_STAGES) & 1;
@@ -400,12 +496,12 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
           uint8_t* sa = smem + s * STAGE_BYTES;
           ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            ptx::tma_load_4d(sa + i * BOX_BYTES, &p.amap[p.tap_map[cls][t_[i]]], &full[s], c_[i],
+          for (int i = 0; i < NA; ++i)
+            ptx::tma_load_4d(sa + i * A_BOX, &p.amap[p.tap_map[cls][t_[i]]], &full[s], c_[i],
                              w0 + p.tap_dw[cls][t_[i]], h0 + p.tap_dh[cls][t_[i]], b0);
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i)
-            ptx::tma_load_4d(sa + A_BYTES + i * BOX_BYTES, &p.dmap[p.dy_map[cls]], &full[s], n0 + i * 64, w0, h0, b0);
+          for (int i = 0; i < NB; ++i)
+            ptx::tma_load_4d(sa + A_BYTES + i * B_BOX, &p.dmap[p.dy_map[cls]], &full[s], n0 + i * 64, w0, h0, b0);
         }
       }
     } else if (warp == 1) {
@@ -417,10 +513,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t ad = desc_mnmajor_sw128(sa, BOX_BYTES), bd = desc_mnmajor_sw128(sa + A_BYTES, BOX_BYTES);
+          const uint64_t ad = desc_mnmajor<SWA>(sa, A_BOX), bd = desc_mnmajor<SWB>(sa + A_BYTES, B_BOX);
 #pragma unroll
-          for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels (2 atoms of 8 k-rows = 2048 B) per MMA
-            ptx::umma_bf16(tmem_base, ad + (uint64_t)(k * 2048 >> 4), bd + (uint64_t)(k * 2048 >> 4), idesc, (kb | k) != 0);
+          for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels = two 8-row atoms per MMA
+            ptx::umma_bf16(tmem_base, ad + (uint64_t)((k * 16 * SWA) >> 4), bd + (uint64_t)((k * 16 * SWB) >> 4), idesc,
+                           (kb | k) != 0);
           ptx::umma_commit(&empty[s]);
           if (kb == nk - 1) ptx::umma_commit(tmem_full);
         }
@@ -428,31 +525,50 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
       }
     } else {
       const int q = warp & 3;
-      const int r = q * 32 + lane;                   // accumulator row = (tap,kc) index inside the 128 block
-      const int k = kblk0 * 64 + r;
+      const int r = q * 32 + lane;                   // accumulator row = (tap,channel) index inside the tile
+      const int k = kbase + r;
       const int t = k / p.Kc, kc = k - t * p.Kc;
+      const bool row_ok = kc < p.Kr;
       float* dst = p.dW + (long long)p.widx[cls][t] * p.s_tap + (long long)kc * p.s_k + (long long)n0 * p.s_n;
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
+      if (BN >= 32) {
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+          if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + (long long)(c + j) * p.s_n, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < p.Nr) atomicAdd(dst + (long long)(c + j) * p.s_n, __uint_as_float(v[j]));
+          }
+        }
+      } else {
+        uint32_t v[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < p.Nr) atomicAdd(dst + (long long)j * p.s_n, __uint_as_float(v[j]));
+        }
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, BN);
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-static size_t wg_smem_bytes(int BN) { return (size_t)WG_STAGES * ((2 + BN / 64) * WG_PIX * 128) + 1024 + 128; }
+static size_t wg_smem_bytes(int BN) {
+  size_t b = BN >= 64 ? (size_t)(BN / 64) * WG_PIX * 128 : (size_t)WG_PIX * 32;
+  return (size_t)WG_STAGES * (16384 + b) + 1024 + 128;
+}
 
 bool umma_wgrad_supported(const ConvOp& op) {
   if (g_encode == nullptr) return false;
-  if (op.Kc % 64 != 0 || op.Nc % 64 != 0) return false;
+  if (!chan_ok(op.Kc) || !chan_ok(op.Nc)) return false;
+  if (op.Kc == 16 && op.Nc == 16) return false;
+  if ((op.cls[0].ntaps * op.Kc) % 128 != 0) return false;
   if (!view_ok(op.in_pitch, op.in_coff, op.in) || !view_ok(op.out_pitch, op.out_coff, op.out)) return false;
   if (op.si == 2 && (op.Hin % 2 != 0 || op.Win % 2 != 0)) return false;
   if (op.so == 2 && (op.Hout % 2 != 0 || op.Wout % 2 != 0)) return false;
@@ -460,45 +576,33 @@ bool umma_wgrad_supported(const ConvOp& op) {
 }
 
 void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
-  const int BN = (op.Nc % 128 == 0) ? 128 : 64;
+  const int BN = (op.Nc % 128 == 0) ? 128 : (op.Nc % 64 == 0 ? 64 : 16);
+  const int KCA = op.Kc == 16 ? 16 : 64;
   UmmaWgradParams P; memset(&P, 0, sizeof(P));
   int PW = pow2ceil(op.Wm); if (PW > WG_PIX) PW = WG_PIX;
   int PH = pow2ceil(op.Hm); if (PH > WG_PIX / PW) PH = WG_PIX / PW;
   int PN = WG_PIX / (PW * PH);
   P.PW = PW; P.PH = PH; P.PN = PN;
   P.tiles_w = (op.Wm + PW - 1) / PW; P.tiles_h = (op.Hm + PH - 1) / PH; P.tiles_n = (op.N + PN - 1) / PN;
-  if (op.si == 1) {
-    P.amap[0] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 1, 0, 0, PW, PH, PN);
-    for (int i = 1; i < 4; ++i) P.amap[i] = P.amap[0];
-  } else {
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b)
-        P.amap[a * 2 + b] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 2, a, b, PW, PH, PN);
-  }
+  fill_in_maps(P.amap, op, PW, PH, PN, KCA);
+  const int bcn = BN >= 64 ? 64 : 16;
   if (op.so == 1) {
-    P.dmap[0] = make_map4(op.out, op.out_pitch, op.out_coff, op.Nc, op.Hout, op.Wout, op.N, 1, 0, 0, PW, PH, PN);
+    P.dmap[0] = make_map4(op.out, op.out_pitch, op.out_coff, op.Nc, op.Hout, op.Wout, op.N, 1, 0, 0, PW, PH, PN, bcn);
     for (int i = 1; i < 4; ++i) P.dmap[i] = P.dmap[0];
   } else {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
-        P.dmap[a * 2 + b] = make_map4(op.out, op.out_pitch, op.out_coff, op.Nc, op.Hout, op.Wout, op.N, 2, a, b, PW, PH, PN);
+        P.dmap[a * 2 + b] = make_map4(op.out, op.out_pitch, op.out_coff, op.Nc, op.Hout, op.Wout, op.N, 2, a, b, PW, PH, PN, bcn);
   }
+  fill_tap_tables(op, P.tap_map, P.tap_dw, P.tap_dh);
   for (int c = 0; c < op.ncls; ++c) {
     const ClassGeom& g = op.cls[c];
     P.ntaps[c] = g.ntaps;
     P.dy_map[c] = op.so == 1 ? 0 : g.oa * 2 + g.ob;
-    for (int t = 0; t < g.ntaps; ++t) {
-      P.widx[c][t] = g.widx[t];
-      if (op.si == 1) { P.tap_map[c][t] = 0; P.tap_dh[c][t] = g.dh[t]; P.tap_dw[c][t] = g.dw[t]; }
-      else {
-        int a = ((g.dh[t] % 2) + 2) % 2, b = ((g.dw[t] % 2) + 2) % 2;
-        P.tap_map[c][t] = (int8_t)(a * 2 + b);
-        P.tap_dh[c][t] = (int8_t)((g.dh[t] - a) / 2); P.tap_dw[c][t] = (int8_t)((g.dw[t] - b) / 2);
-      }
-    }
+    for (int t = 0; t < g.ntaps; ++t) P.widx[c][t] = g.widx[t];
   }
-  P.Kc = op.Kc; P.kc_blocks = op.Kc / 64;
-  P.dW = op.dW; P.s_tap = op.s_tap; P.s_k = op.s_k; P.s_n = op.s_n; P.Nc = op.Nc;
+  P.Kc = op.Kc;
+  P.dW = op.dW; P.s_tap = op.s_tap; P.s_k = op.s_k; P.s_n = op.s_n; P.Nc = op.Nc; P.Kr = op.Kr; P.Nr = op.Nr;
   const int ntaps = op.cls[0].ntaps;
   const int mblocks = ntaps * op.Kc / 128;
   const int ntiles = op.Nc / BN;
@@ -509,8 +613,15 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   if (splits < 1) splits = 1;
   P.splits = splits;
   dim3 grid(mblocks, ntiles, op.ncls * splits);
-  if (BN == 128) k_conv_wgrad_umma<128><<<grid, FWD_THREADS, wg_smem_bytes(128), L.s>>>(P);
-  else k_conv_wgrad_umma<64><<<grid, FWD_THREADS, wg_smem_bytes(64), L.s>>>(P);
+  const size_t sm = wg_smem_bytes(BN);
+  if (KCA == 64) {
+    if (BN == 128) k_conv_wgrad_umma<128, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
+    else if (BN == 64) k_conv_wgrad_umma<64, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
+    else k_conv_wgrad_umma<16, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
+  } else {
+    if (BN == 128) k_conv_wgrad_umma<128, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
+    else k_conv_wgrad_umma<64, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
+  }
   KLAUNCH(L);
 }
 
@@ -522,9 +633,17 @@ void umma_init() {
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (PFN_encodeTiled)fn;
     else cudaGetLastError();
-    cudaFuncSetAttribute(k_conv_fwd_umma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes(128));
-    cudaFuncSetAttribute(k_conv_fwd_umma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes(64));
-    cudaFuncSetAttribute(k_conv_wgrad_umma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem_bytes(128));
-    cudaFuncSetAttribute(k_conv_wgrad_umma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem_bytes(64));
+#define SET_SMEM(K, B) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B))
+    SET_SMEM((k_conv_fwd_umma<128, 64>), fwd_smem_bytes(128));
+    SET_SMEM((k_conv_fwd_umma<64, 64>), fwd_smem_bytes(64));
+    SET_SMEM((k_conv_fwd_umma<16, 64>), fwd_smem_bytes(16));
+    SET_SMEM((k_conv_fwd_umma<128, 16>), fwd_smem_bytes(128));
+    SET_SMEM((k_conv_fwd_umma<64, 16>), fwd_smem_bytes(64));
+    SET_SMEM((k_conv_wgrad_umma<128, 64>), wg_smem_bytes(128));
+    SET_SMEM((k_conv_wgrad_umma<64, 64>), wg_smem_bytes(64));
+    SET_SMEM((k_conv_wgrad_umma<16, 64>), wg_smem_bytes(16));
+    SET_SMEM((k_conv_wgrad_umma<128, 16>), wg_smem_bytes(128));
+    SET_SMEM((k_conv_wgrad_umma<64, 16>), wg_smem_bytes(64));
+#undef SET_SMEM
   });
 }

@@ -358,7 +358,7 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
 template <typename T>
 __global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out, const float* __restrict__ ref, GradSrc d1,
                                                    GradSrc d2, float l1_coef, int64_t total, int C, T* __restrict__ dz,
-                                                   float* dbias) {
+                                                   int dz_pitch, float* dbias) {
   __shared__ float sh[8];
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // C <= 4
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out
     }
     float g = d * (1.f - o * o);
     T gq = from_f<T>(g);
-    dz[i] = gq;
+    dz[p * dz_pitch + c] = gq;
     float gf = to_f(gq);
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (c == k) bsum[k] += gf;
@@ -391,12 +391,12 @@ __global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out
   }
 }
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
-                      float l1_coef, int64_t P, int C, void* dz, float* dbias) {
+                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias) {
   GAN_REQUIRE(C <= 4, "generator head supports up to 4 output channels");
   int64_t total = P * C;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_ghead_bwd<T><<<grid_for(total, 256, 4), 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dbias);
+    k_ghead_bwd<T><<<grid_for(total, 256, 4), 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dz_pitch, dbias);
   });
   KLAUNCH(L);
 }
@@ -419,7 +419,7 @@ __device__ __forceinline__ void block_partial_store(float v, float* dst) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_t n, float label, float coef_over_n,
-                                             T* dz, float* dbias, float* __restrict__ loss_slot) {
+                                             T* dz, int dz_pitch, float* dbias, float* __restrict__ loss_slot) {
   float acc = 0.f, bacc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
     if (dz != nullptr) {
       float sg = 1.f / (1.f + expf(-v));
       T q = from_f<T>(coef_over_n * (sg - label));
-      dz[i] = q;
+      dz[i * dz_pitch] = q;
       bacc += to_f(q);
     }
   }
@@ -445,13 +445,13 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
     }
   }
 }
-void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, float* dbias,
-                float* loss_ws, int slot) {
+void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
+                float* dbias, float* loss_ws, int slot) {
   int blocks = grid_for(n, 256, 1);
   if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dbias, loss_ws + slot * LOSS_BLOCKS);
+    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dz_pitch, dbias, loss_ws + slot * LOSS_BLOCKS);
   });
   KLAUNCH(L);
 }
@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(256) k_pack(const float* __restrict__ master, 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t n = i / K; int64_t k = i - n * K;
     int t = (int)(k / op.Kc); int kc = (int)(k - (int64_t)t * op.Kc);
-    dst[cg.b_off + i] = from_f<T>(master[(int64_t)cg.widx[t] * op.s_tap + (int64_t)kc * op.s_k + n * op.s_n]);
+    float v = (kc < op.Kr && n < op.Nr) ? master[(int64_t)cg.widx[t] * op.s_tap + (int64_t)kc * op.s_k + n * op.s_n] : 0.f;
+    dst[cg.b_off + i] = from_f<T>(v);
   }
 }
 void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op) {

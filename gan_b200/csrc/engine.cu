@@ -65,20 +65,26 @@ static int fill_geometry(int kind, int role, ClassGeom* cls) {
   return 4;
 }
 
-// Master-weight strides for (tap, K-channel, N-channel) of a role.
-static void weight_strides(const Layer& ly, int role, int& Kc, int& Nc, int64_t& s_tap, int64_t& s_k, int64_t& s_n) {
+// Small channel counts are stored zero-padded to 16 in bf16 mode so that every layer fits a
+// tcgen05 tile (first layers Cin in {1,2,3,6}: base_gan.py:141,180; heads Cout in {1,3}: :159,:201).
+static int pad_c(const gan_ctx* ctx, int c) { return (ctx->dt == DT_BF16 && c < 16) ? 16 : c; }
+
+// Master-weight strides for (tap, K-channel, N-channel) of a role; Kc/Nc are the stored (padded)
+// GEMM channel counts, Kr/Nr the real ones.
+static void weight_strides(const Layer& ly, int role, int& Kc, int& Nc, int& Kr, int& Nr, int64_t& s_tap, int64_t& s_k,
+                           int64_t& s_n) {
   s_tap = (int64_t)ly.Cin * ly.Cout;
   bool transposed_master = (ly.kind == K_CONVT_S2);   // (kh,kw,out,in) instead of (kh,kw,in,out)
   int64_t s_in = transposed_master ? 1 : ly.Cout, s_out = transposed_master ? ly.Cin : 1;
-  if (role == R_DGRAD) { Kc = ly.Cout; Nc = ly.Cin; s_k = s_out; s_n = s_in; }
-  else { Kc = ly.Cin; Nc = ly.Cout; s_k = s_in; s_n = s_out; }
+  if (role == R_DGRAD) { Kc = ly.Cout_p; Nc = ly.Cin_p; Kr = ly.Cout; Nr = ly.Cin; s_k = s_out; s_n = s_in; }
+  else { Kc = ly.Cin_p; Nc = ly.Cout_p; Kr = ly.Cin; Nr = ly.Cout; s_k = s_in; s_n = s_out; }
 }
 
 // x: layer-input-side view (N,Hin,Win,Cin); y: layer-output-side view (N,Hout,Wout,Cout).
 static ConvOp make_op(const Layer& ly, int role, View x, View y, const void* wpack) {
   ConvOp op; memset(&op, 0, sizeof(op));
   op.ncls = fill_geometry(ly.kind, role, op.cls);
-  weight_strides(ly, role, op.Kc, op.Nc, op.s_tap, op.s_k, op.s_n);
+  weight_strides(ly, role, op.Kc, op.Nc, op.Kr, op.Nr, op.s_tap, op.s_k, op.s_n);
   View src = (role == R_DGRAD) ? y : x, dst = (role == R_DGRAD) ? x : y;
   op.in = src.p; op.in_pitch = src.pitch; op.in_coff = src.coff; op.Hin = src.H; op.Win = src.W;
   op.out = dst.p; op.out_pitch = dst.pitch; op.out_coff = dst.coff; op.Hout = dst.H; op.Wout = dst.W;
@@ -155,6 +161,7 @@ static void add_layer(gan_net* n, const std::string& name, int kind, int Cin, in
                       bool dropout, int tag, bool head) {
   Layer ly; ly.name = name; ly.kind = kind; ly.Cin = Cin; ly.Cout = Cout; ly.norm = norm; ly.act = act;
   ly.bias = bias; ly.dropout = dropout; ly.tag = tag; ly.head = head;
+  ly.Cin_p = pad_c(n->ctx, Cin); ly.Cout_p = pad_c(n->ctx, Cout);
   ly.w_off = n->nparams;
   if (kind == K_CONVT_S2) add_tensor(n, name + ".kernel", {4, 4, Cout, Cin}, n->nparams, true);
   else add_tensor(n, name + ".kernel", {4, 4, Cin, Cout}, n->nparams, true);
@@ -198,10 +205,10 @@ static void pack_weights(gan_net* n) {
       if (role == R_DGRAD && !ly.need_dgrad) continue;
       PackOp po; memset(&po, 0, sizeof(po));
       po.ncls = fill_geometry(ly.kind, role, po.cls);
-      weight_strides(ly, role, po.Kc, po.Nc, po.s_tap, po.s_k, po.s_n);
+      weight_strides(ly, role, po.Kc, po.Nc, po.Kr, po.Nr, po.s_tap, po.s_k, po.s_n);
       for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
       DevBuf& dst = role == R_FWD ? ly.wp_fwd : ly.wp_dgrad;
-      dst.ensure((size_t)16 * ly.Cin * ly.Cout * ctx->esize());
+      dst.ensure((size_t)16 * ly.Cin_p * ly.Cout_p * ctx->esize());
       launch_pack(ctx->L(), ctx->dt, n->params.as<float>() + ly.w_off, dst.p, po);
     }
   }
@@ -227,13 +234,12 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   s.in_views[li] = in; s.out_views[li] = out;
   if (ly.head) {
     // generator head: bias + tanh -> fp32 image; discriminator head: bias -> fp32 logits
-    View y = make_view(nullptr, B, Ho, Wo, ly.Cout);
+    View y = make_view(nullptr, B, Ho, Wo, ly.Cout_p);
     ConvOp op = make_op(ly, R_FWD, in, y, ly.wp_fwd.p);
     op.bias = n->params.as<float>() + ly.bias_off;
     op.epi = ly.act == ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS;
     op.out_f32 = (float*)out.p;
-    ProfScope ps(ctx, FAM_FFMA_FWD, conv_flops(op));
-    launch_conv_fwd_ffma(ctx->L(), ctx->dt, op);
+    run_conv_fwd(ctx, op);
     return;
   }
   int64_t P = (int64_t)B * Ho * Wo;
@@ -273,7 +279,7 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
   const int64_t P = (int64_t)B * Ho * Wo;
   View dz;
   if (ly.head) {
-    dz = make_view((void*)d1.p, B, Ho, Wo, ly.Cout, d1.pitch, d1.coff);
+    dz = make_view((void*)d1.p, B, Ho, Wo, ly.Cout_p, d1.pitch, d1.coff);
   } else {
     ctx->dz_scratch.ensure((size_t)P * ly.Cout * ctx->esize());
     dz = make_view(ctx->dz_scratch.p, B, Ho, Wo, ly.Cout);
@@ -326,15 +332,16 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   s.sample0 = ctx->sample0_set ? ctx->sample0 : (int64_t)ctx->rank * B;
   const size_t es = ctx->esize();
   const int C = g->C;
-  s.xin.ensure((size_t)B * H * W * C * es);
-  launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, C, 0);
+  const int Cp = g->Cp;
+  s.xin.ensure((size_t)B * H * W * Cp * es);
+  launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
   // concat buffers: cat[k-1] = [up_k output (UP_F[k-1]) | down_{8-k} output (DOWN_F[7-k])] at H/2^(8-k)
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
     s.cat[k - 1].ensure((size_t)B * hs * ws * (UP_F[k - 1] + DOWN_F[7 - k]) * es);
   }
   s.d8.ensure((size_t)B * (H >> 8) * (W >> 8) * 512 * es);
-  View in = make_view(s.xin.p, B, H, W, C);
+  View in = make_view(s.xin.p, B, H, W, Cp);
   for (int j = 1; j <= 8; ++j) {
     int hs = H >> j, ws = W >> j;
     View out;
@@ -364,8 +371,9 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   const size_t es = ctx->esize();
   float* gr = g->grads.as<float>();
   // head
-  s.dlogit.ensure((size_t)B * H * W * C * es);
-  launch_ghead_bwd(ctx->L(), ctx->dt, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p,
+  const int Cp = g->Cp;
+  s.dlogit.ensure((size_t)B * H * W * Cp * es);
+  launch_ghead_bwd(ctx->L(), ctx->dt, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
                    gr + g->layers[15].bias_off);
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
@@ -374,7 +382,7 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   {
     int pitch = UP_F[6] + DOWN_F[0];
     View din = make_view(s.dcat[6].p, B, H / 2, W / 2, pitch);
-    layer_backward(g, s, 15, GradSrc{s.dlogit.p, C, 0}, GradSrc{nullptr, 0, 0}, din, true);
+    layer_backward(g, s, 15, GradSrc{s.dlogit.p, Cp, 0}, GradSrc{nullptr, 0, 0}, din, true);
   }
   s.dd8.ensure((size_t)B * (H >> 8) * (W >> 8) * 512 * es);
   for (int k = 7; k >= 1; --k) {
@@ -393,12 +401,12 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
       a = GradSrc{s.dskip[j].p, DOWN_F[j - 1], 0};                              // from down_{j+1} dgrad
       b = GradSrc{s.dcat[k - 1].p, UP_F[k - 1] + DOWN_F[j - 1], UP_F[k - 1]};   // skip half of the concat gradient
     }
-    View din = make_view(nullptr, B, H >> (j - 1), W >> (j - 1), j > 1 ? DOWN_F[j - 2] : C);
+    View din = make_view(nullptr, B, H >> (j - 1), W >> (j - 1), j > 1 ? DOWN_F[j - 2] : Cp);
     if (j > 1) {
       s.dskip[j - 1].ensure((size_t)B * din.H * din.W * din.C * es);
       din.p = s.dskip[j - 1].p;
     } else if (want_input_grad) {
-      s.dxin.ensure((size_t)B * H * W * C * es);
+      s.dxin.ensure((size_t)B * H * W * Cp * es);
       din.p = s.dxin.p;
     }
     layer_backward(g, s, j - 1, a, b, din, true);
@@ -414,7 +422,7 @@ static void discriminator_forward(gan_net* d, int slot, const float* inp, const 
   Slot& s = d->slots[slot];
   slot_prepare(d, s, B, H, W);
   const size_t es = ctx->esize();
-  const int C = d->C, C0 = d->Cin0;
+  const int C = d->C, C0 = d->Cin0_p;
   s.in0.ensure((size_t)B * H * W * C0 * es);
   launch_convert(ctx->L(), ctx->dt, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
   if (tar) launch_convert(ctx->L(), ctx->dt, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
@@ -442,7 +450,7 @@ static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool w
     View din = make_view(nullptr, B, in.H, in.W, in.C);
     if (li > 0) { s.dact[li - 1].ensure((size_t)B * in.H * in.W * in.C * es); din.p = s.dact[li - 1].p; }
     else if (want_input_grad) { s.din0.ensure((size_t)B * in.H * in.W * in.C * es); din.p = s.din0.p; }
-    GradSrc src = (li == 4) ? GradSrc{s.dlogit.p, 1, 0} : GradSrc{s.dact[li].p, d->layers[li].Cout, 0};
+    GradSrc src = (li == 4) ? GradSrc{s.dlogit.p, d->layers[4].Cout_p, 0} : GradSrc{s.dact[li].p, d->layers[li].Cout, 0};
     layer_backward(d, s, li, src, GradSrc{nullptr, 0, 0}, din, want_wgrad);
   }
 }
@@ -454,8 +462,9 @@ static void disc_bce(gan_net* d, int slot, float label, float coef, bool make_dz
   gan_ctx* ctx = d->ctx;
   Slot& s = d->slots[slot];
   int64_t n = logits_count(s);
-  if (make_dz) s.dlogit.ensure((size_t)n * ctx->esize());
-  launch_bce(ctx->L(), ctx->dt, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr,
+  const int dzp = d->layers[4].Cout_p;
+  if (make_dz) s.dlogit.ensure((size_t)n * dzp * ctx->esize());
+  launch_bce(ctx->L(), ctx->dt, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr, dzp,
              (make_dz && bias_grad) ? d->grads.as<float>() + d->layers[4].bias_off : nullptr, ctx->loss_ws.as<float>(),
              loss_slot);
 }
@@ -549,7 +558,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   disc_bce(d, 1, 1.f, 1.0f, training, false, 0);
   if (training) {
     discriminator_backward(d, 1, false, true);                           // dL_G/d(gen_output) through D (:210)
-    GradSrc dgan{d->slots[1].din0.p, 2 * C, C};
+    GradSrc dgan{d->slots[1].din0.p, d->Cin0_p, C};
     generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, lambda / (float)n_img, false);
     adam_apply(go);                                                      // (:213)
     adam_apply(dopt);                                                    // (:215)
@@ -615,8 +624,8 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
     const float lc = lambda / (float)n_img;
     generator_backward(f, 0, none, none, x, lc, true);                                   // cycle x: through F into fake_y
     generator_backward(g, 1, none, none, y, lc, true);                                   // cycle y: through G into fake_x
-    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, C, 0}, GradSrc{f->slots[0].dxin.p, C, 0}, nullptr, 0.f, false);
-    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, C, 0}, GradSrc{g->slots[1].dxin.p, C, 0}, nullptr, 0.f, false);
+    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->Cin0_p, 0}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false);
+    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, dx->Cin0_p, 0}, GradSrc{g->slots[1].dxin.p, g->Cp, 0}, nullptr, 0.f, false);
     generator_backward(f, 2, none, none, x, 0.5f * lc, false);                           // identity x (:244)
     generator_backward(g, 2, none, none, y, 0.5f * lc, false);                           // identity y (:243)
     adam_apply(og); adam_apply(of); adam_apply(odx); adam_apply(ody);                    // (:263-273)
@@ -736,6 +745,7 @@ int gan_generator_create(gan_ctx* ctx, int norm_type, int height, int width, int
   CUDA_CHECK(cudaSetDevice(ctx->device));
   gan_net* n = new gan_net();
   n->ctx = ctx; n->is_gen = true; n->norm = norm_type; n->H = height; n->W = width; n->C = channels; n->Cin0 = channels;
+  n->Cp = pad_c(ctx, channels); n->Cin0_p = n->Cp;
   int cin = channels;
   for (int j = 1; j <= 8; ++j) {            // downsample blocks, first without norm (base_gan.py:179-188)
     add_layer(n, "down" + std::to_string(j), K_CONV_S2, cin, DOWN_F[j - 1], j == 1 ? NORM_NONE : norm_type, ACT_LEAKY, false,
@@ -761,6 +771,7 @@ int gan_discriminator_create(gan_ctx* ctx, int norm_type, int channels, int targ
   gan_net* n = new gan_net();
   n->ctx = ctx; n->is_gen = false; n->norm = norm_type; n->C = channels; n->target = target != 0;
   n->Cin0 = target ? 2 * channels : channels;
+  n->Cp = pad_c(ctx, channels); n->Cin0_p = pad_c(ctx, n->Cin0);
   add_layer(n, "down1", K_CONV_S2, n->Cin0, 64, NORM_NONE, ACT_LEAKY, false, false, 0, false);   // base_gan.py:141
   add_layer(n, "down2", K_CONV_S2, 64, 128, norm_type, ACT_LEAKY, false, false, 0, false);       // :142
   add_layer(n, "down3", K_CONV_S2, 128, 256, norm_type, ACT_LEAKY, false, false, 0, false);      // :143
@@ -850,7 +861,7 @@ int gan_net_debug_tensor(gan_net* net, int slot, const char* name, float* host_d
   const void* src = nullptr; int pitch = 0, coff = 0, C = 0; int64_t P = 0; bool is_f32 = false;
   if (nm == "out" && net->is_gen) { src = s.out_f32.p; C = net->C; P = (int64_t)s.B * s.H * s.W; pitch = C; is_f32 = true; }
   else if (nm == "logits" && !net->is_gen) { src = s.logits.p; C = 1; P = logits_count(s); pitch = 1; is_f32 = true; }
-  else if (nm == "din0" && !net->is_gen) { src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = C; }
+  else if (nm == "din0" && !net->is_gen) { src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = net->Cin0_p; }
   else {
     size_t dot = nm.rfind('.');
     GAN_REQUIRE(dot != std::string::npos, "debug tensor name must be <layer>.z or <layer>.a");
@@ -971,8 +982,11 @@ int gan_op_conv(gan_ctx* ctx, int kind, int role, int engine, const float* a, co
   GAN_REQUIRE(kind >= 0 && kind <= 2 && role >= 0 && role <= 2, "bad kind/role");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   Layer ly; ly.name = "op"; ly.kind = kind; ly.Cin = cin; ly.Cout = cout; ly.norm = NORM_NONE; ly.act = ACT_NONE;
+  const int cin_p = pad_c(ctx, cin), cout_p = pad_c(ctx, cout);
+  ly.Cin_p = cin_p; ly.Cout_p = cout_p;
   int Ho, Wo; out_dims(kind, height, width, Ho, Wo);
-  const int64_t nx = (int64_t)batch * height * width * cin, ny = (int64_t)batch * Ho * Wo * cout, nw = 16LL * cin * cout;
+  const int64_t px = (int64_t)batch * height * width, py = (int64_t)batch * Ho * Wo;
+  const int64_t nx = px * cin, ny = py * cout, nw = 16LL * cin * cout;
   const size_t es = ctx->esize();
   DevBuf fa, fb, fo, xa, ya, wp;
   Launch L = ctx->L();
@@ -982,39 +996,39 @@ int gan_op_conv(gan_ctx* ctx, int kind, int role, int engine, const float* a, co
       stage.ensure((size_t)n * 4);
       CUDA_CHECK(cudaMemcpyAsync(stage.p, h, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     };
-    View x = make_view(nullptr, batch, height, width, cin), y = make_view(nullptr, batch, Ho, Wo, cout);
-    xa.ensure((size_t)nx * es); ya.ensure((size_t)ny * es);
+    View x = make_view(nullptr, batch, height, width, cin_p), y = make_view(nullptr, batch, Ho, Wo, cout_p);
+    xa.ensure((size_t)px * cin_p * es); ya.ensure((size_t)py * cout_p * es);
     x.p = xa.p; y.p = ya.p;
     if (role != R_WGRAD) {
       // pack the kernel for this role
       up(fb, b, nw);
       PackOp po; memset(&po, 0, sizeof(po));
       po.ncls = fill_geometry(kind, role, po.cls);
-      weight_strides(ly, role, po.Kc, po.Nc, po.s_tap, po.s_k, po.s_n);
+      weight_strides(ly, role, po.Kc, po.Nc, po.Kr, po.Nr, po.s_tap, po.s_k, po.s_n);
       for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
-      wp.ensure((size_t)nw * es);
+      wp.ensure((size_t)16 * cin_p * cout_p * es);
       launch_pack(L, ctx->dt, fb.as<float>(), wp.p, po);
       if (role == R_FWD) {
         up(fa, a, nx);
-        launch_convert(L, ctx->dt, fa.as<float>(), nx / cin, cin, x.p, cin, 0);
+        launch_convert(L, ctx->dt, fa.as<float>(), px, cin, x.p, cin_p, 0);
         run_conv_fwd(ctx, make_op(ly, R_FWD, x, y, wp.p));
         fo.ensure((size_t)ny * 4);
-        launch_export(L, ctx->dt, y.p, cout, 0, ny / cout, cout, fo.as<float>());
+        launch_export(L, ctx->dt, y.p, cout_p, 0, py, cout, fo.as<float>());
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         CUDA_CHECK(cudaMemcpy(out, fo.p, ny * 4, cudaMemcpyDeviceToHost));
       } else {
         up(fa, a, ny);
-        launch_convert(L, ctx->dt, fa.as<float>(), ny / cout, cout, y.p, cout, 0);
+        launch_convert(L, ctx->dt, fa.as<float>(), py, cout, y.p, cout_p, 0);
         run_conv_fwd(ctx, make_op(ly, R_DGRAD, x, y, wp.p));
         fo.ensure((size_t)nx * 4);
-        launch_export(L, ctx->dt, x.p, cin, 0, nx / cin, cin, fo.as<float>());
+        launch_export(L, ctx->dt, x.p, cin_p, 0, px, cin, fo.as<float>());
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         CUDA_CHECK(cudaMemcpy(out, fo.p, nx * 4, cudaMemcpyDeviceToHost));
       }
     } else {
       up(fa, a, nx); up(fb, b, ny);
-      launch_convert(L, ctx->dt, fa.as<float>(), nx / cin, cin, x.p, cin, 0);
-      launch_convert(L, ctx->dt, fb.as<float>(), ny / cout, cout, y.p, cout, 0);
+      launch_convert(L, ctx->dt, fa.as<float>(), px, cin, x.p, cin_p, 0);
+      launch_convert(L, ctx->dt, fb.as<float>(), py, cout, y.p, cout_p, 0);
       fo.ensure((size_t)nw * 4);
       CUDA_CHECK(cudaMemsetAsync(fo.p, 0, nw * 4, ctx->stream));
       ConvOp op = make_op(ly, R_WGRAD, x, y, nullptr);

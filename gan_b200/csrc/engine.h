@@ -76,6 +76,7 @@ struct TensorInfo {
 struct Layer {
   std::string name;
   int kind, Cin, Cout, norm, act;
+  int Cin_p = 0, Cout_p = 0;     // channel counts as stored (zero-padded to 16 in bf16 mode when < 16)
   bool bias = false, dropout = false, need_dgrad = true, head = false;
   int tag = 0;
   int64_t w_off = -1, g_off = -1, b_off = -1, bias_off = -1, mov_off = -1;
@@ -101,7 +102,7 @@ struct Slot {
 struct gan_net {
   gan_ctx* ctx = nullptr;
   bool is_gen = false;
-  int norm = NORM_BATCH, H = 0, W = 0, C = 0, Cin0 = 0;
+  int norm = NORM_BATCH, H = 0, W = 0, C = 0, Cin0 = 0, Cp = 0, Cin0_p = 0;
   bool target = false;
   std::vector<Layer> layers;
   std::vector<TensorInfo> tensors;

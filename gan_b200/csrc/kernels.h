@@ -33,17 +33,17 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz);
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
-                      float l1_coef, int64_t P, int C, void* dz, float* dbias);
+                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias);
 // BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
-void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, float* dbias,
-                float* loss_ws, int slot);
+void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
+                float* dbias, float* loss_ws, int slot);
 void launch_l1(Launch L, const float* a, const float* b, int64_t n, float* loss_ws, int slot);
 // raw[j] = sum(slot j)/denom[j]; out[i] = sum_j mix[i*nraw+j]*raw[j]
 struct LossMix { int nraw, nout; float denom[LOSS_SLOTS]; float mix[8 * LOSS_SLOTS]; };
 void launch_loss_finalize(Launch L, const float* loss_ws, LossMix mix, float* out);
 void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
                  float eps, float gscale);
-struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc; int64_t s_tap, s_k, s_n; };
+struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc, Kr, Nr; int64_t s_tap, s_k, s_n; };   // Kc/Nc padded, Kr/Nr real
 void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op);
 void launch_scale(Launch L, float* p, int64_t n, float s);
 

@@ -102,3 +102,24 @@ def test_umma_wgrad_matches_oracle(ctx16, kind, b, h, w, cin, cout):
     _, dw_ref = oracle_conv_grads(kind, xq, wq, dyq)
     dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=1)
     assert rel_err(dw, dw_ref) < 1e-4
+
+
+SMALLC = [  # first layers (Cin in {1,3,6}) and heads (Cout in {1,3}): channel-padded tcgen05 paths
+    (0, 2, 16, 16, 3, 64), (0, 1, 32, 32, 6, 64), (0, 2, 16, 16, 1, 64),
+    (1, 2, 8, 8, 64, 1), (1, 1, 16, 16, 512, 1), (1, 2, 31, 31, 128, 1),
+    (2, 2, 8, 8, 128, 3), (2, 1, 8, 8, 128, 1), (2, 3, 16, 16, 64, 3),
+]
+
+
+@pytest.mark.parametrize("kind,b,h,w,cin,cout", SMALLC)
+def test_umma_small_channel_layers(ctx16, kind, b, h, w, cin, cout):
+    x, wt, dy = _case(kind, b, h, w, cin, cout, seed=6)
+    xq, wq, dyq = bf16_round(x), bf16_round(wt), bf16_round(dy)
+    y_ref = oracle_conv(kind, xq, wq).numpy()
+    dx_ref, dw_ref = oracle_conv_grads(kind, xq, wq, dyq)
+    y = ctx16.op_conv(kind, 0, x, wt, b, h, w, cin, cout, engine=1)
+    dx = ctx16.op_conv(kind, 1, dy, wt, b, h, w, cin, cout, engine=1)
+    dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=1)
+    assert rel_err(y, y_ref) < 6e-3
+    assert rel_err(dx, dx_ref) < 6e-3
+    assert rel_err(dw, dw_ref) < 1e-4

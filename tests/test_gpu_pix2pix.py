@@ -34,16 +34,21 @@ def _inputs(b, size, c, seed=SEED):
     return O.synthetic_images(rng, b, size, size, c), O.synthetic_images(rng, b, size, size, c)
 
 
-def _check_tensors(names, dev, ref, tol, what):
-    worst = 0.0
+def _check_tensors(names, dev, ref, tol, what, atol=0.0):
+    """Per-tensor max|dev-ref| <= tol*max|ref| + atol; reports every offending tensor at once."""
+    bad, worst = [], 0.0
     for n, a, r in zip(names, dev, ref):
         r = r.detach().numpy() if hasattr(r, "detach") else np.asarray(r)
         if np.abs(r).max() == 0.0:
-            assert np.abs(a).max() < 1e-10, f"{what} {n}: oracle is exactly zero, device is not"
+            if np.abs(a).max() >= 1e-10:
+                bad.append((n, "oracle exactly zero", float(np.abs(a).max())))
             continue
-        e = rel_err(a, r)
-        worst = max(worst, e)
-        assert e < tol, f"{what} {n}: rel err {e:.3e} >= {tol}"
+        err = float(np.abs(np.asarray(a, dtype=np.float64) - r).max())
+        den = float(np.abs(r).max())
+        worst = max(worst, err / den)
+        if err > tol * den + atol:
+            bad.append((n, f"{err / den:.3e}"))
+    assert not bad, f"{what}: {len(bad)}/{len(names)} tensors out of tolerance: {bad}"
     return worst
 
 
@@ -63,8 +68,10 @@ def test_fp32_step_matches_oracle(batch, channels):
             assert abs(float(a) - r) <= 1e-4 * max(1.0, abs(r)), (step, list(map(float, losses)), ref_losses)
         _check_tensors(names_g, [v.grad() for v in m.generator.trainable_variables], gg, 1e-4, f"step{step} dG")
         _check_tensors(names_d, [v.grad() for v in m.discriminator.trainable_variables], dg, 1e-4, f"step{step} dD")
-        _check_tensors(names_g, m.generator.get_weights(), gp, 1e-4, f"step{step} G")
-        _check_tensors(names_d, m.discriminator.get_weights(), dp, 1e-4, f"step{step} D")
+        # post-Adam weights: the first Keras-Adam update is lr*g/(|g|+1e-7), a sign-like function of
+        # gradients as small as eps, so allow 0.5% of one lr-sized step on top of the 1e-4 relative bound
+        _check_tensors(names_g, m.generator.get_weights(), gp, 1e-4, f"step{step} G", atol=5e-3 * 2e-4)
+        _check_tensors(names_d, m.discriminator.get_weights(), dp, 1e-4, f"step{step} D", atol=5e-3 * 2e-4)
     assert m.generator_optimizer.iterations == 2 and m.discriminator_optimizer.iterations == 2
     m.ctx.close()
 
