@@ -8,11 +8,19 @@
 // One ConvOp covers Conv2D 4x4 s2 'same' (base_gan.py:78), ZeroPad+Conv2D 4x4 s1 (base_gan.py:145-148),
 // Conv2DTranspose 4x4 s2 'same' as four parity-class 2x2 correlations (base_gan.py:107), and the
 // data-gradients of all three (which are the same shapes with the channel roles swapped).
+#include <type_traits>
 #include "kernels.h"
 
 #define KLAUNCH(L) (++*(L).count)
 
 namespace {
+
+// Accumulator type: the fp32 precision mode accumulates in double so that the only roundings left
+// are those of the stored fp32 operands/results (the step's gradients are badly conditioned: conv
+// weight gradients in front of a normalisation layer are small residuals of large cancelling sums);
+// the bf16 mode accumulates in fp32 like the tensor cores do.
+template <typename T> struct Acc { typedef float type; };
+template <> struct Acc<float> { typedef double type; };
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
@@ -61,11 +69,12 @@ __global__ void __launch_bounds__(256) k_conv_fwd(ConvOp op) {
   const int bn = n0 + brow;
 
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  typedef typename Acc<T>::type acc_t;
+  acc_t acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
 
   for (int k0 = 0; k0 < K; k0 += BK) {
     float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(ConvOp op) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] += (acc_t)a[i] * (acc_t)b[j];
     }
     __syncthreads();
   }
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(ConvOp op) {
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n < op.Nc) {
-        float v = n < op.Nr ? epilogue(acc[i][j], op, n) : 0.f;
+        float v = n < op.Nr ? epilogue((float)acc[i][j], op, n) : 0.f;
         if (out != nullptr) out[pix * op.out_pitch + op.out_coff + n] = from_f<T>(v);
         if (op.out_f32 != nullptr && n < op.Nr) op.out_f32[pix * op.Nr + n] = v;
       }
@@ -145,9 +154,10 @@ __global__ void __launch_bounds__(256) k_conv_fwd_skinny(ConvOp op) {
   const T* __restrict__ in = (const T*)op.in;
   const T* __restrict__ Bw = (const T*)op.B + cg.b_off;
   int mw = (int)(m % op.Wm); int64_t r = m / op.Wm; int mh = (int)(r % op.Hm); int n_img = (int)(r / op.Hm);
-  float acc[8];
+  typedef typename Acc<T>::type acc_t;
+  acc_t acc[8];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  for (int n = 0; n < 8; ++n) acc[n] = 0;
   for (int t = 0; t < cg.ntaps; ++t) {
     int ih = mh * op.si + cg.dh[t], iw = mw * op.si + cg.dw[t];
     if (ih < 0 || ih >= op.Hin || iw < 0 || iw >= op.Win) continue;
@@ -157,11 +167,13 @@ __global__ void __launch_bounds__(256) k_conv_fwd_skinny(ConvOp op) {
       float a = to_f(ip[c]);
 #pragma unroll
       for (int n = 0; n < 8; ++n)
-        if (n < op.Nc) acc[n] = fmaf(a, to_f(bp[(int64_t)n * K + c]), acc[n]);
+        if (n < op.Nc) acc[n] += (acc_t)a * (acc_t)to_f(bp[(int64_t)n * K + c]);
     }
   }
 #pragma unroll
-  for (int n = 0; n < 8; ++n) acc[n] = warp_sum(acc[n]);
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
   if (lane == 0) {
     int oh = mh * op.so + cg.oa, ow = mw * op.so + cg.ob;
     if (oh < op.Hout && ow < op.Wout) {
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd_skinny(ConvOp op) {
 #pragma unroll
       for (int n = 0; n < 8; ++n)
         if (n < op.Nc) {
-          float v = n < op.Nr ? epilogue(acc[n], op, n) : 0.f;
+          float v = n < op.Nr ? epilogue((float)acc[n], op, n) : 0.f;
           if (out != nullptr) out[pix * op.out_pitch + op.out_coff + n] = from_f<T>(v);
           if (op.out_f32 != nullptr && n < op.Nr) op.out_f32[pix * op.Nr + n] = v;
         }
@@ -206,11 +218,12 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
     if (k < K) { a_t[e] = k / op.Kc; a_c[e] = k - a_t[e] * op.Kc; } else { a_t[e] = -1; a_c[e] = 0; }
   }
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  typedef typename Acc<T>::type acc_t;
+  acc_t acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
 
   for (int64_t mb = mbeg; mb < mend; mb += 16) {
     float av[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] += (acc_t)a[i] * (acc_t)b[j];
     }
     __syncthreads();
   }
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
-      if (n < op.Nr) atomicAdd(op.dW + (int64_t)cg.widx[t] * op.s_tap + (int64_t)c * op.s_k + (int64_t)n * op.s_n, acc[i][j]);
+      if (n < op.Nr) atomicAdd(op.dW + (int64_t)cg.widx[t] * op.s_tap + (int64_t)c * op.s_k + (int64_t)n * op.s_n, (float)acc[i][j]);
     }
   }
 }
@@ -284,11 +297,12 @@ __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits
   const int64_t mbeg = blockIdx.y * per, mend = (mbeg + per < M) ? mbeg + per : M;
   const T* __restrict__ in = (const T*)op.in;
   const T* __restrict__ dy = (const T*)op.out;
-  float acc[NT][NC];
+  typedef typename Acc<T>::type acc_t;
+  acc_t acc[NT][NC];
 #pragma unroll
   for (int t = 0; t < NT; ++t)
 #pragma unroll
-    for (int n = 0; n < NC; ++n) acc[t][n] = 0.f;
+    for (int n = 0; n < NC; ++n) acc[t][n] = 0;
   const bool c_ok = c < op.Kc;
   for (int64_t m = mbeg; m < mend; ++m) {
     int mw = (int)(m % op.Wm); int64_t r = m / op.Wm; int mh = (int)(r % op.Hm); int n_img = (int)(r / op.Hm);
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits
       if (c_ok && ih >= 0 && ih < op.Hin && iw >= 0 && iw < op.Win) {
         float a = to_f(in[(((int64_t)n_img * op.Hin + ih) * op.Win + iw) * op.in_pitch + op.in_coff + c]);
 #pragma unroll
-        for (int n = 0; n < NC; ++n) acc[t][n] = fmaf(a, d[n], acc[t][n]);
+        for (int n = 0; n < NC; ++n) acc[t][n] += (acc_t)a * (acc_t)d[n];
       }
     }
   }
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits
     for (int t = 0; t < NT; ++t)
 #pragma unroll
       for (int n = 0; n < NC; ++n)
-        atomicAdd(op.dW + (int64_t)cg.widx[t] * op.s_tap + (int64_t)c * op.s_k + (int64_t)n * op.s_n, acc[t][n]);
+        atomicAdd(op.dW + (int64_t)cg.widx[t] * op.s_tap + (int64_t)c * op.s_k + (int64_t)n * op.s_n, (float)acc[t][n]);
   }
 }
 

@@ -61,42 +61,29 @@ void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64
 }
 
 // ---------------------------------------------------------------------------------------------
-// Normalisation statistics.  z is compact [G*Pg][C]; group g covers rows [g*Pg,(g+1)*Pg).
-// Stage 1: each block reduces a chunk of rows to per-channel (sum, sumsq) in fp32.
-// Stage 2: chunks are combined in double; mean / inv-std / fused scale+shift are emitted.
+// Normalisation kernels.  z is compact [G*Pg][C]; group g covers rows [g*Pg,(g+1)*Pg) (G == 1:
+// BatchNorm, G == N: InstanceNorm).  C is a power of two >= 64 for every normalised layer, so a
+// thread owns ONE channel vector (V = 8 bf16 / 4 fp32 channels) for its whole lifetime: the
+// per-channel parameters sit in registers, index math is shifts, and each thread keeps UNR
+// independent 128-bit loads in flight (HBM-bound: bytes in flight per SM is what matters).
 // ---------------------------------------------------------------------------------------------
+#define NORM_UNR 4
+
 int stats_chunks(int G, int64_t Pg) {
-  int64_t want = (STATS_MAX_CHUNKS + G - 1) / G;         // fill ~4 waves of 148 SMs across all groups
-  int64_t maxc = (Pg + 31) / 32;                         // at least 32 rows per chunk
+  int64_t want = (2 * STATS_MAX_CHUNKS + G - 1) / G;     // ~8 CTAs per SM across all groups
+  int64_t maxc = (Pg + 63) / 64;                         // at least 64 rows per chunk
   int64_t c = want < maxc ? want : maxc;
   return (int)(c < 1 ? 1 : c);
 }
 size_t stats_ws_floats(int G, int64_t Pg, int C) { return (size_t)G * stats_chunks(G, Pg) * 2 * C; }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, int64_t Pg, int C, int nchunk,
-                                                       float* __restrict__ ws) {
-  constexpr int V = VecIO<T>::N;
-  __shared__ float sh_s[256 * V];
-  __shared__ float sh_q[256 * V];
-  const int g = blockIdx.y, chunk = blockIdx.x;
-  const int cv = C / V;
+static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// Block-level column reduction of per-thread vectors (threads with equal `col` own the same channels).
+template <int V>
+__device__ __forceinline__ void block_col_reduce(const float (&s)[V], const float (&q)[V], int cv, int C, float* sh_s,
+                                                 float* sh_q, float* __restrict__ out) {
   const int rows_par = 256 / cv;
-  const int col = threadIdx.x % cv, r = threadIdx.x / cv;
-  const int64_t per = (Pg + nchunk - 1) / nchunk;
-  const int64_t p0 = chunk * per, p1 = (p0 + per < Pg) ? p0 + per : Pg;
-  float s[V], q[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  if (r < rows_par) {
-    const T* base = z + ((int64_t)g * Pg) * C + col * V;
-    for (int64_t p = p0 + r; p < p1; p += rows_par) {
-      float v[V];
-      VecIO<T>::load(base + p * C, v);
-#pragma unroll
-      for (int i = 0; i < V; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
-    }
-  }
 #pragma unroll
   for (int i = 0; i < V; ++i) { sh_s[threadIdx.x * V + i] = s[i]; sh_q[threadIdx.x * V + i] = q[i]; }
   __syncthreads();
@@ -106,9 +93,45 @@ __global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, 
       int t = rr * cv + c / V;
       S += sh_s[t * V + c % V]; Q += sh_q[t * V + c % V];
     }
-    float* o = ws + ((int64_t)(g * nchunk + chunk) * 2) * C;
-    o[c] = S; o[C + c] = Q;
+    out[c] = S; out[C + c] = Q;
   }
+}
+
+// Stage 1 of the moments: per-chunk (sum, sumsq) per channel in fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, uint32_t Pg, int C, int lcv, int nchunk,
+                                                       float* __restrict__ ws) {
+  constexpr int V = VecIO<T>::N;
+  __shared__ float sh_s[256 * V];
+  __shared__ float sh_q[256 * V];
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int cv = 1 << lcv;
+  const uint32_t rows_par = 256u >> lcv;
+  const int col = threadIdx.x & (cv - 1);
+  const uint32_t r = threadIdx.x >> lcv;
+  const uint32_t per = (Pg + nchunk - 1) / nchunk;
+  const uint32_t p0 = chunk * per, p1 = min(Pg, p0 + per);
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  const T* base = z + ((size_t)g * Pg) * C + col * V;
+  for (uint32_t p = p0 + r; p < p1; p += rows_par * NORM_UNR) {
+    float v[NORM_UNR][V];
+#pragma unroll
+    for (int u = 0; u < NORM_UNR; ++u) {
+      uint32_t pp = p + u * rows_par;
+      if (pp < p1) VecIO<T>::load(base + (size_t)pp * C, v[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NORM_UNR; ++u)
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+  }
+  block_col_reduce<V>(s, q, cv, C, sh_s, sh_q, ws + ((size_t)(g * nchunk + chunk) * 2) * C);
 }
 
 __global__ void k_stats_finalize(const float* __restrict__ ws, int G, int nchunk, int C, double n, float eps,
@@ -145,7 +168,9 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
   int nchunk = stats_chunks(G, Pg);
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_stats_partial<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, Pg, C, nchunk, ws);
+    const int cv = C / VecIO<T>::N;
+    GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256, "normalised channel count must be a power of two");
+    k_stats_partial<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, (uint32_t)Pg, C, ilog2(cv), nchunk, ws);
   });
   KLAUNCH(L);
   k_stats_finalize<<<(G * C + 127) / 128, 128, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, eps, gamma, beta, mean, inv,
@@ -154,7 +179,7 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
 }
 
 // ---------------------------------------------------------------------------------------------
-// out = act(dropout(z*scale + shift)) written into the consumer's (concat-offset) view.
+// out = act(dropout((z-mean)*scale + shift)) written into the consumer's (concat-offset) view.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float act_fwd(float u, int act) {
   if (act == ACT_LEAKY) return u > 0.f ? u : LEAKY_SLOPE * u;
@@ -168,34 +193,67 @@ __device__ __forceinline__ float act_bwd(float u, int act) {
   return 1.f;
 }
 
+template <int V>
+struct ChanParams { float mu[V], sc[V], sf[V]; };
+
+template <int V>
+__device__ __forceinline__ void load_chan_params(ChanParams<V>& cp, const float* mean, const float* scale,
+                                                 const float* shift, size_t off) {
+#pragma unroll
+  for (int k = 0; k < V; ++k) { cp.mu[k] = __ldg(mean + off + k); cp.sc[k] = __ldg(scale + off + k); cp.sf[k] = __ldg(shift + off + k); }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, int64_t nvec, int64_t Pg, int G, int HW,
-                                                    int C, const float* __restrict__ mean,
-                                                    const float* __restrict__ scale,
-                                                    const float* __restrict__ shift, int act, DropKey dk,
-                                                    T* __restrict__ out, int out_pitch, int out_coff) {
+__global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uint32_t P, uint32_t Pg, int G, uint32_t HW,
+                                                    int C, int lcv, const float* __restrict__ mean,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                    int act, DropKey dk, T* __restrict__ out, int out_pitch, int out_coff) {
   constexpr int V = VecIO<T>::N;
-  const int cv = C / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = i / cv; int c0 = (int)(i - p * cv) * V;
-    float v[V];
-    VecIO<T>::load(z + p * C + c0, v);
-    if (scale != nullptr) {
-      int g = (G == 1) ? 0 : (int)(p / Pg);
-      const float* sc = scale + (int64_t)g * C + c0; const float* sh = shift + (int64_t)g * C + c0;
-      const float* mu = mean + (int64_t)g * C + c0;
+  const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
+  const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
+  const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
+  const bool affine = scale != nullptr;
+  ChanParams<V> cp;
+  int cur_g = -1;
+  if (affine && G == 1) { load_chan_params<V>(cp, mean, scale, shift, c0); cur_g = 0; }
+  for (uint32_t p = prow; p < P; p += pstride * NORM_UNR) {
+    float v[NORM_UNR][V];
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] = fmaf(v[k] - __ldg(mu + k), __ldg(sc + k), __ldg(sh + k));
-    }
-    if (dk.enabled) {
-      int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
-#pragma unroll
-      for (int k = 0; k < V; ++k) v[k] = dropout_keep(dk, smp, e0 + k) ? 2.f * v[k] : 0.f;
+    for (int u = 0; u < NORM_UNR; ++u) {
+      uint32_t pp = p + u * pstride;
+      if (pp < P) VecIO<T>::load(z + (size_t)pp * C + c0, v[u]);
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = act_fwd(v[k], act);
-    VecIO<T>::store(out + p * out_pitch + out_coff + c0, v);
+    for (int u = 0; u < NORM_UNR; ++u) {
+      uint32_t pp = p + u * pstride;
+      if (pp >= P) break;
+      if (affine) {
+        if (G != 1) {
+          int g = (int)(pp / Pg);
+          if (g != cur_g) { load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0); cur_g = g; }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) v[u][k] = fmaf(v[u][k] - cp.mu[k], cp.sc[k], cp.sf[k]);
+      }
+      if (dk.enabled) {
+        uint32_t smp = pp / HW, e0 = (pp - smp * HW) * C + c0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) v[u][k] = dropout_keep(dk, smp, e0 + k) ? 2.f * v[u][k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[u][k] = act_fwd(v[u][k], act);
+      VecIO<T>::store(out + (size_t)pp * out_pitch + out_coff + c0, v[u]);
+    }
   }
+}
+
+static inline int norm_grid(int64_t P, int cv) {
+  // every thread owns one channel vector; rows are strided over the grid. ~8 CTAs/SM, fewer for tiny tensors
+  int64_t rows_per_block = 256 / cv;
+  int64_t want = (P + rows_per_block * NORM_UNR - 1) / (rows_per_block * NORM_UNR);
+  int64_t cap = (int64_t)NSM * 8;
+  if (want > cap) want = cap;
+  return (int)(want < 1 ? 1 : want);
 }
 
 void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, int G, int HW, int C,
@@ -203,9 +261,10 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
                        int out_pitch, int out_coff) {
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    int64_t nvec = P * (C / VecIO<T>::N);
-    k_norm_apply<T><<<grid_for(nvec, 256), 256, 0, L.s>>>((const T*)z, nvec, Pg, G, HW, C, mean, scale, shift, act, dk,
-                                                          (T*)out, out_pitch, out_coff);
+    const int cv = C / VecIO<T>::N;
+    GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
+    k_norm_apply<T><<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, ilog2(cv),
+                                                       mean, scale, shift, act, dk, (T*)out, out_pitch, out_coff);
   });
   KLAUNCH(L);
 }
@@ -216,7 +275,7 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
 //   dbeta = sum g, dgamma = sum g*xhat,  dz = gamma*inv * (g - mean(g) - xhat*mean(g*xhat))
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V>
-__device__ __forceinline__ void load_grad(const GradSrc& d1, const GradSrc& d2, int64_t p, int c0, float (&g)[V]) {
+__device__ __forceinline__ void load_grad(const GradSrc& d1, const GradSrc& d2, size_t p, int c0, float (&g)[V]) {
   VecIO<T>::load((const T*)d1.p + p * d1.pitch + d1.coff + c0, g);
   if (d2.p != nullptr) {
     float h[V];
@@ -227,8 +286,8 @@ __device__ __forceinline__ void load_grad(const GradSrc& d1, const GradSrc& d2, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, GradSrc d1, GradSrc d2, int64_t Pg, int HW,
-                                                    int C, int nchunk, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t Pg, uint32_t HW,
+                                                    int C, int lcv, int nchunk, const float* __restrict__ mean,
                                                     const float* __restrict__ inv, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int act, DropKey dk,
                                                     float* __restrict__ ws) {
@@ -236,48 +295,46 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
   __shared__ float sh_s[256 * V];
   __shared__ float sh_q[256 * V];
   const int g = blockIdx.y, chunk = blockIdx.x;
-  const int cv = C / V;
-  const int rows_par = 256 / cv;
-  const int col = threadIdx.x % cv, r = threadIdx.x / cv;
-  const int c0 = col * V;
-  const int64_t per = (Pg + nchunk - 1) / nchunk;
-  const int64_t p0 = chunk * per, p1 = (p0 + per < Pg) ? p0 + per : Pg;
-  float s[V], q[V], mu[V], iv[V], sc[V], sf[V];
+  const int cv = 1 << lcv;
+  const uint32_t rows_par = 256u >> lcv;
+  const int c0 = (threadIdx.x & (cv - 1)) * V;
+  const uint32_t r = threadIdx.x >> lcv;
+  const uint32_t per = (Pg + nchunk - 1) / nchunk;
+  const uint32_t p0 = chunk * per, p1 = min(Pg, p0 + per);
+  float s[V], q[V], iv[V];
+  ChanParams<V> cp;
+  load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    s[i] = 0.f; q[i] = 0.f;
-    mu[i] = mean[(int64_t)g * C + c0 + i]; iv[i] = inv[(int64_t)g * C + c0 + i];
-    sc[i] = scale[(int64_t)g * C + c0 + i]; sf[i] = shift[(int64_t)g * C + c0 + i];
-  }
-  if (r < rows_par) {
-    for (int64_t pl = p0 + r; pl < p1; pl += rows_par) {
-      int64_t p = (int64_t)g * Pg + pl;
-      float v[V], gr[V];
-      VecIO<T>::load(z + p * C + c0, v);
-      load_grad<T, V>(d1, d2, p, c0, gr);
-      int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; iv[i] = __ldg(inv + (size_t)g * C + c0 + i); }
+  for (uint32_t pl = p0 + r; pl < p1; pl += rows_par * 2) {
+    float v[2][V], gr[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      uint32_t pp = pl + u * rows_par;
+      if (pp < p1) {
+        size_t p = (size_t)g * Pg + pp;
+        VecIO<T>::load(z + p * C + c0, v[u]);
+        load_grad<T, V>(d1, d2, p, c0, gr[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      uint32_t pp = pl + u * rows_par;
+      if (pp >= p1) break;
+      uint32_t pg = g * Pg + pp;
+      uint32_t smp = 0, e0 = 0;
+      if (dk.enabled) { smp = pg / HW; e0 = (pg - smp * HW) * C + c0; }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float u = fmaf(v[k] - mu[k], sc[k], sf[k]);
-        float gg = gr[k] * act_bwd(u, act);
+        float xc = v[u][k] - cp.mu[k];
+        float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
+        float gg = gr[u][k] * act_bwd(uu, act);
         if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
-        float xh = (v[k] - mu[k]) * iv[k];
-        s[k] += gg; q[k] = fmaf(gg, xh, q[k]);
+        s[k] += gg; q[k] = fmaf(gg, xc * iv[k], q[k]);
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < V; ++i) { sh_s[threadIdx.x * V + i] = s[i]; sh_q[threadIdx.x * V + i] = q[i]; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float S = 0.f, Q = 0.f;
-    for (int rr = 0; rr < rows_par; ++rr) {
-      int t = rr * cv + c / V;
-      S += sh_s[t * V + c % V]; Q += sh_q[t * V + c % V];
-    }
-    float* o = ws + ((int64_t)(g * nchunk + chunk) * 2) * C;
-    o[c] = S; o[C + c] = Q;
-  }
+  block_col_reduce<V>(s, q, cv, C, sh_s, sh_q, ws + ((size_t)(g * nchunk + chunk) * 2) * C);
 }
 
 __global__ void k_bwd_finalize(const float* __restrict__ ws, int G, int nchunk, int C, double n, float* __restrict__ c1,
@@ -298,37 +355,57 @@ __global__ void k_bwd_finalize(const float* __restrict__ ws, int G, int nchunk, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, GradSrc d1, GradSrc d2, int64_t nvec,
-                                                   int64_t Pg, int G, int HW, int C, int norm,
+__global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t P, uint32_t Pg,
+                                                   int G, uint32_t HW, int C, int lcv, int norm,
                                                    const float* __restrict__ mean, const float* __restrict__ inv,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    const float* __restrict__ c1, const float* __restrict__ c2, int act,
                                                    DropKey dk, T* __restrict__ dz) {
   constexpr int V = VecIO<T>::N;
-  const int cv = C / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = i / cv; int c0 = (int)(i - p * cv) * V;
-    float v[V], gr[V], o[V];
-    VecIO<T>::load(z + p * C + c0, v);
-    load_grad<T, V>(d1, d2, p, c0, gr);
-    if (norm == NORM_NONE) {
+  const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
+  const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
+  const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
+  ChanParams<V> cp;
+  float iv[V], k1[V], k2[V];
+  int cur_g = -1;
+  auto load_all = [&](int g) {
+    size_t off = (size_t)g * C + c0;
+    load_chan_params<V>(cp, mean, scale, shift, off);
 #pragma unroll
-      for (int k = 0; k < V; ++k) o[k] = gr[k] * act_bwd(v[k], act);
-    } else {
-      int64_t gi = ((G == 1) ? 0 : (p / Pg)) * C + c0;
-      int64_t smp = p / HW; uint32_t e0 = (uint32_t)((p - smp * HW) * C + c0);
+    for (int k = 0; k < V; ++k) { iv[k] = __ldg(inv + off + k); k1[k] = __ldg(c1 + off + k); k2[k] = __ldg(c2 + off + k); }
+    cur_g = g;
+  };
+  if (norm != NORM_NONE && G == 1) load_all(0);
+  for (uint32_t p = prow; p < P; p += pstride * 2) {
+    float v[2][V], gr[2][V];
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float sc = __ldg(scale + gi + k);
-        float xc = v[k] - __ldg(mean + gi + k);
-        float u = fmaf(xc, sc, __ldg(shift + gi + k));
-        float gg = gr[k] * act_bwd(u, act);
-        if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
-        float xh = xc * __ldg(inv + gi + k);
-        o[k] = sc * (gg - __ldg(c1 + gi + k) - xh * __ldg(c2 + gi + k));
-      }
+    for (int u = 0; u < 2; ++u) {
+      uint32_t pp = p + u * pstride;
+      if (pp < P) { VecIO<T>::load(z + (size_t)pp * C + c0, v[u]); load_grad<T, V>(d1, d2, pp, c0, gr[u]); }
     }
-    VecIO<T>::store(dz + p * C + c0, o);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      uint32_t pp = p + u * pstride;
+      if (pp >= P) break;
+      float o[V];
+      if (norm == NORM_NONE) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = gr[u][k] * act_bwd(v[u][k], act);
+      } else {
+        if (G != 1) { int g = (int)(pp / Pg); if (g != cur_g) load_all(g); }
+        uint32_t smp = 0, e0 = 0;
+        if (dk.enabled) { smp = pp / HW; e0 = (pp - smp * HW) * C + c0; }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float xc = v[u][k] - cp.mu[k];
+          float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
+          float gg = gr[u][k] * act_bwd(uu, act);
+          if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+          o[k] = cp.sc[k] * (gg - k1[k] - xc * iv[k] * k2[k]);
+        }
+      }
+      VecIO<T>::store(dz + (size_t)pp * C + c0, o);
+    }
   }
 }
 
@@ -338,16 +415,18 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
   int nchunk = stats_chunks(G, Pg);
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
+    const int cv = C / VecIO<T>::N;
+    GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
+    const int lcv = ilog2(cv);
     if (norm != NORM_NONE) {
-      k_bwd_reduce<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, Pg, HW, C, nchunk, mean, inv, scale, shift,
-                                                       act, dk, ws);
+      k_bwd_reduce<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean,
+                                                       inv, scale, shift, act, dk, ws);
       KLAUNCH(L);
       k_bwd_finalize<<<(C + 127) / 128, 128, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
       KLAUNCH(L);
     }
-    int64_t nvec = P * (C / VecIO<T>::N);
-    k_bwd_apply<T><<<grid_for(nvec, 256), 256, 0, L.s>>>((const T*)z, d1, d2, nvec, Pg, G, HW, C, norm, mean, inv, scale,
-                                                         shift, c1, c2, act, dk, (T*)dz);
+    k_bwd_apply<T><<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, lcv,
+                                                      norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz);
     KLAUNCH(L);
   });
 }
