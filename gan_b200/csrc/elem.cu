@@ -70,7 +70,7 @@ void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64
 #define NORM_UNR 4
 
 int stats_chunks(int G, int64_t Pg) {
-  int64_t want = (2 * STATS_MAX_CHUNKS + G - 1) / G;     // ~8 CTAs per SM across all groups
+  int64_t want = (STATS_MAX_CHUNKS + G - 1) / G;         // ~4 CTAs per SM across all groups
   int64_t maxc = (Pg + 63) / 64;                         // at least 64 rows per chunk
   int64_t c = want < maxc ? want : maxc;
   return (int)(c < 1 ? 1 : c);
@@ -134,25 +134,44 @@ __global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, 
   block_col_reduce<V>(s, q, cv, C, sh_s, sh_q, ws + ((size_t)(g * nchunk + chunk) * 2) * C);
 }
 
-__global__ void k_stats_finalize(const float* __restrict__ ws, int G, int nchunk, int C, double n, float eps,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float* __restrict__ mean, float* __restrict__ inv, float* __restrict__ scale,
-                                 float* __restrict__ shift, float* mov_mean, float* mov_var, float momentum) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G * C) return;
-  int g = i / C, c = i - g * C;
-  double S = 0.0, Q = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    const float* o = ws + ((int64_t)(g * nchunk + k) * 2) * C;
-    S += (double)o[c]; Q += (double)o[C + c];
+// Stage 2: one block per (32 channels, group): 8 chunk-lanes per channel sum the partials in
+// double, shared-memory tree over the lanes, then mean / inv-std / fused scale are emitted.
+#define FIN_LANES 8
+__device__ __forceinline__ void fin_reduce(const float* __restrict__ ws, int g, int nchunk, int C, int c, int lane,
+                                           double& S, double& Q) {
+  __shared__ double sh[2][FIN_LANES][32];
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    for (int k = lane; k < nchunk; k += FIN_LANES) {
+      const float* o = ws + ((size_t)(g * nchunk + k) * 2) * C;
+      s += (double)__ldg(o + c); q += (double)__ldg(o + C + c);
+    }
   }
+  sh[0][lane][threadIdx.x & 31] = s; sh[1][lane][threadIdx.x & 31] = q;
+  __syncthreads();
+  S = 0.0; Q = 0.0;
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < FIN_LANES; ++l) { S += sh[0][l][threadIdx.x & 31]; Q += sh[1][l][threadIdx.x & 31]; }
+  }
+}
+
+__global__ void __launch_bounds__(32 * FIN_LANES) k_stats_finalize(
+    const float* __restrict__ ws, int G, int nchunk, int C, double n, float eps, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ inv, float* __restrict__ scale,
+    float* __restrict__ shift, float* mov_mean, float* mov_var, float momentum) {
+  const int g = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+  double S, Q;
+  fin_reduce(ws, g, nchunk, C, c, lane, S, Q);
+  if (lane != 0 || c >= C) return;
+  const size_t i = (size_t)g * C + c;
   double m = S / n;
   double var = Q / n - m * m;
   if (var < 0.0) var = 0.0;
   double iv = 1.0 / sqrt(var + (double)eps);
-  float sc = (float)((double)gamma[c] * iv);
   mean[i] = (float)m; inv[i] = (float)iv;
-  scale[i] = sc; shift[i] = beta[c];     // u = (z - mean)*scale + beta: exactly beta when z == mean (n == 1)
+  scale[i] = (float)((double)gamma[c] * iv);
+  shift[i] = beta[c];     // u = (z - mean)*scale + beta: exactly beta when z == mean (n == 1)
   if (mov_mean != nullptr) {
     // Keras BatchNormalization moving averages (momentum 0.99); the fused TF kernel feeds the
     // Bessel-corrected variance.  Never read on the hot path (every call is training=True).
@@ -173,8 +192,8 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
     k_stats_partial<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, (uint32_t)Pg, C, ilog2(cv), nchunk, ws);
   });
   KLAUNCH(L);
-  k_stats_finalize<<<(G * C + 127) / 128, 128, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, eps, gamma, beta, mean, inv,
-                                                        scale, shift, mov_mean, mov_var, momentum);
+  k_stats_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, eps, gamma, beta, mean,
+                                                                      inv, scale, shift, mov_mean, mov_var, momentum);
   KLAUNCH(L);
 }
 
@@ -337,21 +356,16 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
   block_col_reduce<V>(s, q, cv, C, sh_s, sh_q, ws + ((size_t)(g * nchunk + chunk) * 2) * C);
 }
 
-__global__ void k_bwd_finalize(const float* __restrict__ ws, int G, int nchunk, int C, double n, float* __restrict__ c1,
-                               float* __restrict__ c2, float* dgamma, float* dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double SB = 0.0, SG = 0.0;
-  for (int g = 0; g < G; ++g) {
-    double S = 0.0, Q = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-      const float* o = ws + ((int64_t)(g * nchunk + k) * 2) * C;
-      S += (double)o[c]; Q += (double)o[C + c];
-    }
-    c1[(int64_t)g * C + c] = (float)(S / n); c2[(int64_t)g * C + c] = (float)(Q / n);
-    SB += S; SG += Q;
-  }
-  dbeta[c] += (float)SB; dgamma[c] += (float)SG;
+__global__ void __launch_bounds__(32 * FIN_LANES) k_bwd_finalize(const float* __restrict__ ws, int G, int nchunk, int C,
+                                                                 double n, float* __restrict__ c1, float* __restrict__ c2,
+                                                                 float* dgamma, float* dbeta) {
+  const int g = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+  double S, Q;
+  fin_reduce(ws, g, nchunk, C, c, lane, S, Q);
+  if (lane != 0 || c >= C) return;
+  c1[(size_t)g * C + c] = (float)(S / n); c2[(size_t)g * C + c] = (float)(Q / n);
+  // parameter gradients sum over the groups (InstanceNorm: over samples); one add per channel for BatchNorm
+  atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
 }
 
 template <typename T>
@@ -422,7 +436,7 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
       k_bwd_reduce<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean,
                                                        inv, scale, shift, act, dk, ws);
       KLAUNCH(L);
-      k_bwd_finalize<<<(C + 127) / 128, 128, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
+      k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
       KLAUNCH(L);
     }
     k_bwd_apply<T><<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, lcv,
