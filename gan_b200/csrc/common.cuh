@@ -107,6 +107,28 @@ template <> struct VecIO<bf16> {
   }
 };
 
+// 4-element vector access (16 B fp32 / 8 B bf16): used by the register-heavy normalisation kernels so
+// that several independent loads per thread stay in flight without dropping below 3 CTAs/SM.
+template <typename T> struct Vec4IO;
+template <> struct Vec4IO<float> {
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) { VecIO<float>::load(p, v); }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) { VecIO<float>::store(p, v); }
+};
+template <> struct Vec4IO<bf16> {
+  __device__ static __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  __device__ static __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    uint2 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]); h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

@@ -68,6 +68,7 @@ void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64
 // independent 128-bit loads in flight (HBM-bound: bytes in flight per SM is what matters).
 // ---------------------------------------------------------------------------------------------
 #define NORM_UNR 4
+#define NORM_BWD_UNR 4
 
 int stats_chunks(int G, int64_t Pg) {
   int64_t want = (STATS_MAX_CHUNKS + G - 1) / G;         // ~4 CTAs per SM across all groups
@@ -101,7 +102,7 @@ __device__ __forceinline__ void block_col_reduce(const float (&s)[V], const floa
 template <typename T>
 __global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, uint32_t Pg, int C, int lcv, int nchunk,
                                                        float* __restrict__ ws) {
-  constexpr int V = VecIO<T>::N;
+  constexpr int V = 4;
   __shared__ float sh_s[256 * V];
   __shared__ float sh_q[256 * V];
   const int g = blockIdx.y, chunk = blockIdx.x;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, 
 #pragma unroll
     for (int u = 0; u < NORM_UNR; ++u) {
       uint32_t pp = p + u * rows_par;
-      if (pp < p1) VecIO<T>::load(base + (size_t)pp * C, v[u]);
+      if (pp < p1) Vec4IO<T>::load(base + (size_t)pp * C, v[u]);
       else {
 #pragma unroll
         for (int i = 0; i < V; ++i) v[u][i] = 0.f;
@@ -187,7 +188,7 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
   int nchunk = stats_chunks(G, Pg);
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    const int cv = C / VecIO<T>::N;
+    const int cv = C / 4;
     GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256, "normalised channel count must be a power of two");
     k_stats_partial<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, (uint32_t)Pg, C, ilog2(cv), nchunk, ws);
   });
@@ -222,12 +223,12 @@ __device__ __forceinline__ void load_chan_params(ChanParams<V>& cp, const float*
   for (int k = 0; k < V; ++k) { cp.mu[k] = __ldg(mean + off + k); cp.sc[k] = __ldg(scale + off + k); cp.sf[k] = __ldg(shift + off + k); }
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uint32_t P, uint32_t Pg, int G, uint32_t HW,
                                                     int C, int lcv, const float* __restrict__ mean,
                                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                                     int act, DropKey dk, T* __restrict__ out, int out_pitch, int out_coff) {
-  constexpr int V = VecIO<T>::N;
+  constexpr int V = 4;
   const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
   const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
   const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uin
 #pragma unroll
     for (int u = 0; u < NORM_UNR; ++u) {
       uint32_t pp = p + u * pstride;
-      if (pp < P) VecIO<T>::load(z + (size_t)pp * C + c0, v[u]);
+      if (pp < P) Vec4IO<T>::load(z + (size_t)pp * C + c0, v[u]);
     }
 #pragma unroll
     for (int u = 0; u < NORM_UNR; ++u) {
@@ -254,14 +255,14 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uin
 #pragma unroll
         for (int k = 0; k < V; ++k) v[u][k] = fmaf(v[u][k] - cp.mu[k], cp.sc[k], cp.sf[k]);
       }
-      if (dk.enabled) {
+      if (DROP) {
         uint32_t smp = pp / HW, e0 = (pp - smp * HW) * C + c0;
 #pragma unroll
         for (int k = 0; k < V; ++k) v[u][k] = dropout_keep(dk, smp, e0 + k) ? 2.f * v[u][k] : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < V; ++k) v[u][k] = act_fwd(v[u][k], act);
-      VecIO<T>::store(out + (size_t)pp * out_pitch + out_coff + c0, v[u]);
+      Vec4IO<T>::store(out + (size_t)pp * out_pitch + out_coff + c0, v[u]);
     }
   }
 }
@@ -280,9 +281,10 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
                        int out_pitch, int out_coff) {
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    const int cv = C / VecIO<T>::N;
+    const int cv = C / 4;
     GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
-    k_norm_apply<T><<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, ilog2(cv),
+    auto kern = dk.enabled ? k_norm_apply<T, true> : k_norm_apply<T, false>;
+    kern<<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, ilog2(cv),
                                                        mean, scale, shift, act, dk, (T*)out, out_pitch, out_coff);
   });
   KLAUNCH(L);
@@ -295,22 +297,22 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V>
 __device__ __forceinline__ void load_grad(const GradSrc& d1, const GradSrc& d2, size_t p, int c0, float (&g)[V]) {
-  VecIO<T>::load((const T*)d1.p + p * d1.pitch + d1.coff + c0, g);
+  Vec4IO<T>::load((const T*)d1.p + p * d1.pitch + d1.coff + c0, g);
   if (d2.p != nullptr) {
     float h[V];
-    VecIO<T>::load((const T*)d2.p + p * d2.pitch + d2.coff + c0, h);
+    Vec4IO<T>::load((const T*)d2.p + p * d2.pitch + d2.coff + c0, h);
 #pragma unroll
     for (int k = 0; k < V; ++k) g[k] += h[k];
   }
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t Pg, uint32_t HW,
                                                     int C, int lcv, int nchunk, const float* __restrict__ mean,
                                                     const float* __restrict__ inv, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int act, DropKey dk,
                                                     float* __restrict__ ws) {
-  constexpr int V = VecIO<T>::N;
+  constexpr int V = 4;
   __shared__ float sh_s[256 * V];
   __shared__ float sh_q[256 * V];
   const int g = blockIdx.y, chunk = blockIdx.x;
@@ -320,39 +322,41 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
   const uint32_t r = threadIdx.x >> lcv;
   const uint32_t per = (Pg + nchunk - 1) / nchunk;
   const uint32_t p0 = chunk * per, p1 = min(Pg, p0 + per);
-  float s[V], q[V], iv[V];
+  float s[V], q[V];
   ChanParams<V> cp;
   load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0);
 #pragma unroll
-  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; iv[i] = __ldg(inv + (size_t)g * C + c0 + i); }
-  for (uint32_t pl = p0 + r; pl < p1; pl += rows_par * 2) {
-    float v[2][V], gr[2][V];
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (uint32_t pl = p0 + r; pl < p1; pl += rows_par * NORM_BWD_UNR) {
+    float v[NORM_BWD_UNR][V], gr[NORM_BWD_UNR][V];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NORM_BWD_UNR; ++u) {
       uint32_t pp = pl + u * rows_par;
       if (pp < p1) {
         size_t p = (size_t)g * Pg + pp;
-        VecIO<T>::load(z + p * C + c0, v[u]);
+        Vec4IO<T>::load(z + p * C + c0, v[u]);
         load_grad<T, V>(d1, d2, p, c0, gr[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NORM_BWD_UNR; ++u) {
       uint32_t pp = pl + u * rows_par;
       if (pp >= p1) break;
       uint32_t pg = g * Pg + pp;
       uint32_t smp = 0, e0 = 0;
-      if (dk.enabled) { smp = pg / HW; e0 = (pg - smp * HW) * C + c0; }
+      if (DROP) { smp = pg / HW; e0 = (pg - smp * HW) * C + c0; }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         float xc = v[u][k] - cp.mu[k];
         float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
         float gg = gr[u][k] * act_bwd(uu, act);
-        if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
-        s[k] += gg; q[k] = fmaf(gg, xc * iv[k], q[k]);
+        if (DROP) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+        s[k] += gg; q[k] = fmaf(gg, xc, q[k]);      // x_hat = xc*inv: inv is applied once after the loop
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < V; ++i) q[i] *= __ldg(inv + (size_t)g * C + c0 + i);
   block_col_reduce<V>(s, q, cv, C, sh_s, sh_q, ws + ((size_t)(g * nchunk + chunk) * 2) * C);
 }
 
@@ -368,14 +372,14 @@ __global__ void __launch_bounds__(32 * FIN_LANES) k_bwd_finalize(const float* __
   atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t P, uint32_t Pg,
                                                    int G, uint32_t HW, int C, int lcv, int norm,
                                                    const float* __restrict__ mean, const float* __restrict__ inv,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    const float* __restrict__ c1, const float* __restrict__ c2, int act,
                                                    DropKey dk, T* __restrict__ dz) {
-  constexpr int V = VecIO<T>::N;
+  constexpr int V = 4;
   const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
   const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
   const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
@@ -390,15 +394,15 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
     cur_g = g;
   };
   if (norm != NORM_NONE && G == 1) load_all(0);
-  for (uint32_t p = prow; p < P; p += pstride * 2) {
-    float v[2][V], gr[2][V];
+  for (uint32_t p = prow; p < P; p += pstride * NORM_BWD_UNR) {
+    float v[NORM_BWD_UNR][V], gr[NORM_BWD_UNR][V];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NORM_BWD_UNR; ++u) {
       uint32_t pp = p + u * pstride;
-      if (pp < P) { VecIO<T>::load(z + (size_t)pp * C + c0, v[u]); load_grad<T, V>(d1, d2, pp, c0, gr[u]); }
+      if (pp < P) { Vec4IO<T>::load(z + (size_t)pp * C + c0, v[u]); load_grad<T, V>(d1, d2, pp, c0, gr[u]); }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NORM_BWD_UNR; ++u) {
       uint32_t pp = p + u * pstride;
       if (pp >= P) break;
       float o[V];
@@ -408,17 +412,17 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
       } else {
         if (G != 1) { int g = (int)(pp / Pg); if (g != cur_g) load_all(g); }
         uint32_t smp = 0, e0 = 0;
-        if (dk.enabled) { smp = pp / HW; e0 = (pp - smp * HW) * C + c0; }
+        if (DROP) { smp = pp / HW; e0 = (pp - smp * HW) * C + c0; }
 #pragma unroll
         for (int k = 0; k < V; ++k) {
           float xc = v[u][k] - cp.mu[k];
           float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
           float gg = gr[u][k] * act_bwd(uu, act);
-          if (dk.enabled) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+          if (DROP) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
           o[k] = cp.sc[k] * (gg - k1[k] - xc * iv[k] * k2[k]);
         }
       }
-      VecIO<T>::store(dz + (size_t)pp * C + c0, o);
+      Vec4IO<T>::store(dz + (size_t)pp * C + c0, o);
     }
   }
 }
@@ -429,17 +433,19 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
   int nchunk = stats_chunks(G, Pg);
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    const int cv = C / VecIO<T>::N;
+    const int cv = C / 4;
     GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
     const int lcv = ilog2(cv);
     if (norm != NORM_NONE) {
-      k_bwd_reduce<T><<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean,
+      auto kred = dk.enabled ? k_bwd_reduce<T, true> : k_bwd_reduce<T, false>;
+      kred<<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean,
                                                        inv, scale, shift, act, dk, ws);
       KLAUNCH(L);
       k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
       KLAUNCH(L);
     }
-    k_bwd_apply<T><<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, lcv,
+    auto kapp = dk.enabled ? k_bwd_apply<T, true> : k_bwd_apply<T, false>;
+    kapp<<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, lcv,
                                                       norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz);
     KLAUNCH(L);
   });
