@@ -159,6 +159,7 @@ def run_ours(args):
            "batch_size": B, "epochs": 1}
     model = Pix2Pix(cfg)                       # random-init weights N(0,0.02) from default_rng(seed+1)
     ctx = model.ctx
+    ctx.set_graphs(not args.no_graphs)          # whole-step CUDA graphs (eager for the profiled roofline pass)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
     # synthetic inputs: U[-1,1) float32 NHWC, global sample index keyed so every world size sees the same data
@@ -266,7 +267,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"Pix2Pix train step 256x256x3, global batch {GLOBAL_BATCH}, data-parallel",
                            "global_batch": GLOBAL_BATCH, "per_gpu_batch": B, "img_size": SIZE, "channels": CH,
-                           "lambda": LAMBDA, "parallelism": f"dp{world}",
+                           "lambda": LAMBDA, "parallelism": f"dp{world}", "cuda_graphs": not args.no_graphs,
                            "l2": f"inputs larger than L2: pool of {POOL} distinct batches ({2 * POOL * img_bytes / 1e6:.0f} MB/rank)"},
                 "conv_tflops_per_gpu": FLOPS_PER_IMAGE * value / world / 1e12,
                 "conv_frac_of_bf16_peak": FLOPS_PER_IMAGE * value / world / 1e12 / peak_tf,
@@ -288,6 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

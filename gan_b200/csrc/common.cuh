@@ -156,11 +156,13 @@ __device__ __forceinline__ uint32_t philox_word0(uint32_t c0, uint32_t c1, uint3
 }
 
 // Dropout(0.5) keep decision for element `elem` of global sample `sample` (base_gan.py:118).
-struct DropKey { uint32_t seed_lo, seed_hi, call, layer; int64_t sample0; int enabled; };
-__device__ __forceinline__ bool dropout_keep(const DropKey& k, int64_t sample_local, uint32_t elem) {
-  uint32_t w = philox_word0(elem, (uint32_t)(k.sample0 + sample_local), k.layer, k.call, k.seed_lo, k.seed_hi);
+// The call counter lives in device memory (call = *call_dev + call_off) so that a captured CUDA
+// graph draws fresh masks on every replay.
+struct DropKey { uint32_t seed_lo, seed_hi; const uint32_t* call_dev; uint32_t call_off, layer; int64_t sample0; int enabled; };
+__device__ __forceinline__ bool dropout_keep(const DropKey& k, uint32_t call, int64_t sample_local, uint32_t elem) {
+  uint32_t w = philox_word0(elem, (uint32_t)(k.sample0 + sample_local), k.layer, call, k.seed_lo, k.seed_hi);
   return (w >> 31) != 0u;
 }
 #else
-struct DropKey { uint32_t seed_lo, seed_hi, call, layer; int64_t sample0; int enabled; };
+struct DropKey { uint32_t seed_lo, seed_hi; const uint32_t* call_dev; uint32_t call_off, layer; int64_t sample0; int enabled; };
 #endif

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uin
   const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
   const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
   const bool affine = scale != nullptr;
+  const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
   ChanParams<V> cp;
   int cur_g = -1;
   if (affine && G == 1) { load_chan_params<V>(cp, mean, scale, shift, c0); cur_g = 0; }
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uin
       if (DROP) {
         uint32_t smp = pp / HW, e0 = (pp - smp * HW) * C + c0;
 #pragma unroll
-        for (int k = 0; k < V; ++k) v[u][k] = dropout_keep(dk, smp, e0 + k) ? 2.f * v[u][k] : 0.f;
+        for (int k = 0; k < V; ++k) v[u][k] = dropout_keep(dk, call, smp, e0 + k) ? 2.f * v[u][k] : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < V; ++k) v[u][k] = act_fwd(v[u][k], act);
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
   const uint32_t p0 = chunk * per, p1 = min(Pg, p0 + per);
   float s[V], q[V];
   ChanParams<V> cp;
+  const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
   load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0);
 #pragma unroll
   for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
         float xc = v[u][k] - cp.mu[k];
         float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
         float gg = gr[u][k] * act_bwd(uu, act);
-        if (DROP) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+        if (DROP) gg = dropout_keep(dk, call, smp, e0 + k) ? 2.f * gg : 0.f;
         s[k] += gg; q[k] = fmaf(gg, xc, q[k]);      // x_hat = xc*inv: inv is applied once after the loop
       }
     }
@@ -386,6 +388,7 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
   ChanParams<V> cp;
   float iv[V], k1[V], k2[V];
   int cur_g = -1;
+  const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
   auto load_all = [&](int g) {
     size_t off = (size_t)g * C + c0;
     load_chan_params<V>(cp, mean, scale, shift, off);
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
           float xc = v[u][k] - cp.mu[k];
           float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
           float gg = gr[u][k] * act_bwd(uu, act);
-          if (DROP) gg = dropout_keep(dk, smp, e0 + k) ? 2.f * gg : 0.f;
+          if (DROP) gg = dropout_keep(dk, call, smp, e0 + k) ? 2.f * gg : 0.f;
           o[k] = cp.sc[k] * (gg - k1[k] - xc * iv[k] * k2[k]);
         }
       }
@@ -595,8 +598,12 @@ void launch_loss_finalize(Launch L, const float* loss_ws, LossMix mix, float* ou
 // One launch per network over the flat parameter buffer: 28 B/param of HBM traffic.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                              float* __restrict__ v, int64_t n4, int64_t n, float lr_t, float b1, float b2,
-                                              float eps, float gscale) {
+                                              float* __restrict__ v, int64_t n4, int64_t n, const long long* __restrict__ t_dev,
+                                              double lr, double b1d, double b2d, float eps, float gscale) {
+  // lr_t = lr*sqrt(1-b2^t)/(1-b1^t) from the device-resident step counter (graph-replay safe)
+  const double t = (double)(*t_dev);
+  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2d, t)) / (1.0 - pow(b1d, t)));
+  const float b1 = (float)b1d, b2 = (float)b2d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 P = reinterpret_cast<float4*>(p)[i], Gr = reinterpret_cast<const float4*>(g)[i];
     float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
@@ -611,18 +618,26 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
   }
   // tail (n not a multiple of 4)
-  int64_t t = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t < n) {
-    float gr = g[t] * gscale;
-    m[t] += (gr - m[t]) * (1.f - b1);
-    v[t] += (gr * gr - v[t]) * (1.f - b2);
-    p[t] -= lr_t * m[t] / (sqrtf(v[t]) + eps);
+  int64_t tl = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tl < n) {
+    float gr = g[tl] * gscale;
+    m[tl] += (gr - m[tl]) * (1.f - b1);
+    v[tl] += (gr * gr - v[tl]) * (1.f - b2);
+    p[tl] -= lr_t * m[tl] / (sqrtf(v[tl]) + eps);
   }
 }
-void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
-                 float eps, float gscale) {
+__global__ void k_bump(long long* t64, uint32_t* c32, uint32_t by) {
+  if (t64) *t64 += (long long)by;
+  if (c32) *c32 += by;
+}
+void launch_bump(Launch L, long long* t64, uint32_t* c32, uint32_t by) {
+  k_bump<<<1, 1, 0, L.s>>>(t64, c32, by);
+  KLAUNCH(L);
+}
+void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, const long long* t_dev, double lr,
+                 double b1, double b2, float eps, float gscale) {
   int64_t n4 = n / 4;
-  k_adam<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, L.s>>>(p, g, m, v, n4, n, lr_t, b1, b2, eps, gscale);
+  k_adam<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, L.s>>>(p, g, m, v, n4, n, t_dev, lr, b1, b2, eps, gscale);
   KLAUNCH(L);
 }
 
@@ -654,6 +669,62 @@ void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp&
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     k_pack<T><<<dim3(grid_for(total, 256, 4), op.ncls), 256, 0, L.s>>>(master, (T*)dst, op);
+  });
+  KLAUNCH(L);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict__ tab, int nent) {
+  __shared__ float tile[32][33];
+  __shared__ int s_e;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < nent && (int)blockIdx.x >= tab[e + 1].tile_begin) ++e;
+    s_e = e;
+  }
+  __syncthreads();
+  const PackEntry& E = tab[s_e];
+  const PackOp& op = E.op;
+  int lt = blockIdx.x - E.tile_begin;
+  const int tn = lt % E.tiles_n; lt /= E.tiles_n;
+  const int tk = lt % E.tiles_k; lt /= E.tiles_k;
+  const int ntaps = op.cls[0].ntaps;
+  const int t = lt % ntaps, ci = lt / ntaps;
+  const ClassGeom& cg = op.cls[ci];
+  const float* __restrict__ src = E.master + (int64_t)cg.widx[t] * op.s_tap;
+  T* __restrict__ dst = (T*)E.dst + cg.b_off;
+  const int64_t Ktot = (int64_t)ntaps * op.Kc;
+  const int k0 = tk * 32, n0 = tn * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  if (op.s_n == 1) {
+    // master contiguous along n: read rows = kc, cols = n; write rows = n, cols = kc (transpose)
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      int kc = k0 + r, n = n0 + tx;
+      tile[r][tx] = (kc < op.Kr && n < op.Nr) ? src[(int64_t)kc * op.s_k + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      int n = n0 + r, kc = k0 + tx;
+      if (n < op.Nc && kc < op.Kc) dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(tile[tx][r]);
+    }
+  } else {
+    // master contiguous along kc (s_k == 1): straight tile copy
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      int n = n0 + r, kc = k0 + tx;
+      if (n < op.Nc && kc < op.Kc) {
+        float v = (kc < op.Kr && n < op.Nr) ? src[(int64_t)kc * op.s_k + (int64_t)n * op.s_n] : 0.f;
+        dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(v);
+      }
+    }
+  }
+}
+void launch_pack_multi(Launch L, int dt, const PackEntry* tab_dev, int nent, int total_tiles) {
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_pack_multi<T><<<total_tiles, 256, 0, L.s>>>(tab_dev, nent);
   });
   KLAUNCH(L);
 }

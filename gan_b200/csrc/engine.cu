@@ -7,8 +7,10 @@
 // Autodiff (tf.GradientTape) is replaced by hand-derived backward sweeps over the saved raw
 // convolution outputs ("z") and normalisation statistics of each forward call (a Slot).
 #include <cstring>
+#include <cstdio>
 #include <cmath>
 #include <mutex>
+#include <functional>
 #include "engine.h"
 #include "../../include/gan_b200.h"
 
@@ -200,18 +202,32 @@ static void finish_net(gan_net* n) {
 static void pack_weights(gan_net* n) {
   if (!n->packed_dirty) return;
   gan_ctx* ctx = n->ctx;
-  for (auto& ly : n->layers) {
-    for (int role = R_FWD; role <= R_DGRAD; ++role) {
-      if (role == R_DGRAD && !ly.need_dgrad) continue;
-      PackOp po; memset(&po, 0, sizeof(po));
-      po.ncls = fill_geometry(ly.kind, role, po.cls);
-      weight_strides(ly, role, po.Kc, po.Nc, po.Kr, po.Nr, po.s_tap, po.s_k, po.s_n);
-      for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
-      DevBuf& dst = role == R_FWD ? ly.wp_fwd : ly.wp_dgrad;
-      dst.ensure((size_t)16 * ly.Cin_p * ly.Cout_p * ctx->esize());
-      launch_pack(ctx->L(), ctx->dt, n->params.as<float>() + ly.w_off, dst.p, po);
+  if (n->pack_nent == 0) {
+    // build the (static) table once: every layer x {forward, data-gradient} role
+    std::vector<PackEntry> tab;
+    int tiles = 0;
+    for (auto& ly : n->layers) {
+      for (int role = R_FWD; role <= R_DGRAD; ++role) {
+        if (role == R_DGRAD && !ly.need_dgrad) continue;
+        PackEntry e; memset(&e, 0, sizeof(e));
+        PackOp& po = e.op;
+        po.ncls = fill_geometry(ly.kind, role, po.cls);
+        weight_strides(ly, role, po.Kc, po.Nc, po.Kr, po.Nr, po.s_tap, po.s_k, po.s_n);
+        for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
+        DevBuf& dst = role == R_FWD ? ly.wp_fwd : ly.wp_dgrad;
+        dst.ensure((size_t)16 * ly.Cin_p * ly.Cout_p * ctx->esize());
+        e.master = n->params.as<float>() + ly.w_off; e.dst = dst.p;
+        e.tiles_k = (po.Kc + 31) / 32; e.tiles_n = (po.Nc + 31) / 32;
+        e.tile_begin = tiles;
+        tiles += e.tiles_k * e.tiles_n * po.cls[0].ntaps * po.ncls;
+        tab.push_back(e);
+      }
     }
+    n->pack_tab.ensure(tab.size() * sizeof(PackEntry));
+    CUDA_CHECK(cudaMemcpy(n->pack_tab.p, tab.data(), tab.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
+    n->pack_nent = (int)tab.size(); n->pack_tiles = tiles;
   }
+  launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab.p, n->pack_nent, n->pack_tiles);
   n->packed_dirty = false;
 }
 
@@ -221,7 +237,7 @@ static void pack_weights(gan_net* n) {
 static DropKey drop_key(gan_ctx* ctx, const Layer& ly, const Slot& s) {
   DropKey k;
   k.seed_lo = (uint32_t)(ctx->seed & 0xffffffffu); k.seed_hi = (uint32_t)(ctx->seed >> 32);
-  k.call = s.call_id; k.layer = (uint32_t)ly.tag; k.sample0 = s.sample0;
+  k.call_dev = ctx->call_dev.as<uint32_t>(); k.call_off = s.call_off; k.layer = (uint32_t)ly.tag; k.sample0 = s.sample0;
   k.enabled = (ly.dropout && ctx->dropout_enabled) ? 1 : 0;
   return k;
 }
@@ -328,7 +344,8 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   pack_weights(g);
   Slot& s = g->slots[slot];
   slot_prepare(g, s, B, H, W);
-  s.call_id = ctx->call_counter++;
+  s.call_off = ctx->gen_calls_pending++;
+  s.call_id = ctx->call_counter + s.call_off;
   s.sample0 = ctx->sample0_set ? ctx->sample0 : (int64_t)ctx->rank * B;
   const size_t es = ctx->esize();
   const int C = g->C;
@@ -498,11 +515,11 @@ static void adam_apply(gan_adam* o) {
   gan_net* n = o->net; gan_ctx* ctx = n->ctx;
   if (ctx->world > 1) comm_allreduce_sum(ctx, n->grads.as<float>(), n->nparams);
   o->t += 1;
-  double lr_t = o->lr * std::sqrt(1.0 - std::pow(o->b2, (double)o->t)) / (1.0 - std::pow(o->b1, (double)o->t));
+  launch_bump(ctx->L(), o->t_dev.as<long long>(), nullptr, 1);
   {
     ProfScope ps(ctx, FAM_ADAM, 28.0 * (double)n->nparams);
     launch_adam(ctx->L(), n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), n->nparams,
-                (float)lr_t, (float)o->b1, (float)o->b2, (float)o->eps, 1.f / (float)ctx->world);
+                o->t_dev.as<long long>(), o->lr, o->b1, o->b2, (float)o->eps, 1.f / (float)ctx->world);
   }
   n->packed_dirty = true;
   ProfScope ps(ctx, FAM_PACK, (double)n->nparams * (4.0 + 2.0 * ctx->esize()));
@@ -521,6 +538,13 @@ static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) 
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     memcpy(losses_host, ctx->loss_host, mix.nout * 4);
   }
+}
+// Advance the device-resident dropout call counter by the generator forwards run since the last bump.
+static void bump_calls(gan_ctx* ctx) {
+  if (ctx->gen_calls_pending == 0) return;
+  launch_bump(ctx->L(), nullptr, ctx->call_dev.as<uint32_t>(), ctx->gen_calls_pending);
+  ctx->call_counter += ctx->gen_calls_pending;
+  ctx->gen_calls_pending = 0;
 }
 static void loss_ws_reset(gan_ctx* ctx) {
   ctx->loss_ws.ensure((size_t)LOSS_SLOTS * LOSS_BLOCKS * 4);
@@ -572,6 +596,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   M(1, 0) = 1.f;                          // gen_gan_loss
   M(2, 1) = 1.f;                          // gen_gan_loss2 (L1)
   M(3, 2) = 0.5f; M(3, 3) = 0.5f;         // disc_loss = (real+generated)*0.5         (:206)
+  bump_calls(ctx);
   finish_losses(ctx, mix, losses);
 }
 
@@ -592,7 +617,6 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
   loss_ws_reset(ctx);
   if (training) { zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy); }
-  for (gan_net* n : {g, f}) for (auto& ly : n->layers) ly.need_dgrad = true;
 
   generator_forward(g, 0, x, B, H, W);  const float* fake_y = g->slots[0].out_f32.as<float>();     // (:220)
   generator_forward(f, 0, fake_y, B, H, W); const float* cycled_x = f->slots[0].out_f32.as<float>(); // (:221)
@@ -642,7 +666,53 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   M(4, 1) = 1.f; M(4, 2) = lambda; M(4, 3) = lambda; M(4, 5) = 0.5f * lambda;   // total_gen_f_loss (:244)
   M(5, 6) = 0.5f; M(5, 7) = 0.5f;                                      // disc_x_loss (:246)
   M(6, 8) = 0.5f; M(6, 9) = 0.5f;                                      // disc_y_loss (:247)
+  bump_calls(ctx);
   finish_losses(ctx, mix, losses);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-graph execution of a whole train step.  First call with a key: eager (allocates every
+// buffer); second call: stream capture + instantiate; later calls: one cudaGraphLaunch.  Inputs
+// are always copied into the ctx staging buffers first (their addresses are baked into the graph);
+// the Adam step counters and the dropout call counter live in device memory.
+// ---------------------------------------------------------------------------------------------
+template <typename F>
+static void run_step_graphed(gan_ctx* ctx, const std::string& key, const float* x_in, const float* y_in, size_t img_bytes,
+                             float* losses_host, int nloss, const std::vector<gan_net*>& nets,
+                             const std::vector<gan_adam*>& opts, F&& body) {
+  for (gan_net* n : nets) pack_weights(n);      // host-side set_tensor since the last step: repack outside the graph
+  ctx->stage[0].ensure(img_bytes); ctx->stage[1].ensure(img_bytes);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->stage[0].p, x_in, img_bytes, cudaMemcpyDefault, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(ctx->stage[1].p, y_in, img_bytes, cudaMemcpyDefault, ctx->stream));
+  const float* xs = ctx->stage[0].as<float>(); const float* ys = ctx->stage[1].as<float>();
+  gan_ctx::GraphEntry& ge = ctx->graph_cache[key];
+  if (ge.exec != nullptr) {
+    CUDA_CHECK(cudaGraphLaunch(ge.exec, ctx->stream));
+    ctx->launches += ge.launches;
+    ctx->call_counter += ge.gen_calls;
+    for (gan_adam* o : opts) o->t += 1;
+    ctx->n_losses = nloss;
+  } else if (ge.warm == 0) {
+    body(xs, ys);
+    ge.warm = 1;
+  } else {
+    const uint64_t l0 = ctx->launches;
+    const uint32_t c0 = ctx->call_counter;
+    cudaGraph_t graph = nullptr;
+    CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    try { body(xs, ys); }
+    catch (...) { cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+    CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+    ge.launches = ctx->launches - l0;
+    ge.gen_calls = ctx->call_counter - c0;
+    CUDA_CHECK(cudaGraphInstantiate(&ge.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    CUDA_CHECK(cudaGraphLaunch(ge.exec, ctx->stream));   // the capture itself executed nothing
+  }
+  if (losses_host) {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(losses_host, ctx->loss_host, (size_t)nloss * 4);
+  }
 }
 
 // =============================================================================================
@@ -672,6 +742,7 @@ int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
   c->device = device; c->dt = precision == GAN_FP32 ? DT_F32 : DT_BF16; c->seed = seed;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost((void**)&c->loss_host, 16 * 4));
+  c->call_dev.ensure(16);
   umma_init();
   *out = c;
   API_END
@@ -681,6 +752,7 @@ int gan_ctx_destroy(gan_ctx* ctx) {
   if (!ctx) return GAN_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   comm_destroy(ctx);
   cudaFreeHost(ctx->loss_host);
   cudaStreamDestroy(ctx->stream);
@@ -694,7 +766,15 @@ int gan_ctx_sync(gan_ctx* ctx) {
   API_END
 }
 int gan_ctx_set_dropout(gan_ctx* ctx, int enabled) { ctx->dropout_enabled = enabled ? 1 : 0; return GAN_OK; }
-int gan_ctx_set_rng(gan_ctx* ctx, uint64_t seed, uint32_t call_counter) { ctx->seed = seed; ctx->call_counter = call_counter; return GAN_OK; }
+int gan_ctx_set_rng(gan_ctx* ctx, uint64_t seed, uint32_t call_counter) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->seed = seed; ctx->call_counter = call_counter; ctx->gen_calls_pending = 0;
+  CUDA_CHECK(cudaMemcpy(ctx->call_dev.p, &call_counter, 4, cudaMemcpyHostToDevice));
+  for (auto& kv : ctx->graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  ctx->graph_cache.clear();      // the seed is baked into captured kernels
+  API_END
+}
 int gan_ctx_get_call_counter(gan_ctx* ctx, uint32_t* out) { *out = ctx->call_counter; return GAN_OK; }
 int gan_ctx_set_engine(gan_ctx* ctx, int engine) { ctx->engine = engine; return GAN_OK; }
 int gan_ctx_set_graphs(gan_ctx* ctx, int enabled) { ctx->graphs = enabled; return GAN_OK; }
@@ -897,6 +977,7 @@ int gan_generator_forward(gan_net* g, const float* x, int batch, float* out) {
   size_t bytes = (size_t)batch * g->H * g->W * g->C * 4;
   const float* xd = stage_in(ctx, 0, x, bytes);
   generator_forward(g, 0, xd, batch, g->H, g->W);
+  bump_calls(ctx);
   copy_out(ctx, out, g->slots[0].out_f32.as<float>(), bytes);
   API_END
 }
@@ -922,6 +1003,7 @@ int gan_adam_create(gan_net* net, double lr, double beta1, double beta2, double 
   gan_adam* o = new gan_adam();
   o->net = net; o->lr = lr; o->b1 = beta1; o->b2 = beta2; o->eps = eps;
   o->m.ensure((size_t)(net->nparams + 4) * 4); o->v.ensure((size_t)(net->nparams + 4) * 4);
+  o->t_dev.ensure(16);
   *out = o;
   API_END
 }
@@ -931,7 +1013,14 @@ int gan_adam_destroy(gan_adam* opt) {
   API_END
 }
 int gan_adam_get_step(gan_adam* opt, int64_t* t) { *t = opt->t; return GAN_OK; }
-int gan_adam_set_step(gan_adam* opt, int64_t t) { opt->t = t; return GAN_OK; }
+int gan_adam_set_step(gan_adam* opt, int64_t t) {
+  API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(opt->net->ctx->stream));
+  opt->t = t;
+  long long tv = t;
+  CUDA_CHECK(cudaMemcpy(opt->t_dev.p, &tv, 8, cudaMemcpyHostToDevice));
+  API_END
+}
 int gan_adam_get_state(gan_adam* opt, int which, float* host_dst) {
   API_BEGIN
   CUDA_CHECK(cudaStreamSynchronize(opt->net->ctx->stream));
@@ -950,8 +1039,18 @@ int gan_pix2pix_train_step(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_
   API_BEGIN
   GAN_REQUIRE(g && d && input_image && target, "null argument");
   GAN_REQUIRE(!training || (g_opt && d_opt && g_opt->net == g && d_opt->net == d), "optimizers do not match the nets");
-  CUDA_CHECK(cudaSetDevice(g->ctx->device));
-  pix2pix_step(g, d, g_opt, d_opt, input_image, target, batch, lambda, training, losses);
+  gan_ctx* ctx = g->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->graphs || ctx->profile) {
+    pix2pix_step(g, d, g_opt, d_opt, input_image, target, batch, lambda, training, losses);
+  } else {
+    char key[160];
+    snprintf(key, sizeof(key), "p2p:%p:%p:%p:%p:%d:%d:%g", (void*)g, (void*)d, (void*)g_opt, (void*)d_opt, batch, training, (double)lambda);
+    const size_t img_bytes = (size_t)batch * g->H * g->W * g->C * 4;
+    run_step_graphed(ctx, key, input_image, target, img_bytes, losses, 4, std::vector<gan_net*>{g, d},
+                     training ? std::vector<gan_adam*>{g_opt, d_opt} : std::vector<gan_adam*>{},
+                     [&](const float* xs, const float* ys) { pix2pix_step(g, d, g_opt, d_opt, xs, ys, batch, lambda, training, nullptr); });
+  }
   API_END
 }
 
@@ -962,8 +1061,20 @@ int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, ga
   GAN_REQUIRE(g && f && dx && dy && real_x && real_y, "null argument");
   GAN_REQUIRE(!training || (g_opt && f_opt && dx_opt && dy_opt && g_opt->net == g && f_opt->net == f &&
                             dx_opt->net == dx && dy_opt->net == dy), "optimizers do not match the nets");
-  CUDA_CHECK(cudaSetDevice(g->ctx->device));
-  cyclegan_step(g, f, dx, dy, g_opt, f_opt, dx_opt, dy_opt, real_x, real_y, batch, lambda, training, losses);
+  gan_ctx* ctx = g->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->graphs || ctx->profile) {
+    cyclegan_step(g, f, dx, dy, g_opt, f_opt, dx_opt, dy_opt, real_x, real_y, batch, lambda, training, losses);
+  } else {
+    char key[200];
+    snprintf(key, sizeof(key), "cyc:%p:%p:%p:%p:%d:%d:%g", (void*)g, (void*)f, (void*)dx, (void*)dy, batch, training, (double)lambda);
+    const size_t img_bytes = (size_t)batch * g->H * g->W * g->C * 4;
+    run_step_graphed(ctx, key, real_x, real_y, img_bytes, losses, 7, std::vector<gan_net*>{g, f, dx, dy},
+                     training ? std::vector<gan_adam*>{g_opt, f_opt, dx_opt, dy_opt} : std::vector<gan_adam*>{},
+                     [&](const float* xs, const float* ys) {
+                       cyclegan_step(g, f, dx, dy, g_opt, f_opt, dx_opt, dy_opt, xs, ys, batch, lambda, training, nullptr);
+                     });
+  }
   API_END
 }
 

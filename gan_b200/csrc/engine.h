@@ -49,6 +49,12 @@ struct gan_ctx {
   DevBuf stage[4];
   float* loss_host = nullptr;   // pinned
   int n_losses = 0;
+  // device-resident dropout call counter (graph-replay safe) + generator calls since the last bump
+  DevBuf call_dev;
+  uint32_t gen_calls_pending = 0;
+  // captured train steps, keyed on (nets, batch, training)
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int warm = 0; uint32_t gen_calls = 0; };
+  std::map<std::string, GraphEntry> graph_cache;
   // profiling
   int profile = 0;
   std::vector<ProfEntry> prof;
@@ -86,7 +92,7 @@ struct Layer {
 // Saved state of one forward call of a net (the "tape" of that call).
 struct Slot {
   int B = 0, H = 0, W = 0;
-  uint32_t call_id = 0;
+  uint32_t call_id = 0, call_off = 0;
   int64_t sample0 = 0;
   std::vector<DevBuf> z;        // raw conv outputs per layer
   std::vector<DevBuf> stats;    // per layer: mean, inv, scale, shift, c1, c2  ([G][C] each)
@@ -111,13 +117,15 @@ struct gan_net {
   DevBuf params, grads, mov;
   std::vector<Slot> slots;
   bool packed_dirty = true;
+  DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
+  int pack_nent = 0, pack_tiles = 0;
 };
 
 struct gan_adam {
   gan_net* net = nullptr;
   double lr, b1, b2, eps;
-  int64_t t = 0;
-  DevBuf m, v;
+  int64_t t = 0;             // host mirror of *t_dev
+  DevBuf m, v, t_dev;
 };
 
 // comm.cu

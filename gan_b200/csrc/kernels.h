@@ -41,10 +41,15 @@ void launch_l1(Launch L, const float* a, const float* b, int64_t n, float* loss_
 // raw[j] = sum(slot j)/denom[j]; out[i] = sum_j mix[i*nraw+j]*raw[j]
 struct LossMix { int nraw, nout; float denom[LOSS_SLOTS]; float mix[8 * LOSS_SLOTS]; };
 void launch_loss_finalize(Launch L, const float* loss_ws, LossMix mix, float* out);
-void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
-                 float eps, float gscale);
+void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, const long long* t_dev, double lr,
+                 double b1, double b2, float eps, float gscale);
+void launch_bump(Launch L, long long* t64, uint32_t* c32, uint32_t by);   // device-resident step / dropout-call counters
 struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc, Kr, Nr; int64_t s_tap, s_k, s_n; };   // Kc/Nc padded, Kr/Nr real
 void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op);
+// All layers / roles of a net in ONE launch: 32x32 tiles, transposed through shared memory when the
+// master layout is contiguous along the packed N index.  `tab` is a device array of PackEntry.
+struct PackEntry { PackOp op; const float* master; void* dst; int tiles_k, tiles_n, tile_begin, pad; };
+void launch_pack_multi(Launch L, int dt, const PackEntry* tab_dev, int nent, int total_tiles);
 void launch_scale(Launch L, float* p, int64_t n, float s);
 
 // ---- conv_ffma.cu ---------------------------------------------------------------------------

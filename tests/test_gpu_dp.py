@@ -1,0 +1,78 @@
+"""GPU parity of the data-parallel train step on 2 GPUs (skipped on single-GPU boxes): one process
+per GPU, NCCL sum-all-reduce of the flat gradient buffers inside the library; result must equal the
+oracle's data-parallel definition (per-shard step with identical weights and per-replica BatchNorm,
+losses and gradients averaged — SURVEY 5.8/8e) and both ranks must end with identical weights."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+SEED = 123
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gan_b200 import Pix2Pix, shard_bounds
+    from helpers import make_pix2pix, load_model
+    from oracle import gan_oracle as O
+    cfg = dict(img_size=256, channels='3', learning_rate=2e-4, beta_1=0.5, beta_2=0.999, generator_loss='l1',
+               seed=SEED, precision='fp32', device=rank)
+    cfg['lambda'] = 100
+    m = Pix2Pix(cfg)                      # joins the NCCL communicator through torch.distributed
+    assert m.ctx.world == world and m.ctx.rank == rank
+    g_np, d_np = make_pix2pix(SEED + 1, 3, None)
+    load_model(m.generator, g_np); load_model(m.discriminator, d_np)
+    GB = 4
+    rng = np.random.default_rng(SEED)
+    x = O.synthetic_images(rng, GB, 256, 256, 3); y = O.synthetic_images(rng, GB, 256, 256, 3)
+    lo, hi = shard_bounds(GB, rank, world)
+    call0 = m.ctx.call_counter()
+    losses = [float(v) for v in m.train_step(x[lo:hi], y[lo:hi], True)]
+    wg = m.generator.get_flat_params(); wd = m.discriminator.get_flat_params()
+    gg = m.generator.get_flat_grads()
+    res = {"rank": rank, "losses": losses, "wg_sum": float(np.abs(wg).sum()), "wd_sum": float(np.abs(wd).sum())}
+    if rank == 0:
+        # oracle: data-parallel definition with the same global-sample-keyed dropout masks
+        gp, dp = O.to_torch(g_np, torch.float64), O.to_torch(d_np, torch.float64)
+        go, do = O.KerasAdam(gp), O.KerasAdam(dp)
+        masks = O.generator_keep_masks(SEED, call0, 0, GB, 256)
+        ref_losses, ref_gg, _ = O.pix2pix_train_step(gp, dp, go, do, torch.tensor(x, dtype=torch.float64),
+                                                     torch.tensor(y, dtype=torch.float64), 100.0, True, masks, world=world)
+        ref_flat = np.concatenate([g.numpy().ravel() for g in ref_gg])
+        # the library leaves the SUM over ranks in the gradient buffer (Adam divides by world)
+        res["grad_err"] = float(np.abs(gg / world - ref_flat).max() / np.abs(ref_flat).max())
+        res["ref_losses"] = ref_losses
+    q.put(res)
+    dist.barrier()
+    m.ctx.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_data_parallel_step_matches_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    out.sort(key=lambda r: r["rank"])
+    r0, r1 = out
+    assert r0["losses"] == r1["losses"]                      # losses are all-reduced means
+    assert r0["wg_sum"] == r1["wg_sum"] and r0["wd_sum"] == r1["wd_sum"]   # replicas stay identical
+    for a, r in zip(r0["losses"], r0["ref_losses"]):
+        assert abs(a - r) <= 1e-4 * max(1.0, abs(r)), (r0["losses"], r0["ref_losses"])
+    assert r0["grad_err"] < 3e-3, r0["grad_err"]            # batch-2 shards: fp32 conditioning level

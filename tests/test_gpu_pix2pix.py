@@ -242,3 +242,25 @@ def test_bf16_step_tracks_oracle():
     print(f"bf16 after 3 steps: gen_out l2_rel vs oracle at device weights={l2_sync:.3e}, vs free-running oracle={l2_free:.3e}")
     assert l2_sync < 1e-2
     m.ctx.close()
+
+
+def test_cuda_graph_replay_matches_eager():
+    """gan_ctx_set_graphs(1): the captured step (replayed from the 3rd call on) must reproduce the
+    eager step — same losses step after step (fresh dropout masks and Adam bias correction come from
+    device-resident counters) and the same weights, up to fp32 atomic-accumulation order."""
+    x, y = _inputs(2, 256, 3, seed=5)
+    runs = []
+    for graphs in (False, True):
+        m, _, _ = _build("bf16", 3)
+        m.ctx.set_graphs(graphs)
+        losses = [[float(v) for v in m.train_step(x, y, True)] for _ in range(5)]
+        val = [float(v) for v in m.train_step(x, y, False)]
+        runs.append((losses, val, m.generator.get_flat_params(), m.ctx.call_counter(), m.generator_optimizer.iterations))
+        m.ctx.close()
+    (l0, v0, w0, c0, t0), (l1, v1, w1, c1, t1) = runs
+    assert c0 == c1 == 6 and t0 == t1 == 5
+    for a, b in zip(l0 + [v0], l1 + [v1]):
+        for p, q in zip(a, b):
+            assert abs(p - q) <= 2e-3 * max(1.0, abs(q)), (l0, l1)
+    assert len({tuple(l) for l in l1}) == 5                     # every step differs: counters advance under replay
+    assert np.abs(w0 - w1).max() <= 2 * 5 * 2e-4 * 1.01
