@@ -107,6 +107,26 @@ template <> struct VecIO<bf16> {
   }
 };
 
+// Thread-private cp.async ring: each thread prefetches the 16-byte vectors it will consume itself
+// RING_STAGES-1 iterations ahead into its own shared-memory slots, so the bytes in flight per SM are
+// bounded by shared memory (not by registers) and no block-level synchronisation is needed.
+#define RING_STAGES 8
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;       // src-size 0: nothing is read, the slot is zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void unpack16(const uint4& t, float (&v)[4], const float*) {
+  v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+}
+__device__ __forceinline__ void unpack16(const uint4& t, float (&v)[8], const bf16*) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
 // 4-element vector access (16 B fp32 / 8 B bf16): used by the register-heavy normalisation kernels so
 // that several independent loads per thread stay in flight without dropping below 3 CTAs/SM.
 template <typename T> struct Vec4IO;

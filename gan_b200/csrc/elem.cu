@@ -228,53 +228,59 @@ __global__ void __launch_bounds__(256) k_norm_apply(const T* __restrict__ z, uin
                                                     int C, int lcv, const float* __restrict__ mean,
                                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                                     int act, DropKey dk, T* __restrict__ out, int out_pitch, int out_coff) {
-  constexpr int V = 4;
+  constexpr int V = VecIO<T>::N;
+  extern __shared__ uint4 ring[];                      // [RING_STAGES][256] thread-private slots
   const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
   const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
   const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
+  const uint32_t nit = prow < P ? (P - prow + pstride - 1) / pstride : 0;
   const bool affine = scale != nullptr;
   const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
   ChanParams<V> cp;
   int cur_g = -1;
   if (affine && G == 1) { load_chan_params<V>(cp, mean, scale, shift, c0); cur_g = 0; }
-  for (uint32_t p = prow; p < P; p += pstride * NORM_UNR) {
-    float v[NORM_UNR][V];
-#pragma unroll
-    for (int u = 0; u < NORM_UNR; ++u) {
-      uint32_t pp = p + u * pstride;
-      if (pp < P) Vec4IO<T>::load(z + (size_t)pp * C + c0, v[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < NORM_UNR; ++u) {
-      uint32_t pp = p + u * pstride;
-      if (pp >= P) break;
-      if (affine) {
-        if (G != 1) {
-          int g = (int)(pp / Pg);
-          if (g != cur_g) { load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0); cur_g = g; }
-        }
-#pragma unroll
-        for (int k = 0; k < V; ++k) v[u][k] = fmaf(v[u][k] - cp.mu[k], cp.sc[k], cp.sf[k]);
-      }
-      if (DROP) {
-        uint32_t smp = pp / HW, e0 = (pp - smp * HW) * C + c0;
-#pragma unroll
-        for (int k = 0; k < V; ++k) v[u][k] = dropout_keep(dk, call, smp, e0 + k) ? 2.f * v[u][k] : 0.f;
+  auto issue = [&](uint32_t it) {
+    const bool ok = it < nit;
+    cp_async16(&ring[(it % RING_STAGES) * 256 + threadIdx.x], z + (ok ? (size_t)(prow + it * pstride) * C + c0 : 0), ok);
+    cp_async_commit();
+  };
+  for (uint32_t it = 0; it < RING_STAGES - 1; ++it) issue(it);
+  for (uint32_t it = 0; it < nit; ++it) {
+    issue(it + RING_STAGES - 1);
+    cp_async_wait<RING_STAGES - 1>();
+    const uint32_t pp = prow + it * pstride;
+    float v[V];
+    unpack16(ring[(it % RING_STAGES) * 256 + threadIdx.x], v, (const T*)nullptr);
+    if (affine) {
+      if (G != 1) {
+        int g = (int)(pp / Pg);
+        if (g != cur_g) { load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0); cur_g = g; }
       }
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[u][k] = act_fwd(v[u][k], act);
-      Vec4IO<T>::store(out + (size_t)pp * out_pitch + out_coff + c0, v[u]);
+      for (int k = 0; k < V; ++k) v[k] = fmaf(v[k] - cp.mu[k], cp.sc[k], cp.sf[k]);
     }
+    if (DROP) {
+      uint32_t smp = pp / HW, e0 = (pp - smp * HW) * C + c0;
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = dropout_keep(dk, call, smp, e0 + k) ? 2.f * v[k] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = act_fwd(v[k], act);
+    VecIO<T>::store(out + (size_t)pp * out_pitch + out_coff + c0, v);
   }
 }
 
-static inline int norm_grid(int64_t P, int cv) {
-  // every thread owns one channel vector; rows are strided over the grid. ~8 CTAs/SM, fewer for tiny tensors
+// grid for the row-strided ring kernels: every thread owns one channel vector, rows are strided over
+// the grid; `per_sm` CTAs per SM (shared-memory bound), fewer for tiny tensors.
+static inline int norm_grid(int64_t P, int cv, int per_sm) {
   int64_t rows_per_block = 256 / cv;
-  int64_t want = (P + rows_per_block * NORM_UNR - 1) / (rows_per_block * NORM_UNR);
-  int64_t cap = (int64_t)NSM * 8;
+  int64_t want = (P + rows_per_block - 1) / rows_per_block;
+  int64_t cap = (int64_t)NSM * per_sm;
   if (want > cap) want = cap;
   return (int)(want < 1 ? 1 : want);
+}
+template <typename K> static void set_smem(K kern, size_t bytes) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, int G, int HW, int C,
@@ -282,11 +288,14 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
                        int out_pitch, int out_coff) {
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    const int cv = C / 4;
+    const int cv = C / VecIO<T>::N;
     GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
+    const size_t smem = (size_t)RING_STAGES * 256 * 16;
     auto kern = dk.enabled ? k_norm_apply<T, true> : k_norm_apply<T, false>;
-    kern<<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, ilog2(cv),
-                                                       mean, scale, shift, act, dk, (T*)out, out_pitch, out_coff);
+    static bool once = (set_smem(k_norm_apply<T, true>, smem), set_smem(k_norm_apply<T, false>, smem), true);
+    (void)once;
+    kern<<<norm_grid(P, cv, 5), 256, smem, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, ilog2(cv),
+                                                  mean, scale, shift, act, dk, (T*)out, out_pitch, out_coff);
   });
   KLAUNCH(L);
 }
@@ -296,12 +305,26 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
 //   g    = (d1 + d2) * act'(.) * dropout'      (gradient w.r.t. the affine output u = gamma*xhat+beta)
 //   dbeta = sum g, dgamma = sum g*xhat,  dz = gamma*inv * (g - mean(g) - xhat*mean(g*xhat))
 // ---------------------------------------------------------------------------------------------
+// Issue the cp.async copies of one iteration (z row vector + one or two gradient sources).
+template <typename T>
+__device__ __forceinline__ void ring_issue3(uint4* ring, uint32_t it, bool ok, const T* z, size_t zoff, const GradSrc& d1,
+                                            const GradSrc& d2, size_t p, int c0) {
+  const int narr = d2.p != nullptr ? 3 : 2;
+  uint4* slot = ring + ((it % RING_STAGES) * narr) * 256 + threadIdx.x;
+  cp_async16(slot, z + (ok ? zoff : 0), ok);
+  cp_async16(slot + 256, (const T*)d1.p + (ok ? p * d1.pitch + d1.coff + c0 : 0), ok);
+  if (narr == 3) cp_async16(slot + 512, (const T*)d2.p + (ok ? p * d2.pitch + d2.coff + c0 : 0), ok);
+  cp_async_commit();
+}
 template <typename T, int V>
-__device__ __forceinline__ void load_grad(const GradSrc& d1, const GradSrc& d2, size_t p, int c0, float (&g)[V]) {
-  Vec4IO<T>::load((const T*)d1.p + p * d1.pitch + d1.coff + c0, g);
-  if (d2.p != nullptr) {
+__device__ __forceinline__ void ring_read3(const uint4* ring, uint32_t it, bool has_d2, float (&v)[V], float (&g)[V]) {
+  const int narr = has_d2 ? 3 : 2;
+  const uint4* slot = ring + ((it % RING_STAGES) * narr) * 256 + threadIdx.x;
+  unpack16(slot[0], v, (const T*)nullptr);
+  unpack16(slot[256], g, (const T*)nullptr);
+  if (has_d2) {
     float h[V];
-    Vec4IO<T>::load((const T*)d2.p + p * d2.pitch + d2.coff + c0, h);
+    unpack16(slot[512], h, (const T*)nullptr);
 #pragma unroll
     for (int k = 0; k < V; ++k) g[k] += h[k];
   }
@@ -313,9 +336,8 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
                                                     const float* __restrict__ inv, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int act, DropKey dk,
                                                     float* __restrict__ ws) {
-  constexpr int V = 4;
-  __shared__ float sh_s[256 * V];
-  __shared__ float sh_q[256 * V];
+  constexpr int V = VecIO<T>::N;
+  extern __shared__ uint4 ring[];
   const int g = blockIdx.y, chunk = blockIdx.x;
   const int cv = 1 << lcv;
   const uint32_t rows_par = 256u >> lcv;
@@ -323,42 +345,44 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
   const uint32_t r = threadIdx.x >> lcv;
   const uint32_t per = (Pg + nchunk - 1) / nchunk;
   const uint32_t p0 = chunk * per, p1 = min(Pg, p0 + per);
+  const uint32_t first = p0 + r;
+  const uint32_t nit = first < p1 ? (p1 - first + rows_par - 1) / rows_par : 0;
+  const bool has_d2 = d2.p != nullptr;
   float s[V], q[V];
   ChanParams<V> cp;
   const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
   load_chan_params<V>(cp, mean, scale, shift, (size_t)g * C + c0);
 #pragma unroll
   for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  for (uint32_t pl = p0 + r; pl < p1; pl += rows_par * NORM_BWD_UNR) {
-    float v[NORM_BWD_UNR][V], gr[NORM_BWD_UNR][V];
+  auto issue = [&](uint32_t it) {
+    const bool ok = it < nit;
+    const size_t p = (size_t)g * Pg + first + (size_t)it * rows_par;
+    ring_issue3<T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
+  };
+  for (uint32_t it = 0; it < RING_STAGES - 1; ++it) issue(it);
+  for (uint32_t it = 0; it < nit; ++it) {
+    issue(it + RING_STAGES - 1);
+    cp_async_wait<RING_STAGES - 1>();
+    float v[V], gr[V];
+    ring_read3<T, V>(ring, it, has_d2, v, gr);
+    const uint32_t pg = g * Pg + first + it * rows_par;
+    uint32_t smp = 0, e0 = 0;
+    if (DROP) { smp = pg / HW; e0 = (pg - smp * HW) * C + c0; }
 #pragma unroll
-    for (int u = 0; u < NORM_BWD_UNR; ++u) {
-      uint32_t pp = pl + u * rows_par;
-      if (pp < p1) {
-        size_t p = (size_t)g * Pg + pp;
-        Vec4IO<T>::load(z + p * C + c0, v[u]);
-        load_grad<T, V>(d1, d2, p, c0, gr[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < NORM_BWD_UNR; ++u) {
-      uint32_t pp = pl + u * rows_par;
-      if (pp >= p1) break;
-      uint32_t pg = g * Pg + pp;
-      uint32_t smp = 0, e0 = 0;
-      if (DROP) { smp = pg / HW; e0 = (pg - smp * HW) * C + c0; }
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float xc = v[u][k] - cp.mu[k];
-        float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
-        float gg = gr[u][k] * act_bwd(uu, act);
-        if (DROP) gg = dropout_keep(dk, call, smp, e0 + k) ? 2.f * gg : 0.f;
-        s[k] += gg; q[k] = fmaf(gg, xc, q[k]);      // x_hat = xc*inv: inv is applied once after the loop
-      }
+    for (int k = 0; k < V; ++k) {
+      float xc = v[k] - cp.mu[k];
+      float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
+      float gg = gr[k] * act_bwd(uu, act);
+      if (DROP) gg = dropout_keep(dk, call, smp, e0 + k) ? 2.f * gg : 0.f;
+      s[k] += gg; q[k] = fmaf(gg, xc, q[k]);      // x_hat = xc*inv: inv is applied once after the loop
     }
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) q[i] *= __ldg(inv + (size_t)g * C + c0 + i);
+  cp_async_wait<0>();
+  __syncthreads();                                   // ring slots of other threads are reused for the reduction
+  float* sh_s = reinterpret_cast<float*>(ring);
+  float* sh_q = sh_s + 256 * V;
   block_col_reduce<V>(s, q, cv, C, sh_s, sh_q, ws + ((size_t)(g * nchunk + chunk) * 2) * C);
 }
 
@@ -381,10 +405,13 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    const float* __restrict__ c1, const float* __restrict__ c2, int act,
                                                    DropKey dk, T* __restrict__ dz) {
-  constexpr int V = 4;
+  constexpr int V = VecIO<T>::N;
+  extern __shared__ uint4 ring[];
   const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
   const int c0 = (int)(tid & ((1u << lcv) - 1)) * V;
   const uint32_t prow = tid >> lcv, pstride = (gridDim.x * 256u) >> lcv;
+  const uint32_t nit = prow < P ? (P - prow + pstride - 1) / pstride : 0;
+  const bool has_d2 = d2.p != nullptr;
   ChanParams<V> cp;
   float iv[V], k1[V], k2[V];
   int cur_g = -1;
@@ -397,36 +424,35 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
     cur_g = g;
   };
   if (norm != NORM_NONE && G == 1) load_all(0);
-  for (uint32_t p = prow; p < P; p += pstride * NORM_BWD_UNR) {
-    float v[NORM_BWD_UNR][V], gr[NORM_BWD_UNR][V];
+  auto issue = [&](uint32_t it) {
+    const bool ok = it < nit;
+    const size_t p = (size_t)prow + (size_t)it * pstride;
+    ring_issue3<T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
+  };
+  for (uint32_t it = 0; it < RING_STAGES - 1; ++it) issue(it);
+  for (uint32_t it = 0; it < nit; ++it) {
+    issue(it + RING_STAGES - 1);
+    cp_async_wait<RING_STAGES - 1>();
+    const uint32_t pp = prow + it * pstride;
+    float v[V], gr[V], o[V];
+    ring_read3<T, V>(ring, it, has_d2, v, gr);
+    if (norm == NORM_NONE) {
 #pragma unroll
-    for (int u = 0; u < NORM_BWD_UNR; ++u) {
-      uint32_t pp = p + u * pstride;
-      if (pp < P) { Vec4IO<T>::load(z + (size_t)pp * C + c0, v[u]); load_grad<T, V>(d1, d2, pp, c0, gr[u]); }
-    }
+      for (int k = 0; k < V; ++k) o[k] = gr[k] * act_bwd(v[k], act);
+    } else {
+      if (G != 1) { int g = (int)(pp / Pg); if (g != cur_g) load_all(g); }
+      uint32_t smp = 0, e0 = 0;
+      if (DROP) { smp = pp / HW; e0 = (pp - smp * HW) * C + c0; }
 #pragma unroll
-    for (int u = 0; u < NORM_BWD_UNR; ++u) {
-      uint32_t pp = p + u * pstride;
-      if (pp >= P) break;
-      float o[V];
-      if (norm == NORM_NONE) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) o[k] = gr[u][k] * act_bwd(v[u][k], act);
-      } else {
-        if (G != 1) { int g = (int)(pp / Pg); if (g != cur_g) load_all(g); }
-        uint32_t smp = 0, e0 = 0;
-        if (DROP) { smp = pp / HW; e0 = (pp - smp * HW) * C + c0; }
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          float xc = v[u][k] - cp.mu[k];
-          float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
-          float gg = gr[u][k] * act_bwd(uu, act);
-          if (DROP) gg = dropout_keep(dk, call, smp, e0 + k) ? 2.f * gg : 0.f;
-          o[k] = cp.sc[k] * (gg - k1[k] - xc * iv[k] * k2[k]);
-        }
+      for (int k = 0; k < V; ++k) {
+        float xc = v[k] - cp.mu[k];
+        float uu = fmaf(xc, cp.sc[k], cp.sf[k]);
+        float gg = gr[k] * act_bwd(uu, act);
+        if (DROP) gg = dropout_keep(dk, call, smp, e0 + k) ? 2.f * gg : 0.f;
+        o[k] = cp.sc[k] * (gg - k1[k] - xc * iv[k] * k2[k]);
       }
-      Vec4IO<T>::store(dz + (size_t)pp * C + c0, o);
     }
+    VecIO<T>::store(dz + (size_t)pp * C + c0, o);
   }
 }
 
@@ -436,20 +462,26 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
   int nchunk = stats_chunks(G, Pg);
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    const int cv = C / 4;
+    const int cv = C / VecIO<T>::N;
     GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
     const int lcv = ilog2(cv);
+    const int narr = d2.p != nullptr ? 3 : 2;
+    const size_t smem = (size_t)RING_STAGES * narr * 256 * 16;
+    const size_t smem_max = (size_t)RING_STAGES * 3 * 256 * 16;
+    static bool once = (set_smem(k_bwd_reduce<T, true>, smem_max), set_smem(k_bwd_reduce<T, false>, smem_max),
+                        set_smem(k_bwd_apply<T, true>, smem_max), set_smem(k_bwd_apply<T, false>, smem_max), true);
+    (void)once;
     if (norm != NORM_NONE) {
       auto kred = dk.enabled ? k_bwd_reduce<T, true> : k_bwd_reduce<T, false>;
-      kred<<<dim3(nchunk, G), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean,
-                                                       inv, scale, shift, act, dk, ws);
+      kred<<<dim3(nchunk, G), 256, smem, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean, inv,
+                                                scale, shift, act, dk, ws);
       KLAUNCH(L);
       k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
       KLAUNCH(L);
     }
     auto kapp = dk.enabled ? k_bwd_apply<T, true> : k_bwd_apply<T, false>;
-    kapp<<<norm_grid(P, cv), 256, 0, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW, C, lcv,
-                                                      norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz);
+    kapp<<<norm_grid(P, cv, narr == 3 ? 2 : 3), 256, smem, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW,
+                                                                 C, lcv, norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz);
     KLAUNCH(L);
   });
 }
