@@ -85,6 +85,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -183,6 +186,7 @@ struct alignas(64) UmmaFwdParams {
   bf16* out; int out_pitch, out_coff, Hout, Wout, so;
   int N, Hm, Wm, Nc;
   const float* bias; float* out_f32; int epi, Nr;
+  int num_tiles;
 };
 
 constexpr int FWD_STAGES = 3;
@@ -194,6 +198,10 @@ __device__ __forceinline__ float epi_apply(float v, int epi, const float* bias, 
   return v;
 }
 
+// Persistent: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x, M-tile index
+// fastest so that concurrently running CTAs share the same weight tile in L2).  Two TMEM accumulator
+// buffers: the epilogue warps drain tile i while the MMA warp already accumulates tile i+1, and the
+// TMA producer runs ahead across tile boundaries through the shared-memory ring.
 template <int BN, int KC>
 __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_constant__ UmmaFwdParams p) {
   constexpr int SW = (KC == 64) ? 128 : 32;
@@ -203,23 +211,19 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + FWD_STAGES * STAGE_BYTES);
   uint64_t* empty = full + FWD_STAGES;
-  uint64_t* tmem_full = empty + FWD_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = empty + FWD_STAGES;          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;              // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.z;
-  const int n0 = blockIdx.y * BN;
-  int tm = blockIdx.x;
-  const int tw_i = tm % p.tiles_w; tm /= p.tiles_w;
-  const int th_i = tm % p.tiles_h; tm /= p.tiles_h;
-  const int w0 = tw_i * p.TW, h0 = th_i * p.TH, b0 = tm * p.TN;
-  const int ntaps = p.ntaps[cls];
-  const int nk = (KC == 64) ? ntaps * p.kchunks : ntaps / SUB;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int ntn = p.Nc / BN;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.bmap);
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < FWD_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    ptx::mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -236,98 +240,133 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> (class, n-tile, M-space origin)
+  auto decode = [&](int tile, int& cls, int& n0, int& w0, int& h0, int& b0) {
+    int tm = tile % tiles_m; int r = tile / tiles_m;
+    n0 = (r % ntn) * BN; cls = r / ntn;
+    w0 = (tm % p.tiles_w) * p.TW; tm /= p.tiles_w;
+    h0 = (tm % p.tiles_h) * p.TH; tm /= p.tiles_h;
+    b0 = tm * p.TN;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % FWD_STAGES;
-        const uint32_t ph = (kb / FWD_STAGES) & 1;
-        ptx::mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
-        if (KC == 64) {
-          const int t = kb / p.kchunks, kc = kb - t * p.kchunks;
-          ptx::tma_load_4d(sa, &p.amap[p.tap_map[cls][t]], &full[s], kc * 64, w0 + p.tap_dw[cls][t], h0 + p.tap_dh[cls][t], b0);
-          ptx::tma_load_2d(sa + A_BYTES, &p.bmap, &full[s], kb * 64, cls * p.Nc + n0);
-        } else {
+      uint32_t it = 0;                               // global k-block counter (ring position)
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int cls, n0, w0, h0, b0;
+        decode(tile, cls, n0, w0, h0, b0);
+        const int nk = (KC == 64) ? p.ntaps[cls] * p.kchunks : p.ntaps[cls] / SUB;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % FWD_STAGES;
+          const uint32_t ph = (it / FWD_STAGES) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
+          if (KC == 64) {
+            const int t = kb / p.kchunks, kc = kb - t * p.kchunks;
+            ptx::tma_load_4d(sa, &p.amap[p.tap_map[cls][t]], &full[s], kc * 64, w0 + p.tap_dw[cls][t], h0 + p.tap_dh[cls][t], b0);
+            ptx::tma_load_2d(sa + A_BYTES, &p.bmap, &full[s], kb * 64, cls * p.Nc + n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < SUB; ++j) {
-            const int t = kb * SUB + j;
-            ptx::tma_load_4d(sa + j * A_SUB, &p.amap[p.tap_map[cls][t]], &full[s], 0, w0 + p.tap_dw[cls][t],
-                             h0 + p.tap_dh[cls][t], b0);
-            ptx::tma_load_2d(sa + A_BYTES + j * B_SUB, &p.bmap, &full[s], t * KC, cls * p.Nc + n0);
+            for (int j = 0; j < SUB; ++j) {
+              const int t = kb * SUB + j;
+              ptx::tma_load_4d(sa + j * A_SUB, &p.amap[p.tap_map[cls][t]], &full[s], 0, w0 + p.tap_dw[cls][t],
+                               h0 + p.tap_dh[cls][t], b0);
+              ptx::tma_load_2d(sa + A_BYTES + j * B_SUB, &p.bmap, &full[s], t * KC, cls * p.Nc + n0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % FWD_STAGES;
-      const uint32_t ph = (kb / FWD_STAGES) & 1;
-      ptx::mbar_wait(&full[s], ph);
+    uint32_t it = 0, li = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
+      const int cls = tile / (tiles_m * ntn);
+      const int nk = (KC == 64) ? p.ntaps[cls] * p.kchunks : p.ntaps[cls] / SUB;
+      const uint32_t buf = li & 1, use = li >> 1;
+      ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t acc = tmem_base + buf * ACC_COLS;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % FWD_STAGES;
+        const uint32_t ph = (it / FWD_STAGES) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // KC==64: +32 B inside the 128-byte swizzle atom per K=16; KC==16: one 32-byte-swizzled box per K=16
-          const uint64_t ad = (KC == 64) ? desc_kmajor<SW>(sa) + 2 * k : desc_kmajor<SW>(sa + k * A_SUB);
-          const uint64_t bd = (KC == 64) ? desc_kmajor<SW>(sa + A_BYTES) + 2 * k : desc_kmajor<SW>(sa + A_BYTES + k * B_SUB);
-          ptx::umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            // KC==64: +32 B inside the 128-byte swizzle atom per K=16; KC==16: one 32-byte-swizzled box per K=16
+            const uint64_t ad = (KC == 64) ? desc_kmajor<SW>(sa) + 2 * k : desc_kmajor<SW>(sa + k * A_SUB);
+            const uint64_t bd = (KC == 64) ? desc_kmajor<SW>(sa + A_BYTES) + 2 * k : desc_kmajor<SW>(sa + A_BYTES + k * B_SUB);
+            ptx::umma_bf16(acc, ad, bd, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty[s]);
+          if (kb == nk - 1) ptx::umma_commit(&tmem_full[buf]);
         }
-        ptx::umma_commit(&empty[s]);
-        if (kb == nk - 1) ptx::umma_commit(tmem_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                    // accumulator row == M-space point inside the tile
     const int wl = r % p.TW, hl = (r / p.TW) % p.TH, nl = r / (p.TW * p.TH);
-    const int mw = w0 + wl, mh = h0 + hl, nb = b0 + nl;
-    const int oh = mh * p.so + p.oa[cls], ow = mw * p.so + p.ob[cls];
-    const bool valid = nb < p.N && mh < p.Hm && mw < p.Wm && oh < p.Hout && ow < p.Wout;
-    const int64_t pix = ((int64_t)nb * p.Hout + oh) * p.Wout + ow;
-    bf16* dst = p.out + pix * p.out_pitch + p.out_coff + n0;
-    ptx::mbar_wait(tmem_full, 0);
-    ptx::tc_fence_after();
-    if (BN >= 32) {
+    uint32_t li = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
+      int cls, n0, w0, h0, b0;
+      decode(tile, cls, n0, w0, h0, b0);
+      const uint32_t buf = li & 1, use = li >> 1;
+      const int mw = w0 + wl, mh = h0 + hl, nb = b0 + nl;
+      const int oh = mh * p.so + p.oa[cls], ow = mw * p.so + p.ob[cls];
+      const bool valid = nb < p.N && mh < p.Hm && mw < p.Wm && oh < p.Hout && ow < p.Wout;
+      const int64_t pix = ((int64_t)nb * p.Hout + oh) * p.Wout + ow;
+      bf16* dst = p.out + pix * p.out_pitch + p.out_coff + n0;
+      ptx::mbar_wait(&tmem_full[buf], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      if (BN >= 32) {
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(acc + c, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
+              *reinterpret_cast<uint4*>(dst + c + j * 8) = o;
+            }
+          }
+        }
+      } else {
+        // N = 16 tile: channel-padded heads (fp32 output with bias / tanh) and padded data gradients
+        uint32_t v[16];
+        ptx::tmem_ld16(acc, v);
         if (valid) {
+          if (p.out_f32 != nullptr) {
+            for (int n = 0; n < p.Nr; ++n) p.out_f32[pix * p.Nr + n] = epi_apply(__uint_as_float(v[n]), p.epi, p.bias, n);
+          }
+          if (p.out != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+            for (int j = 0; j < 2; ++j) {
+              uint4 o;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
-            *reinterpret_cast<uint4*>(dst + c + j * 8) = o;
+              for (int e = 0; e < 4; ++e)
+                h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
+              *reinterpret_cast<uint4*>(dst + j * 8) = o;
+            }
           }
         }
       }
-    } else {
-      // N = 16 tile: channel-padded heads (fp32 output with bias / tanh) and padded data gradients
-      uint32_t v[16];
-      ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), v);
-      if (valid) {
-        if (p.out_f32 != nullptr) {
-          for (int n = 0; n < p.Nr; ++n) p.out_f32[pix * p.Nr + n] = epi_apply(__uint_as_float(v[n]), p.epi, p.bias, n);
-        }
-        if (p.out != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 o;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
-            *reinterpret_cast<uint4*>(dst + j * 8) = o;
-          }
-        }
-      }
+      // accumulator buffer fully read into registers: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
     }
   }
   ptx::tc_fence_before();
@@ -335,7 +374,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-static size_t fwd_smem_bytes(int BN) { return (size_t)FWD_STAGES * (128 * 128 + BN * 128) + 1024 + 128; }
+static size_t fwd_smem_bytes(int BN) { return (size_t)FWD_STAGES * (128 * 128 + BN * 128) + 1024 + 256; }
 
 static bool view_ok(int pitch, int coff, const void* p) {
   return pitch % 8 == 0 && coff % 8 == 0 && ((uintptr_t)p % 16) == 0;
@@ -402,7 +441,8 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   const int KC = op.Kc == 16 ? 16 : 64;
   UmmaFwdParams P;
   fill_fwd_params(P, op, BN, KC);
-  dim3 grid(P.tiles_w * P.tiles_h * P.tiles_n, op.Nc / BN, op.ncls);
+  P.num_tiles = P.tiles_w * P.tiles_h * P.tiles_n * (op.Nc / BN) * op.ncls;
+  dim3 grid(P.num_tiles < 2 * 148 ? P.num_tiles : 2 * 148);       // persistent: 2 CTAs per SM
   const size_t sm = fwd_smem_bytes(BN);
   if (KC == 64) {
     if (BN == 128) k_conv_fwd_umma<128, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);

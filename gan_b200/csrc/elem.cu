@@ -137,13 +137,24 @@ __global__ void __launch_bounds__(256) k_stats_partial(const T* __restrict__ z, 
 
 // Stage 2: one block per (32 channels, group): 8 chunk-lanes per channel sum the partials in
 // double, shared-memory tree over the lanes, then mean / inv-std / fused scale are emitted.
-#define FIN_LANES 8
+#define FIN_LANES 32
 __device__ __forceinline__ void fin_reduce(const float* __restrict__ ws, int g, int nchunk, int C, int c, int lane,
                                            double& S, double& Q) {
   __shared__ double sh[2][FIN_LANES][32];
   double s = 0.0, q = 0.0;
   if (c < C) {
-    for (int k = lane; k < nchunk; k += FIN_LANES) {
+    int k = lane;
+    for (; k + 3 * FIN_LANES < nchunk; k += 4 * FIN_LANES) {       // 8 independent loads in flight per thread
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* o = ws + ((size_t)(g * nchunk + k + u * FIN_LANES) * 2) * C;
+        a[u] = __ldg(o + c); b[u] = __ldg(o + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s += (double)a[u]; q += (double)b[u]; }
+    }
+    for (; k < nchunk; k += FIN_LANES) {
       const float* o = ws + ((size_t)(g * nchunk + k) * 2) * C;
       s += (double)__ldg(o + c); q += (double)__ldg(o + C + c);
     }
