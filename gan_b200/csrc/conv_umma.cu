@@ -647,8 +647,10 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   const int mblocks = ntaps * op.Kc / 128;
   const int ntiles = op.Nc / BN;
   const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_n;
+  // split the pixel reduction so that all CTAs form ONE full wave (2 CTAs/SM): equal-length CTAs
+  // make any partial second wave pure tail
   int64_t ctas = (int64_t)mblocks * ntiles * op.ncls;
-  int splits = (int)((148 * 2 + ctas - 1) / ctas);
+  int splits = (int)((148 * 2) / ctas);
   if (splits > total_boxes) splits = total_boxes;
   if (splits < 1) splits = 1;
   P.splits = splits;
