@@ -57,11 +57,44 @@ void comm_init(gan_ctx* ctx, int rank, int world, const void* id128) {
   ncclComm_t_ c = nullptr;
   nccl_check(g_nccl.initrank(&c, world, id, rank), "ncclCommInitRank");
   ctx->comm = c;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; ++i) {
+    cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->comm_events.push_back(e);
+  }
 }
 
 void comm_destroy(gan_ctx* ctx) {
   if (ctx->comm && g_nccl.destroy) g_nccl.destroy((ncclComm_t_)ctx->comm);
   ctx->comm = nullptr;
+  for (auto e : ctx->comm_events) cudaEventDestroy(e);
+  ctx->comm_events.clear();
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  ctx->comm_stream = nullptr;
+}
+
+static cudaEvent_t next_event(gan_ctx* ctx) {
+  cudaEvent_t e = ctx->comm_events[ctx->comm_ev_next % ctx->comm_events.size()];
+  ctx->comm_ev_next++;
+  return e;
+}
+
+void comm_allreduce_async(gan_ctx* ctx, float* buf, int64_t n) {
+  if (ctx->world <= 1 || n <= 0) return;
+  GAN_REQUIRE(ctx->comm != nullptr, "communicator not initialised");
+  cudaEvent_t e = next_event(ctx);
+  CUDA_CHECK(cudaEventRecord(e, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, e, 0));
+  nccl_check(g_nccl.allreduce(buf, buf, (size_t)n, 7, 0, (ncclComm_t_)ctx->comm, ctx->comm_stream), "ncclAllReduce");
+  ctx->comm_pending = true;
+}
+
+void comm_join(gan_ctx* ctx) {
+  if (!ctx->comm_pending) return;
+  cudaEvent_t e = next_event(ctx);
+  CUDA_CHECK(cudaEventRecord(e, ctx->comm_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e, 0));
+  ctx->comm_pending = false;
 }
 
 // Sum-all-reduce of an fp32 buffer, enqueued on the ctx stream (ncclFloat32 = 7, ncclSum = 0).

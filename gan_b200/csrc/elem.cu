@@ -771,3 +771,82 @@ void launch_pack_multi(Launch L, int dt, const PackEntry* tab_dev, int nent, int
   });
   KLAUNCH(L);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Fused Keras-Adam + packing (see kernels.h)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float adam_lr_t(const AdamArgs& a) {
+  const double t = (double)(*a.t_dev);
+  return (float)(a.lr * sqrt(1.0 - pow(a.b2, t)) / (1.0 - pow(a.b1, t)));
+}
+__device__ __forceinline__ float adam_update(const AdamArgs& a, long long i, float lr_t, float b1, float b2) {
+  float gr = a.g[i] * a.gscale, mm = a.m[i], vv = a.v[i], pp = a.p[i];
+  mm += (gr - mm) * (1.f - b1);
+  vv += (gr * gr - vv) * (1.f - b2);
+  pp -= lr_t * mm / (sqrtf(vv) + a.eps);
+  a.m[i] = mm; a.v[i] = vv; a.p[i] = pp;
+  return pp;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEntry* __restrict__ tab, int nent) {
+  __shared__ float tile[32][33];
+  __shared__ int s_e;
+  __shared__ float s_lr;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < nent && (int)blockIdx.x >= tab[e + 1].tile_begin) ++e;
+    s_e = e;
+    s_lr = adam_lr_t(a);
+  }
+  __syncthreads();
+  const AdamPackEntry& E = tab[s_e];
+  const float lr_t = s_lr, b1 = (float)a.b1, b2 = (float)a.b2;
+  int lt = blockIdx.x - E.tile_begin;
+  const int tb = lt % E.tiles_b; lt /= E.tiles_b;
+  const int ta = lt % E.tiles_a; const int widx = lt / E.tiles_a;
+  const int a0 = ta * 32, b0 = tb * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int cF = E.invF[widx] >> 4, tF = E.invF[widx] & 15, cD = E.invD[widx] >> 4, tD = E.invD[widx] & 15;
+  T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
+  T* __restrict__ dD = (T*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
+  const long long base = E.w_off + (long long)widx * E.A * E.B;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int ai = a0 + r, bi = b0 + tx;
+    float pn = 0.f;
+    if (ai < E.A && bi < E.B) {
+      pn = adam_update(a, base + (long long)ai * E.B + bi, lr_t, b1, b2);
+      // destination that is contiguous along the master's fast index b
+      if (E.conv2d) dD[(long long)ai * E.KtotD + bi] = from_f<T>(pn);        // ci = a, co = b
+      else dF[(long long)ai * E.KtotF + bi] = from_f<T>(pn);                 // co = a, ci = b
+    }
+    tile[r][tx] = pn;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int bi = b0 + r, ai = a0 + tx;
+    if (ai < E.A && bi < E.B) {
+      if (E.conv2d) dF[(long long)bi * E.KtotF + ai] = from_f<T>(tile[tx][r]);   // co = b, ci = a
+      else dD[(long long)bi * E.KtotD + ai] = from_f<T>(tile[tx][r]);            // ci = b, co = a
+    }
+  }
+}
+void launch_adam_pack(Launch L, int dt, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles) {
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_adam_pack<T><<<total_tiles, 256, 0, L.s>>>(a, tab_dev, nent);
+  });
+  KLAUNCH(L);
+}
+
+__global__ void __launch_bounds__(256) k_adam_ranges(AdamArgs a, const AdamRange* __restrict__ tab) {
+  const AdamRange r = tab[blockIdx.x];
+  const float lr_t = adam_lr_t(a), b1 = (float)a.b1, b2 = (float)a.b2;
+  for (int i = threadIdx.x; i < r.n; i += 256) adam_update(a, r.off + i, lr_t, b1, b2);
+}
+void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, int nranges) {
+  k_adam_ranges<<<nranges, 256, 0, L.s>>>(a, tab_dev);
+  KLAUNCH(L);
+}

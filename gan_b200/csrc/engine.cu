@@ -380,8 +380,11 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
 
 // Backward through one generator call.  d1/d2: extra gradient sources w.r.t. the tanh output
 // (activation dtype); ref/l1_coef: + l1_coef*sign(out-ref).  Accumulates into g->grads.
+// `final_call`: this is the last contribution to g->grads in the step, so finished gradient ranges
+// can be all-reduced on the communication stream while the rest of the sweep still runs (buckets in
+// backward-completion order: [up5..last], [up1..up4], [down1..down8]).
 static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, const float* ref_f32, float l1_coef,
-                               bool want_input_grad) {
+                               bool want_input_grad, bool final_call = false) {
   gan_ctx* ctx = g->ctx;
   Slot& s = g->slots[slot];
   const int B = s.B, H = s.H, W = s.W, C = g->C;
@@ -409,6 +412,10 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
     if (k == 1) din = make_view(s.dd8.p, B, H >> 8, W >> 8, 512);
     else { int pp = UP_F[k - 2] + DOWN_F[8 - k]; din = make_view(s.dcat[k - 2].p, B, H >> (9 - k), W >> (9 - k), pp); }
     layer_backward(g, s, 7 + k, src, GradSrc{nullptr, 0, 0}, din, true);
+    if (final_call && ctx->world > 1) {
+      if (k == 5) comm_allreduce_async(ctx, gr + g->layers[12].w_off, g->nparams - g->layers[12].w_off);
+      if (k == 1) comm_allreduce_async(ctx, gr + g->layers[8].w_off, g->layers[12].w_off - g->layers[8].w_off);
+    }
   }
   for (int j = 8; j >= 1; --j) {
     GradSrc a, b{nullptr, 0, 0};
@@ -428,6 +435,7 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
     }
     layer_backward(g, s, j - 1, a, b, din, true);
   }
+  if (final_call && ctx->world > 1) comm_allreduce_async(ctx, gr, g->layers[8].w_off);
 }
 
 // inp/tar: device fp32 (B,H,W,C); tar may be nullptr when target == false.
@@ -511,19 +519,56 @@ static void copy_out(gan_ctx* ctx, float* dst, const float* src_dev, size_t byte
 static void zero_grads(gan_net* n) {
   CUDA_CHECK(cudaMemsetAsync(n->grads.p, 0, (size_t)n->nparams * 4, n->ctx->stream));
 }
-static void adam_apply(gan_adam* o) {
+static void build_adam_tables(gan_net* n) {
+  pack_weights(n);                                   // makes sure the packed buffers exist
+  std::vector<AdamPackEntry> tab;
+  std::vector<AdamRange> ranges;
+  int tiles = 0;
+  for (auto& ly : n->layers) {
+    AdamPackEntry e; memset(&e, 0, sizeof(e));
+    e.w_off = ly.w_off;
+    e.conv2d = ly.kind != K_CONVT_S2;
+    e.A = e.conv2d ? ly.Cin : ly.Cout; e.B = e.conv2d ? ly.Cout : ly.Cin;
+    e.dstF = ly.wp_fwd.p; e.dstD = ly.wp_dgrad.p;
+    ClassGeom cf[4], cd[4];
+    int nf = fill_geometry(ly.kind, R_FWD, cf), nd = fill_geometry(ly.kind, R_DGRAD, cd);
+    e.KcF = ly.Cin_p; e.KtotF = cf[0].ntaps * ly.Cin_p; e.KcD = ly.Cout_p; e.KtotD = cd[0].ntaps * ly.Cout_p;
+    for (int c = 0; c < nf; ++c) {
+      e.boffF[c] = (long long)c * ly.Cout_p * e.KtotF;
+      for (int t = 0; t < cf[c].ntaps; ++t) e.invF[cf[c].widx[t]] = (int8_t)((c << 4) | t);
+    }
+    for (int c = 0; c < nd; ++c) {
+      e.boffD[c] = (long long)c * ly.Cin_p * e.KtotD;
+      for (int t = 0; t < cd[c].ntaps; ++t) e.invD[cd[c].widx[t]] = (int8_t)((c << 4) | t);
+    }
+    e.tiles_a = (e.A + 31) / 32; e.tiles_b = (e.B + 31) / 32;
+    e.tile_begin = tiles;
+    tiles += 16 * e.tiles_a * e.tiles_b;
+    tab.push_back(e);
+    if (ly.g_off >= 0) { ranges.push_back(AdamRange{ly.g_off, ly.Cout, 0}); ranges.push_back(AdamRange{ly.b_off, ly.Cout, 0}); }
+    if (ly.bias_off >= 0) ranges.push_back(AdamRange{ly.bias_off, ly.Cout, 0});
+  }
+  n->adam_tab.ensure(tab.size() * sizeof(AdamPackEntry));
+  CUDA_CHECK(cudaMemcpy(n->adam_tab.p, tab.data(), tab.size() * sizeof(AdamPackEntry), cudaMemcpyHostToDevice));
+  n->adam_ranges.ensure(ranges.size() * sizeof(AdamRange));
+  CUDA_CHECK(cudaMemcpy(n->adam_ranges.p, ranges.data(), ranges.size() * sizeof(AdamRange), cudaMemcpyHostToDevice));
+  n->adam_nent = (int)tab.size(); n->adam_tiles = tiles; n->adam_nranges = (int)ranges.size();
+}
+
+// `reduced`: the gradient buffer has already been all-reduced (overlapped buckets + comm_join).
+static void adam_apply(gan_adam* o, bool reduced = false) {
   gan_net* n = o->net; gan_ctx* ctx = n->ctx;
-  if (ctx->world > 1) comm_allreduce_sum(ctx, n->grads.as<float>(), n->nparams);
+  if (n->adam_nent == 0) build_adam_tables(n);
+  if (ctx->world > 1 && !reduced) comm_allreduce_sum(ctx, n->grads.as<float>(), n->nparams);
   o->t += 1;
   launch_bump(ctx->L(), o->t_dev.as<long long>(), nullptr, 1);
-  {
-    ProfScope ps(ctx, FAM_ADAM, 28.0 * (double)n->nparams);
-    launch_adam(ctx->L(), n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), n->nparams,
-                o->t_dev.as<long long>(), o->lr, o->b1, o->b2, (float)o->eps, 1.f / (float)ctx->world);
-  }
-  n->packed_dirty = true;
-  ProfScope ps(ctx, FAM_PACK, (double)n->nparams * (4.0 + 2.0 * ctx->esize()));
-  pack_weights(n);
+  AdamArgs a{n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), o->t_dev.as<long long>(),
+             o->lr, o->b1, o->b2, (float)o->eps, 1.f / (float)ctx->world};
+  // fused update + repack: 28 B/param of optimizer traffic + 4 B/param for the two packed bf16 copies
+  ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
+  launch_adam_pack(ctx->L(), ctx->dt, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
+  launch_adam_ranges(ctx->L(), a, (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
+  n->packed_dirty = false;
 }
 static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {
   ctx->loss_out.ensure(16 * 4);
@@ -578,14 +623,18 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   disc_bce(d, 0, 1.f, 0.5f, training, true, 2);
   if (training) discriminator_backward(d, 0, true, false);
   disc_bce(d, 1, 0.f, 0.5f, training, true, 3);
-  if (training) discriminator_backward(d, 1, true, false);
+  if (training) {
+    discriminator_backward(d, 1, true, false);
+    comm_allreduce_async(ctx, d->grads.as<float>(), d->nparams);          // D gradients final: reduce under G's backward
+  }
   disc_bce(d, 1, 1.f, 1.0f, training, false, 0);
   if (training) {
     discriminator_backward(d, 1, false, true);                           // dL_G/d(gen_output) through D (:210)
     GradSrc dgan{d->slots[1].din0.p, d->Cin0_p, C};
-    generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, lambda / (float)n_img, false);
-    adam_apply(go);                                                      // (:213)
-    adam_apply(dopt);                                                    // (:215)
+    generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, lambda / (float)n_img, false, true);
+    comm_join(ctx);
+    adam_apply(go, true);                                                // (:213)
+    adam_apply(dopt, true);                                              // (:215)
   }
   LossMix mix; memset(&mix, 0, sizeof(mix));
   mix.nraw = 4; mix.nout = 4;

@@ -66,6 +66,10 @@ struct gan_ctx {
   // data parallel
   void* comm = nullptr;
   int rank = 0, world = 1;
+  cudaStream_t comm_stream = nullptr;     // gradient all-reduces run here, overlapped with backward
+  std::vector<cudaEvent_t> comm_events;   // fork/join events (reused round-robin)
+  size_t comm_ev_next = 0;
+  bool comm_pending = false;
   Launch L() { return Launch{stream, &launches}; }
   size_t esize() const { return dt == DT_F32 ? 4 : 2; }
 };
@@ -119,6 +123,8 @@ struct gan_net {
   bool packed_dirty = true;
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
   int pack_nent = 0, pack_tiles = 0;
+  DevBuf adam_tab, adam_ranges;   // fused Adam+pack tables (AdamPackEntry / AdamRange)
+  int adam_nent = 0, adam_tiles = 0, adam_nranges = 0;
 };
 
 struct gan_adam {
@@ -133,3 +139,7 @@ int comm_unique_id(void* out128);
 void comm_init(gan_ctx* ctx, int rank, int world, const void* id128);
 void comm_destroy(gan_ctx* ctx);
 void comm_allreduce_sum(gan_ctx* ctx, float* buf, int64_t n);
+// Fork: all-reduce [buf, buf+n) on the communication stream once everything enqueued so far on the
+// compute stream has finished; comm_join makes the compute stream wait for all forked reductions.
+void comm_allreduce_async(gan_ctx* ctx, float* buf, int64_t n);
+void comm_join(gan_ctx* ctx);

@@ -51,6 +51,23 @@ void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp&
 struct PackEntry { PackOp op; const float* master; void* dst; int tiles_k, tiles_n, tile_begin, pad; };
 void launch_pack_multi(Launch L, int dt, const PackEntry* tab_dev, int nent, int total_tiles);
 void launch_scale(Launch L, float* p, int64_t n, float s);
+// Fused Keras-Adam + weight packing: one pass over every convolution kernel of a net (32x32 tiles of
+// the master [16][A][B] tensors) updates p/m/v in place and writes the new weight into BOTH packed
+// copies (forward and data-gradient roles; one directly, one transposed through shared memory), so the
+// weights are read once per step (28+4 B/param instead of 28 + 8).  Non-kernel tensors (gamma/beta/
+// bias) are updated by launch_adam_ranges.
+struct AdamPackEntry {
+  long long w_off; int A, B, conv2d, pad0;
+  void* dstF; void* dstD;
+  int KcF, KtotF, KcD, KtotD;
+  long long boffF[4], boffD[4];
+  int8_t invF[16], invD[16];          // master tap index -> (class << 4) | tap-in-class for each role
+  int tiles_a, tiles_b, tile_begin, pad1;
+};
+struct AdamRange { long long off; int n, pad; };
+struct AdamArgs { float* p; const float* g; float* m; float* v; const long long* t_dev; double lr, b1, b2; float eps, gscale; };
+void launch_adam_pack(Launch L, int dt, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles);
+void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, int nranges);
 
 // ---- conv_ffma.cu ---------------------------------------------------------------------------
 void launch_conv_fwd_ffma(Launch L, int dt, const ConvOp& op);
