@@ -788,9 +788,12 @@ __device__ __forceinline__ float adam_update(const AdamArgs& a, long long i, flo
   return pp;
 }
 
+// 64x64 tiles of the master [16][A][B] kernel tensors, 256 threads: thread = (column b, 4 row groups);
+// the 4 x 8 rows of a half-tile are loaded first (32 independent loads per thread), then updated.
+#define APT 64
 template <typename T>
 __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEntry* __restrict__ tab, int nent) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[APT][APT + 1];
   __shared__ int s_e;
   __shared__ float s_lr;
   if (threadIdx.x == 0) {
@@ -805,31 +808,50 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
   int lt = blockIdx.x - E.tile_begin;
   const int tb = lt % E.tiles_b; lt /= E.tiles_b;
   const int ta = lt % E.tiles_a; const int widx = lt / E.tiles_a;
-  const int a0 = ta * 32, b0 = tb * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int a0 = ta * APT, b0 = tb * APT;
+  const int tx = threadIdx.x & (APT - 1), ty = threadIdx.x >> 6;          // 64 x 4
   const int cF = E.invF[widx] >> 4, tF = E.invF[widx] & 15, cD = E.invD[widx] >> 4, tD = E.invD[widx] & 15;
   T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
   T* __restrict__ dD = (T*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
   const long long base = E.w_off + (long long)widx * E.A * E.B;
+  const int bi = b0 + tx;
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int ai = a0 + r, bi = b0 + tx;
-    float pn = 0.f;
-    if (ai < E.A && bi < E.B) {
-      pn = adam_update(a, base + (long long)ai * E.B + bi, lr_t, b1, b2);
-      // destination that is contiguous along the master's fast index b
-      if (E.conv2d) dD[(long long)ai * E.KtotD + bi] = from_f<T>(pn);        // ci = a, co = b
-      else dF[(long long)ai * E.KtotF + bi] = from_f<T>(pn);                 // co = a, ci = b
+  for (int half = 0; half < 2; ++half) {
+    float P[8], G[8], M[8], V[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ai = a0 + half * 32 + ty + 4 * i;
+      if (ai < E.A && bi < E.B) {
+        const long long idx = base + (long long)ai * E.B + bi;
+        P[i] = a.p[idx]; G[i] = a.g[idx]; M[i] = a.m[idx]; V[i] = a.v[idx];
+      }
     }
-    tile[r][tx] = pn;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = half * 32 + ty + 4 * i, ai = a0 + r;
+      float pn = 0.f;
+      if (ai < E.A && bi < E.B) {
+        const long long idx = base + (long long)ai * E.B + bi;
+        float gr = G[i] * a.gscale, mm = M[i], vv = V[i];
+        mm += (gr - mm) * (1.f - b1);
+        vv += (gr * gr - vv) * (1.f - b2);
+        pn = P[i] - lr_t * mm / (sqrtf(vv) + a.eps);
+        a.m[idx] = mm; a.v[idx] = vv; a.p[idx] = pn;
+        // destination that is contiguous along the master's fast index b
+        if (E.conv2d) dD[(long long)ai * E.KtotD + bi] = from_f<T>(pn);        // ci = a, co = b
+        else dF[(long long)ai * E.KtotF + bi] = from_f<T>(pn);                 // co = a, ci = b
+      }
+      tile[r][tx] = pn;
+    }
   }
   __syncthreads();
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int bi = b0 + r, ai = a0 + tx;
-    if (ai < E.A && bi < E.B) {
-      if (E.conv2d) dF[(long long)bi * E.KtotF + ai] = from_f<T>(tile[tx][r]);   // co = b, ci = a
-      else dD[(long long)bi * E.KtotD + ai] = from_f<T>(tile[tx][r]);            // ci = b, co = a
+  for (int i = 0; i < 16; ++i) {
+    const int r = ty + 4 * i;                 // row of the transposed tile = b index
+    const int bj = b0 + r, ai = a0 + tx;
+    if (ai < E.A && bj < E.B) {
+      if (E.conv2d) dF[(long long)bj * E.KtotF + ai] = from_f<T>(tile[tx][r]);   // co = b, ci = a
+      else dD[(long long)bj * E.KtotD + ai] = from_f<T>(tile[tx][r]);            // ci = b, co = a
     }
   }
 }

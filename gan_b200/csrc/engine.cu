@@ -541,7 +541,7 @@ static void build_adam_tables(gan_net* n) {
       e.boffD[c] = (long long)c * ly.Cin_p * e.KtotD;
       for (int t = 0; t < cd[c].ntaps; ++t) e.invD[cd[c].widx[t]] = (int8_t)((c << 4) | t);
     }
-    e.tiles_a = (e.A + 31) / 32; e.tiles_b = (e.B + 31) / 32;
+    e.tiles_a = (e.A + 63) / 64; e.tiles_b = (e.B + 63) / 64;
     e.tile_begin = tiles;
     tiles += 16 * e.tiles_a * e.tiles_b;
     tab.push_back(e);
