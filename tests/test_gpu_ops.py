@@ -76,6 +76,7 @@ UMMA_CASES = [  # shapes where Kc and Nc are multiples of 64 (the tcgen05 tile c
     (0, 2, 16, 16, 64, 128), (0, 1, 32, 32, 128, 64), (0, 4, 4, 4, 64, 64), (0, 3, 2, 2, 128, 128),
     (1, 2, 8, 8, 64, 128), (1, 1, 32, 32, 64, 64), (1, 2, 9, 11, 64, 64),
     (2, 2, 8, 8, 128, 64), (2, 1, 16, 16, 64, 128), (2, 5, 2, 2, 64, 64), (2, 2, 1, 1, 128, 128),
+    (1, 20, 32, 32, 64, 256), (0, 19, 64, 64, 64, 256),     # >= 148 tiles with Cout % 256 == 0: N=256 tile variant
 ]
 
 
