@@ -186,7 +186,7 @@ struct alignas(64) UmmaFwdParams {
   bf16* out; int out_pitch, out_coff, Hout, Wout, so;
   int N, Hm, Wm, Nc;
   const float* bias; float* out_f32; int epi, Nr;
-  int num_tiles;
+  int num_tiles, ncls;
 };
 
 constexpr int FWD_STAGES = 3;         // BN <= 128: 3 x 32 KB, two CTAs per SM
@@ -225,7 +225,6 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int ntn = p.Nc / BN;
 
   if (warp == 0 && lane == 0) {
@@ -244,8 +243,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   // tile -> (class, n-tile, M-space origin)
+  // tile order: (class, n-tile) fastest, M tile slowest: the CTAs running at the same time share
+  // the same activation boxes (L2 hits instead of HBM re-reads; the weight tiles always fit in L2)
+  const int inner = ntn * p.ncls;
   auto decode = [&](int tile, int& cls, int& n0, int& w0, int& h0, int& b0) {
-    int tm = tile % tiles_m; int r = tile / tiles_m;
+    int tm = tile / inner; int r = tile - tm * inner;
     n0 = (r % ntn) * BN; cls = r / ntn;
     w0 = (tm % p.tiles_w) * p.TW; tm /= p.tiles_w;
     h0 = (tm % p.tiles_h) * p.TH; tm /= p.tiles_h;
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
     constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
     uint32_t it = 0, li = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
-      const int cls = tile / (tiles_m * ntn);
+      const int cls = (tile % inner) / ntn;
       const int nk = (KC == 64) ? p.ntaps[cls] * p.kchunks : p.ntaps[cls] / SUB;
       const uint32_t buf = li & 1, use = li >> 1;
       ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
@@ -436,7 +438,7 @@ static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile, int
   P.kchunks = op.Kc / 64;
   P.out = (bf16*)op.out; P.out_pitch = op.out_pitch; P.out_coff = op.out_coff; P.Hout = op.Hout; P.Wout = op.Wout; P.so = op.so;
   P.N = op.N; P.Hm = op.Hm; P.Wm = op.Wm; P.Nc = op.Nc;
-  P.bias = op.bias; P.out_f32 = op.out_f32; P.epi = op.epi; P.Nr = op.Nr;
+  P.bias = op.bias; P.out_f32 = op.out_f32; P.epi = op.epi; P.Nr = op.Nr; P.ncls = op.ncls;
 }
 
 void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
