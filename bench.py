@@ -238,10 +238,17 @@ def run_ours(args):
            for k, v in prof.items() if v[2] > 0}
     uf = prof["umma_fwd"]
     roof = None
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch_avg"), tj.get("source")
     if uf[2] > 0 and uf[0] > 0:
         ach = uf[1] / (uf[0] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "k_conv_fwd_umma (tcgen05 fwd+dgrad implicit GEMM)", "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "launches_per_step": uf[2] / nprof, "avg_launch_ms": uf[0] / uf[2],
                 "flops_per_launch": uf[1] / uf[2], "share_of_step": (uf[0] / nprof) / ms_step}
     for k in ("norm", "adam", "pack"):
