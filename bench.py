@@ -216,9 +216,14 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
+    ctx.prefetch(*pool_h[0])
     for i in range(args.steps):
         x, y = pool_h[i % POOL]
-        model.train_step(x, y, True)               # returns the four losses -> D2H + sync every step
+        # tf.data-style prefetch of the NEXT batch (pix2pix.py:163): its H2D copy overlaps this step
+        nxt = pool_h[(i + 1) % POOL]
+        model.train_step(x, y, True, sync=False)   # consumes the prefetched device copy of (x, y)
+        ctx.prefetch(*nxt)
+        losses_i = ctx.last_losses(4)              # D2H read of the four losses + sync every step
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3

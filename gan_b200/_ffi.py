@@ -66,6 +66,7 @@ SIGNATURES = {
     "gan_cyclegan_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float,
                                           C.c_int, _vp]),
     "gan_ctx_last_losses": (C.c_int, [_vp, _vp, C.c_int]),
+    "gan_ctx_prefetch": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "gan_op_conv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int]),
 }

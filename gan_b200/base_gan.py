@@ -94,6 +94,14 @@ class Context:
         _ffi.check(_ffi.lib().gan_ctx_last_losses(self._h, _ffi.ptr_of(out), n))
         return out
 
+    def prefetch(self, x, y):
+        """Start the host->device copy of the next step's (input, target) batches (pinned host arrays /
+        tensors) while the current step computes; pass the SAME objects to the next train_step."""
+        x, y = _as_f32(x), _as_f32(y)
+        nbytes = int(np.prod(x.shape)) * 4
+        _ffi.check(_ffi.lib().gan_ctx_prefetch(self._h, _ffi.ptr_of(x), _ffi.ptr_of(y), C.c_int64(nbytes)))
+        return x, y
+
     def set_sample_offset(self, sample0: int):
         _ffi.check(_ffi.lib().gan_ctx_set_sample_offset(self._h, C.c_int64(sample0)))
 

@@ -504,6 +504,16 @@ static bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 static const float* stage_in(gan_ctx* ctx, int idx, const float* p, size_t bytes) {
+  if (idx < 2 && p == ctx->prefetch_src[idx] && bytes == ctx->prefetch_bytes) {
+    // already on the device (gan_ctx_prefetch): wait for that copy, move it into the staging buffer
+    // (device-to-device) and release the prefetch buffer for the next batch right away
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->prefetch_done, 0));
+    ctx->stage[idx].ensure(bytes);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->stage[idx].p, ctx->prefetch_buf[idx].p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->prefetch_consumed, ctx->stream));
+    ctx->prefetch_src[idx] = nullptr;
+    return ctx->stage[idx].as<float>();
+  }
   if (is_device_ptr(p)) return p;
   ctx->stage[idx].ensure(bytes);
   CUDA_CHECK(cudaMemcpyAsync(ctx->stage[idx].p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -731,8 +741,19 @@ static void run_step_graphed(gan_ctx* ctx, const std::string& key, const float* 
                              const std::vector<gan_adam*>& opts, F&& body) {
   for (gan_net* n : nets) pack_weights(n);      // host-side set_tensor since the last step: repack outside the graph
   ctx->stage[0].ensure(img_bytes); ctx->stage[1].ensure(img_bytes);
-  CUDA_CHECK(cudaMemcpyAsync(ctx->stage[0].p, x_in, img_bytes, cudaMemcpyDefault, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(ctx->stage[1].p, y_in, img_bytes, cudaMemcpyDefault, ctx->stream));
+  const float* srcs[2] = {x_in, y_in};
+  for (int i = 0; i < 2; ++i) {
+    const void* src = srcs[i];
+    bool pre = false;
+    if (src == ctx->prefetch_src[i] && img_bytes == ctx->prefetch_bytes) {   // prefetched: device-to-device
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->prefetch_done, 0));
+      src = ctx->prefetch_buf[i].p;
+      ctx->prefetch_src[i] = nullptr;
+      pre = true;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(ctx->stage[i].p, src, img_bytes, cudaMemcpyDefault, ctx->stream));
+    if (pre) CUDA_CHECK(cudaEventRecord(ctx->prefetch_consumed, ctx->stream));   // prefetch buffer free again
+  }
   const float* xs = ctx->stage[0].as<float>(); const float* ys = ctx->stage[1].as<float>();
   gan_ctx::GraphEntry& ge = ctx->graph_cache[key];
   if (ge.exec != nullptr) {
@@ -804,6 +825,7 @@ int gan_ctx_destroy(gan_ctx* ctx) {
   for (auto& kv : ctx->graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   comm_destroy(ctx);
   cudaFreeHost(ctx->loss_host);
+  if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->prefetch_done); cudaEventDestroy(ctx->prefetch_consumed); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   API_END
@@ -1124,6 +1146,27 @@ int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, ga
                        cyclegan_step(g, f, dx, dy, g_opt, f_opt, dx_opt, dy_opt, xs, ys, batch, lambda, training, nullptr);
                      });
   }
+  API_END
+}
+
+int gan_ctx_prefetch(gan_ctx* ctx, const float* x_host, const float* y_host, int64_t bytes_each) {
+  API_BEGIN
+  GAN_REQUIRE(ctx && x_host && y_host && bytes_each > 0, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->prefetch_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->prefetch_consumed, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ctx->prefetch_consumed, ctx->stream));
+  }
+  // the previous batch is moved out of the prefetch buffers at the very start of the step that consumes
+  // it; the new copy only has to wait for that device-to-device move, not for the whole step
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->prefetch_consumed, 0));
+  ctx->prefetch_buf[0].ensure((size_t)bytes_each); ctx->prefetch_buf[1].ensure((size_t)bytes_each);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->prefetch_buf[0].p, x_host, (size_t)bytes_each, cudaMemcpyDefault, ctx->copy_stream));
+  CUDA_CHECK(cudaMemcpyAsync(ctx->prefetch_buf[1].p, y_host, (size_t)bytes_each, cudaMemcpyDefault, ctx->copy_stream));
+  CUDA_CHECK(cudaEventRecord(ctx->prefetch_done, ctx->copy_stream));
+  ctx->prefetch_src[0] = x_host; ctx->prefetch_src[1] = y_host; ctx->prefetch_bytes = (size_t)bytes_each;
   API_END
 }
 

@@ -47,6 +47,12 @@ struct gan_ctx {
   uint64_t launches = 0;
   DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk;
   DevBuf stage[4];
+  // input prefetch (tf.data-style): H2D of the NEXT step's images on a copy stream while this step computes
+  DevBuf prefetch_buf[2];
+  const void* prefetch_src[2] = {nullptr, nullptr};
+  size_t prefetch_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t prefetch_done = nullptr, prefetch_consumed = nullptr;
   float* loss_host = nullptr;   // pinned
   int n_losses = 0;
   // device-resident dropout call counter (graph-replay safe) + generator calls since the last bump

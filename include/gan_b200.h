@@ -142,6 +142,10 @@ GAN_API int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net
                             const float* real_x, const float* real_y, int batch,
                             float lambda, int training, float losses[7]);
 GAN_API int gan_ctx_last_losses(gan_ctx* ctx, float* out, int n);
+/* Input prefetch, the role of `dataset.prefetch(AUTOTUNE)` in the reference (pix2pix.py:163): start the
+ * host->device copy of the NEXT step's two image batches on a copy stream while the current step
+ * computes.  The next train step recognises the same host pointers and uses the device copies. */
+GAN_API int gan_ctx_prefetch(gan_ctx* ctx, const float* x_host, const float* y_host, int64_t bytes_each);
 
 /* ---- single-operator entry points (parity tests of each kernel family) --------------------
  * kind: 0 = Conv2D 4x4 s2 'same', 1 = ZeroPad(1)+Conv2D 4x4 s1 'valid', 2 = Conv2DTranspose 4x4 s2 'same'

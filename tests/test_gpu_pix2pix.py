@@ -264,3 +264,26 @@ def test_cuda_graph_replay_matches_eager():
             assert abs(p - q) <= 2e-3 * max(1.0, abs(q)), (l0, l1)
     assert len({tuple(l) for l in l1}) == 5                     # every step differs: counters advance under replay
     assert np.abs(w0 - w1).max() <= 2 * 5 * 2e-4 * 1.01
+
+
+def test_prefetch_is_transparent():
+    """gan_ctx_prefetch (the reference's dataset.prefetch, pix2pix.py:163): copying the next batch on a
+    copy stream while the current step runs must not change any result."""
+    batches = [_inputs(2, 256, 3, seed=s) for s in (11, 12, 13)]
+    res = []
+    for use_prefetch in (False, True):
+        m, _, _ = _build("fp32", 3)
+        m.ctx.set_graphs(use_prefetch)        # exercise the graph path together with prefetch
+        out = []
+        if use_prefetch:
+            m.ctx.prefetch(*batches[0])
+        for i, (x, y) in enumerate(batches):
+            losses = m.train_step(x, y, True, sync=False)
+            if use_prefetch and i + 1 < len(batches):
+                m.ctx.prefetch(*batches[i + 1])
+            out.append([float(v) for v in m.ctx.last_losses(4)])
+        res.append(out)
+        m.ctx.close()
+    for a, b in zip(*res):
+        for p, q in zip(a, b):
+            assert abs(p - q) <= 1e-4 * max(1.0, abs(q)), res
