@@ -53,6 +53,8 @@ struct ConvOp {
   float* out_f32;                // optional fp32 copy of the epilogue output, compact [pix][Nc]
   // wgrad: dW[widx*s_tap + kc*s_k + nc*s_n] += sum_m in(m,t,kc) * out(m,nc)
   float* dW; int64_t s_tap, s_k, s_n;
+  // optional fp32 workspace for split-K forward launches (small-M layers): [out pixels][Nc]
+  float* splitk_ws; size_t splitk_ws_bytes;
 };
 
 // ---- error handling (host) -----------------------------------------------------------------

@@ -187,6 +187,7 @@ struct alignas(64) UmmaFwdParams {
   int N, Hm, Wm, Nc;
   const float* bias; float* out_f32; int epi, Nr;
   int num_tiles, ncls;
+  float* ws; int ksplit;           // split-K: fp32 atomics into ws[pix][Nc] instead of bf16 stores
 };
 
 constexpr int FWD_STAGES = 3;         // BN <= 128: 3 x 32 KB, two CTAs per SM
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   // the same activation boxes (L2 hits instead of HBM re-reads; the weight tiles always fit in L2)
   const int inner = ntn * p.ncls;
   auto decode = [&](int tile, int& cls, int& n0, int& w0, int& h0, int& b0) {
+    tile /= p.ksplit;                                  // k-split index is the fastest tile coordinate
     int tm = tile / inner; int r = tile - tm * inner;
     n0 = (r % ntn) * BN; cls = r / ntn;
     w0 = (tm % p.tiles_w) * p.TW; tm /= p.tiles_w;
@@ -261,7 +263,9 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
         int cls, n0, w0, h0, b0;
         decode(tile, cls, n0, w0, h0, b0);
         const int nk = (KC == 64) ? p.ntaps[cls] * p.kchunks : p.ntaps[cls] / SUB;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int ks = tile % p.ksplit;
+        const int kb0 = ks * nk / p.ksplit, kb1 = (ks + 1) * nk / p.ksplit;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % NSTAGE;
           const uint32_t ph = (it / NSTAGE) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -287,13 +291,15 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
     constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
     uint32_t it = 0, li = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
-      const int cls = (tile % inner) / ntn;
+      const int cls = ((tile / p.ksplit) % inner) / ntn;
       const int nk = (KC == 64) ? p.ntaps[cls] * p.kchunks : p.ntaps[cls] / SUB;
+      const int ks = tile % p.ksplit;
+      const int kb0 = ks * nk / p.ksplit, kb1 = (ks + 1) * nk / p.ksplit;
       const uint32_t buf = li & 1, use = li >> 1;
       ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + buf * ACC_COLS;
-      for (int kb = 0; kb < nk; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
         ptx::mbar_wait(&full[s], ph);
@@ -305,10 +311,10 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
             // KC==64: +32 B inside the 128-byte swizzle atom per K=16; KC==16: one 32-byte-swizzled box per K=16
             const uint64_t ad = (KC == 64) ? desc_kmajor<SW>(sa) + 2 * k : desc_kmajor<SW>(sa + k * A_SUB);
             const uint64_t bd = (KC == 64) ? desc_kmajor<SW>(sa + A_BYTES) + 2 * k : desc_kmajor<SW>(sa + A_BYTES + k * B_SUB);
-            ptx::umma_bf16(acc, ad, bd, idesc, (kb | k) != 0);
+            ptx::umma_bf16(acc, ad, bd, idesc, (kb > kb0) || (k != 0));
           }
           ptx::umma_commit(&empty[s]);
-          if (kb == nk - 1) ptx::umma_commit(&tmem_full[buf]);
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[buf]);
         }
         __syncwarp();
       }
@@ -335,7 +341,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(acc + c, v);
-          if (valid) {
+          if (valid && p.ksplit > 1) {
+            float* wdst = p.ws + pix * p.Nc + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(wdst + j, __uint_as_float(v[j]));
+          } else if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -452,6 +462,21 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
     fill_fwd_params(P, op, BN, KC);
   }
   P.num_tiles = P.tiles_w * P.tiles_h * P.tiles_n * (op.Nc / BN) * op.ncls;
+  P.ksplit = 1; P.ws = nullptr;
+  // split-K for layers with too few output tiles to fill the chip (the 1x1..8x8 bottleneck layers:
+  // a serial 128-k-block loop on 4..128 CTAs is pure TMA->MMA latency): k-ranges go to separate CTAs,
+  // fp32 atomics into a workspace, one conversion pass to bf16.
+  const int nk = (KC == 64) ? op.cls[0].ntaps * (op.Kc / 64) : op.cls[0].ntaps / 4;
+  const size_t out_elems = (size_t)op.N * op.Hout * op.Wout * op.Nc;
+  if (op.splitk_ws != nullptr && BN >= 64 && BN <= 128 && P.num_tiles < 148 && op.epi == EPI_NONE && op.out_f32 == nullptr &&
+      out_elems * 4 <= op.splitk_ws_bytes) {
+    int ks = (2 * 148 + P.num_tiles - 1) / P.num_tiles;
+    if (ks > nk / 8) ks = nk / 8;
+    if (ks >= 2) {
+      P.ksplit = ks; P.ws = op.splitk_ws; P.num_tiles *= ks;
+      cudaMemsetAsync(op.splitk_ws, 0, out_elems * 4, L.s);
+    }
+  }
   const int per_sm = BN == 256 ? 1 : 2;
   dim3 grid(P.num_tiles < per_sm * 148 ? P.num_tiles : per_sm * 148);     // persistent
   const size_t sm = fwd_smem_bytes(BN);
@@ -465,6 +490,8 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
     else k_conv_fwd_umma<64, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
   }
   KLAUNCH(L);
+  if (P.ksplit > 1)
+    launch_convert(L, DT_BF16, op.splitk_ws, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
 }
 
 // =============================================================================================

@@ -129,7 +129,10 @@ static double conv_flops(const ConvOp& op) {
 // ---------------------------------------------------------------------------------------------
 // conv dispatch: tcgen05 where the op fits (bf16 mode), FFMA otherwise
 // ---------------------------------------------------------------------------------------------
-static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op) {
+static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
+  ConvOp op = op_in;
+  ctx->splitk_ws.ensure((size_t)32 << 20);
+  op.splitk_ws = ctx->splitk_ws.as<float>(); op.splitk_ws_bytes = ctx->splitk_ws.bytes;
   bool can = ctx->dt == DT_BF16 && umma_fwd_supported(op);
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;

@@ -45,7 +45,7 @@ struct gan_ctx {
   int64_t sample0 = 0;
   bool sample0_set = false;
   uint64_t launches = 0;
-  DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk;
+  DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk, splitk_ws;
   DevBuf stage[4];
   // input prefetch (tf.data-style): H2D of the NEXT step's images on a copy stream while this step computes
   DevBuf prefetch_buf[2];
