@@ -187,7 +187,7 @@ struct alignas(64) UmmaFwdParams {
   int N, Hm, Wm, Nc;
   const float* bias; float* out_f32; int epi, Nr;
   int num_tiles, ncls;
-  float* ws; int ksplit;           // split-K: fp32 atomics into ws[pix][Nc] instead of bf16 stores
+  float* ws; int ksplit; long long slab;   // split-K: split ks stores fp32 into ws[ks][pix][Nc] (no atomics)
 };
 
 constexpr int FWD_STAGES = 3;         // BN <= 128: 3 x 32 KB, two CTAs per SM
@@ -342,9 +342,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
           uint32_t v[32];
           ptx::tmem_ld32(acc + c, v);
           if (valid && p.ksplit > 1) {
-            float* wdst = p.ws + pix * p.Nc + n0 + c;
+            float4* wdst = reinterpret_cast<float4*>(p.ws + (long long)(tile % p.ksplit) * p.slab + pix * p.Nc + n0 + c);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(wdst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 8; ++j)
+              wdst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                    __uint_as_float(v[4 * j + 3]));
           } else if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -468,14 +470,11 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   // fp32 atomics into a workspace, one conversion pass to bf16.
   const int nk = (KC == 64) ? op.cls[0].ntaps * (op.Kc / 64) : op.cls[0].ntaps / 4;
   const size_t out_elems = (size_t)op.N * op.Hout * op.Wout * op.Nc;
-  if (op.splitk_ws != nullptr && BN >= 64 && BN <= 128 && P.num_tiles < 148 && op.epi == EPI_NONE && op.out_f32 == nullptr &&
-      out_elems * 4 <= op.splitk_ws_bytes) {
-    int ks = (2 * 148 + P.num_tiles - 1) / P.num_tiles;
+  if (op.splitk_ws != nullptr && BN >= 64 && BN <= 128 && P.num_tiles <= 74 && op.epi == EPI_NONE && op.out_f32 == nullptr) {
+    int ks = (2 * 148) / P.num_tiles;
     if (ks > nk / 8) ks = nk / 8;
-    if (ks >= 2) {
-      P.ksplit = ks; P.ws = op.splitk_ws; P.num_tiles *= ks;
-      cudaMemsetAsync(op.splitk_ws, 0, out_elems * 4, L.s);
-    }
+    while (ks >= 2 && out_elems * 4 * ks > op.splitk_ws_bytes) --ks;
+    if (ks >= 2) { P.ksplit = ks; P.ws = op.splitk_ws; P.slab = (long long)out_elems; P.num_tiles *= ks; }
   }
   const int per_sm = BN == 256 ? 1 : 2;
   dim3 grid(P.num_tiles < per_sm * 148 ? P.num_tiles : per_sm * 148);     // persistent
@@ -490,8 +489,8 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
     else k_conv_fwd_umma<64, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
   }
   KLAUNCH(L);
-  if (P.ksplit > 1)
-    launch_convert(L, DT_BF16, op.splitk_ws, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
+  if (P.ksplit > 1)   // deterministic reduction of the k-split slabs + conversion to bf16
+    launch_sum_slabs(L, DT_BF16, op.splitk_ws, P.ksplit, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
 }
 
 // =============================================================================================

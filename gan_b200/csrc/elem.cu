@@ -872,3 +872,27 @@ void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, i
   k_adam_ranges<<<nranges, 256, 0, L.s>>>(a, tab_dev);
   KLAUNCH(L);
 }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_sum_slabs(const float* __restrict__ slabs, int nslab, int64_t total, int C,
+                                                   T* __restrict__ dst, int pitch, int coff) {
+  const int64_t tot4 = total / 4;                 // C % 4 == 0
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(slabs)[i];
+    for (int k = 1; k < nslab; ++k) {
+      float4 b = reinterpret_cast<const float4*>(slabs + (int64_t)k * total)[i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const int64_t e = i * 4; const int64_t p = e / C; const int c = (int)(e - p * C);
+    T* o = dst + p * pitch + coff + c;
+    o[0] = from_f<T>(a.x); o[1] = from_f<T>(a.y); o[2] = from_f<T>(a.z); o[3] = from_f<T>(a.w);
+  }
+}
+void launch_sum_slabs(Launch L, int dt, const float* slabs, int nslab, int64_t P, int C, void* dst, int pitch, int coff) {
+  const int64_t total = P * C;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_sum_slabs<T><<<grid_for(total / 4, 256, 4), 256, 0, L.s>>>(slabs, nslab, total, C, (T*)dst, pitch, coff);
+  });
+  KLAUNCH(L);
+}

@@ -14,6 +14,8 @@ struct Launch {
 // ---- elem.cu --------------------------------------------------------------------------------
 void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* dst, int pitch, int coff);
 void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64_t P, int C, float* dst);
+// dst view = sum over `nslab` fp32 slabs [nslab][P][C] (deterministic split-K reduction)
+void launch_sum_slabs(Launch L, int dt, const float* slabs, int nslab, int64_t P, int C, void* dst, int pitch, int coff);
 
 int stats_chunks(int G, int64_t Pg);
 size_t stats_ws_floats(int G, int64_t Pg, int C);
