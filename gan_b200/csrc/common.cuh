@@ -55,6 +55,9 @@ struct ConvOp {
   float* dW; int64_t s_tap, s_k, s_n;
   // optional fp32 workspace for split-K forward launches (small-M layers): [out pixels][Nc]
   float* splitk_ws; size_t splitk_ws_bytes;
+  // im2col first layers (bf16/tcgen05 mode): the op is a 1x1 GEMM whose `ntaps` K-blocks of 64 are
+  // separate im2col buffers [M][64] (one per input source); k' = t16*im2col_c + c inside a block.
+  const void* in_tap[4]; int im2col_c;
 };
 
 // ---- error handling (host) -----------------------------------------------------------------

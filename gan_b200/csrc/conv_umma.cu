@@ -415,7 +415,8 @@ static void fill_tap_tables(const ConvOp& op, int8_t (*tap_map)[16], int8_t (*ta
   for (int c = 0; c < op.ncls; ++c) {
     const ClassGeom& g = op.cls[c];
     for (int t = 0; t < g.ntaps; ++t) {
-      if (op.si == 1) { tap_map[c][t] = 0; tap_dh[c][t] = g.dh[t]; tap_dw[c][t] = g.dw[t]; }
+      if (op.in_tap[0] != nullptr) { tap_map[c][t] = (int8_t)(t & 3); tap_dh[c][t] = 0; tap_dw[c][t] = 0; }
+      else if (op.si == 1) { tap_map[c][t] = 0; tap_dh[c][t] = g.dh[t]; tap_dw[c][t] = g.dw[t]; }
       else {
         int a = ((g.dh[t] % 2) + 2) % 2, b = ((g.dw[t] % 2) + 2) % 2;
         tap_map[c][t] = (int8_t)(a * 2 + b);
@@ -425,7 +426,13 @@ static void fill_tap_tables(const ConvOp& op, int8_t (*tap_map)[16], int8_t (*ta
   }
 }
 static void fill_in_maps(CUtensorMap* maps, const ConvOp& op, int bw, int bh, int bn, int bc) {
-  if (op.si == 1) {
+  if (op.in_tap[0] != nullptr) {
+    // im2col first layer: K-block t is its own [M][64] buffer
+    for (int t = 0; t < 4; ++t) {
+      const void* base = op.in_tap[t] ? op.in_tap[t] : op.in_tap[0];
+      maps[t] = make_map4(base, 64, 0, 64, op.Hin, op.Win, op.N, 1, 0, 0, bw, bh, bn, bc);
+    }
+  } else if (op.si == 1) {
     maps[0] = make_map4(op.in, op.in_pitch, op.in_coff, op.Kc, op.Hin, op.Win, op.N, 1, 0, 0, bw, bh, bn, bc);
     for (int i = 1; i < 4; ++i) maps[i] = maps[0];
   } else {
@@ -508,6 +515,7 @@ struct alignas(64) UmmaWgradParams {
   int splits;
   float* dW; long long s_tap, s_k, s_n;
   int Nc, Kr, Nr;
+  int im2col_c;            // >0: rows are im2col K-blocks (t = source, kc = tap16*c + channel)
 };
 
 constexpr int WG_STAGES = 3;
@@ -606,8 +614,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
       const int r = q * 32 + lane;                   // accumulator row = (tap,channel) index inside the tile
       const int k = kbase + r;
       const int t = k / p.Kc, kc = k - t * p.Kc;
-      const bool row_ok = kc < p.Kr;
-      float* dst = p.dW + (long long)p.widx[cls][t] * p.s_tap + (long long)kc * p.s_k + (long long)n0 * p.s_n;
+      bool row_ok = kc < p.Kr && t < p.ntaps[cls];
+      float* dst = p.dW + (long long)p.widx[cls][t & 15] * p.s_tap + (long long)kc * p.s_k + (long long)n0 * p.s_n;
+      if (p.im2col_c > 0) {
+        const int ic = p.im2col_c;
+        row_ok = t < p.ntaps[cls] && kc < 16 * ic;
+        dst = p.dW + (long long)(kc / ic) * p.s_tap + (long long)(t * ic + kc % ic) * p.s_k + (long long)n0 * p.s_n;
+      }
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
       if (BN >= 32) {
@@ -646,7 +659,7 @@ bool umma_wgrad_supported(const ConvOp& op) {
   if (g_encode == nullptr) return false;
   if (!chan_ok(op.Kc) || !chan_ok(op.Nc)) return false;
   if (op.Kc == 16 && op.Nc == 16) return false;
-  if ((op.cls[0].ntaps * op.Kc) % 128 != 0) return false;
+  if ((op.cls[0].ntaps * op.Kc) % 128 != 0 && op.in_tap[0] == nullptr) return false;
   if (!view_ok(op.in_pitch, op.in_coff, op.in) || !view_ok(op.out_pitch, op.out_coff, op.out)) return false;
   if (op.si == 2 && (op.Hin % 2 != 0 || op.Win % 2 != 0)) return false;
   if (op.so == 2 && (op.Hout % 2 != 0 || op.Wout % 2 != 0)) return false;
@@ -681,8 +694,9 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   }
   P.Kc = op.Kc;
   P.dW = op.dW; P.s_tap = op.s_tap; P.s_k = op.s_k; P.s_n = op.s_n; P.Nc = op.Nc; P.Kr = op.Kr; P.Nr = op.Nr;
+  P.im2col_c = op.in_tap[0] != nullptr ? op.im2col_c : 0;
   const int ntaps = op.cls[0].ntaps;
-  const int mblocks = ntaps * op.Kc / 128;
+  const int mblocks = (ntaps * op.Kc + 127) / 128;
   const int ntiles = op.Nc / BN;
   const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_n;
   // split the pixel reduction so that all CTAs form ONE full wave (2 CTAs/SM): equal-length CTAs

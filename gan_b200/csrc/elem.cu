@@ -736,7 +736,10 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
   const ClassGeom& cg = op.cls[ci];
   const float* __restrict__ src = E.master + (int64_t)cg.widx[t] * op.s_tap;
   T* __restrict__ dst = (T*)E.dst + cg.b_off;
-  const int64_t Ktot = (int64_t)ntaps * op.Kc;
+  const int64_t Ktot = op.im2col_c ? op.Ktot : (int64_t)ntaps * op.Kc;
+  const int ic = op.im2col_c;
+  // packed K index of channel kc of tap t
+  auto kidx = [&](int kc) -> int64_t { return ic ? (int64_t)(kc / ic) * 64 + (int64_t)t * ic + kc % ic : (int64_t)t * op.Kc + kc; };
   const int k0 = tk * 32, n0 = tn * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   if (op.s_n == 1) {
@@ -750,7 +753,7 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
       int n = n0 + r, kc = k0 + tx;
-      if (n < op.Nc && kc < op.Kc) dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(tile[tx][r]);
+      if (n < op.Nc && kc < (ic ? op.Kr : op.Kc)) dst[(int64_t)n * Ktot + kidx(kc)] = from_f<T>(tile[tx][r]);
     }
   } else {
     // master contiguous along kc (s_k == 1): straight tile copy
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
       int n = n0 + r, kc = k0 + tx;
       if (n < op.Nc && kc < op.Kc) {
         float v = (kc < op.Kr && n < op.Nr) ? src[(int64_t)kc * op.s_k + (int64_t)n * op.s_n] : 0.f;
-        dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(v);
+        if (!ic || kc < op.Kr) dst[(int64_t)n * Ktot + kidx(kc)] = from_f<T>(v);
       }
     }
   }
@@ -811,7 +814,8 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
   const int a0 = ta * APT, b0 = tb * APT;
   const int tx = threadIdx.x & (APT - 1), ty = threadIdx.x >> 6;          // 64 x 4
   const int cF = E.invF[widx] >> 4, tF = E.invF[widx] & 15, cD = E.invD[widx] >> 4, tD = E.invD[widx] & 15;
-  T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
+  const int ic = E.im2col_c;
+  T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (ic ? (long long)tF * ic : (long long)tF * E.KcF);   // + co*KtotF + ci
   T* __restrict__ dD = (T*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
   const long long base = E.w_off + (long long)widx * E.A * E.B;
   const int bi = b0 + tx;
@@ -850,7 +854,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
     const int r = ty + 4 * i;                 // row of the transposed tile = b index
     const int bj = b0 + r, ai = a0 + tx;
     if (ai < E.A && bj < E.B) {
-      if (E.conv2d) dF[(long long)bj * E.KtotF + ai] = from_f<T>(tile[tx][r]);   // co = b, ci = a
+      if (E.conv2d) dF[(long long)bj * E.KtotF + (ic ? (ai / ic) * 64 + ai % ic : ai)] = from_f<T>(tile[tx][r]);   // co = b, ci = a
       else dD[(long long)bj * E.KtotD + ai] = from_f<T>(tile[tx][r]);            // ci = b, co = a
     }
   }
@@ -894,5 +898,41 @@ void launch_sum_slabs(Launch L, int dt, const float* slabs, int nslab, int64_t P
     using T = typename std::remove_pointer<decltype(tag)>::type;
     k_sum_slabs<T><<<grid_for(total / 4, 256, 4), 256, 0, L.s>>>(slabs, nslab, total, C, (T*)dst, pitch, coff);
   });
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col of the first layer (Conv2D 4x4 s2 'same' on 1..4-channel images, base_gan.py:141,180):
+// one thread per output pixel writes one full 128-byte row [16 taps x C | zero pad].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_im2col(const float* __restrict__ src, int B, int H, int W, int C,
+                                                bf16* __restrict__ dst) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t M = (int64_t)B * Ho * Wo;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(m % Wo); const int64_t r = m / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    __nv_bfloat16 row[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) row[k] = __float2bfloat16_rn(0.f);
+    for (int kh = 0; kh < 4; ++kh) {
+      const int ih = 2 * oh + kh - 1;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 4; ++kw) {
+        const int iw = 2 * ow + kw - 1;
+        if (iw < 0 || iw >= W) continue;
+        const float* sp = src + (((int64_t)n * H + ih) * W + iw) * C;
+        for (int c = 0; c < C; ++c) row[(kh * 4 + kw) * C + c] = __float2bfloat16_rn(__ldg(sp + c));
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + m * 64);
+    const uint4* rv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rv[j];
+  }
+}
+void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16) {
+  GAN_REQUIRE(16 * C <= 64, "im2col first layer supports up to 4 channels per source");
+  const int64_t M = (int64_t)B * (H / 2) * (W / 2);
+  k_im2col<<<grid_for(M, 256, 16), 256, 0, L.s>>>(src, B, H, W, C, (bf16*)dst_bf16);
   KLAUNCH(L);
 }

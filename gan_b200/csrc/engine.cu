@@ -104,6 +104,28 @@ static ConvOp make_op(const Layer& ly, int role, View x, View y, const void* wpa
   return op;
 }
 
+// First layers as a GEMM over im2col rows (bf16 + tcgen05 engine only; the FFMA cross-check and the
+// fp32 mode keep the generic tap path).
+static bool im2col_on(const gan_ctx* ctx, const Layer& ly) {
+  return ly.first && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.src_c * 16 <= 64 && ly.Cout_p % 64 == 0;
+}
+// role: R_FWD (y = z written) or R_WGRAD (y = dz read).  M-space = output grid of the layer.
+static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
+  ConvOp op; memset(&op, 0, sizeof(op));
+  op.ncls = 1;
+  op.cls[0].ntaps = ly.nsrc;
+  for (int t = 0; t < ly.nsrc; ++t) { op.cls[0].widx[t] = (int8_t)t; op.in_tap[t] = s.im2col[t].p; }
+  op.im2col_c = ly.src_c;
+  op.in = s.im2col[0].p; op.in_pitch = 64; op.in_coff = 0; op.Hin = y.H; op.Win = y.W;
+  op.out = y.p; op.out_pitch = y.pitch; op.out_coff = y.coff; op.Hout = y.H; op.Wout = y.W;
+  op.N = y.N; op.Hm = y.H; op.Wm = y.W; op.si = 1; op.so = 1;
+  op.Kc = 64; op.Kr = 64; op.Nc = ly.Cout_p; op.Nr = ly.Cout;
+  op.s_tap = (int64_t)ly.Cin * ly.Cout; op.s_k = ly.Cout; op.s_n = 1;      // Conv2D master (kh,kw,ci,co)
+  op.B = ly.wp_im2col.p;
+  (void)role;
+  return op;
+}
+
 static void out_dims(int kind, int Hin, int Win, int& Ho, int& Wo) {
   if (kind == K_CONV_S2) { Ho = Hin / 2; Wo = Win / 2; }
   else if (kind == K_CONV_S1P) { Ho = Hin - 1; Wo = Win - 1; }
@@ -167,6 +189,9 @@ static void add_layer(gan_net* n, const std::string& name, int kind, int Cin, in
   Layer ly; ly.name = name; ly.kind = kind; ly.Cin = Cin; ly.Cout = Cout; ly.norm = norm; ly.act = act;
   ly.bias = bias; ly.dropout = dropout; ly.tag = tag; ly.head = head;
   ly.Cin_p = pad_c(n->ctx, Cin); ly.Cout_p = pad_c(n->ctx, Cout);
+  if (n->layers.empty() && kind == K_CONV_S2) {       // first layer of the net: image channels (x sources)
+    ly.first = true; ly.src_c = n->C; ly.nsrc = Cin / n->C;
+  }
   ly.w_off = n->nparams;
   if (kind == K_CONVT_S2) add_tensor(n, name + ".kernel", {4, 4, Cout, Cin}, n->nparams, true);
   else add_tensor(n, name + ".kernel", {4, 4, Cin, Cout}, n->nparams, true);
@@ -229,8 +254,26 @@ static void pack_weights(gan_net* n) {
     n->pack_tab.ensure(tab.size() * sizeof(PackEntry));
     CUDA_CHECK(cudaMemcpy(n->pack_tab.p, tab.data(), tab.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
     n->pack_nent = (int)tab.size(); n->pack_tiles = tiles;
+    // extra forward copy of the first layer in im2col K order (bf16 mode)
+    Layer& l0 = n->layers[0];
+    if (l0.first && ctx->dt == DT_BF16 && l0.src_c * 16 <= 64) {
+      PackEntry e; memset(&e, 0, sizeof(e));
+      PackOp& po = e.op;
+      po.ncls = 1; po.cls[0] = geom_conv16(1);
+      po.Kc = l0.Cin; po.Kr = l0.Cin; po.Nc = l0.Cout_p; po.Nr = l0.Cout;
+      po.s_tap = (int64_t)l0.Cin * l0.Cout; po.s_k = l0.Cout; po.s_n = 1;
+      po.im2col_c = l0.src_c; po.Ktot = l0.nsrc * 64;
+      l0.wp_im2col.ensure((size_t)l0.Cout_p * po.Ktot * ctx->esize());
+      e.master = n->params.as<float>() + l0.w_off; e.dst = l0.wp_im2col.p;
+      e.tiles_k = (po.Kc + 31) / 32; e.tiles_n = (po.Nc + 31) / 32; e.tile_begin = 0;
+      n->pack_im2col_tiles = e.tiles_k * e.tiles_n * 16;
+      n->pack_tab_im2col.ensure(sizeof(PackEntry));
+      CUDA_CHECK(cudaMemcpy(n->pack_tab_im2col.p, &e, sizeof(PackEntry), cudaMemcpyHostToDevice));
+    }
   }
   launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab.p, n->pack_nent, n->pack_tiles);
+  if (n->pack_im2col_tiles > 0)
+    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, 1, n->pack_im2col_tiles);
   n->packed_dirty = false;
 }
 
@@ -264,7 +307,8 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   int64_t P = (int64_t)B * Ho * Wo;
   s.z[li].ensure((size_t)P * ly.Cout * ctx->esize());
   View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
-  run_conv_fwd(ctx, make_op(ly, R_FWD, in, z, ly.wp_fwd.p));
+  if (li == 0 && s.used_im2col) run_conv_fwd(ctx, make_op_im2col(ly, R_FWD, s, z));
+  else run_conv_fwd(ctx, make_op(ly, R_FWD, in, z, ly.wp_fwd.p));
   DropKey dk = drop_key(ctx, ly, s);
   ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 2 : 3));
   if (ly.norm == NORM_NONE) {
@@ -317,7 +361,7 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
                     ctx->stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
   }
   if (want_wgrad) {
-    ConvOp op = make_op(ly, R_WGRAD, in, dz, nullptr);
+    ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ly, R_WGRAD, s, dz) : make_op(ly, R_WGRAD, in, dz, nullptr);
     op.dW = n->grads.as<float>() + ly.w_off;
     run_conv_wgrad(ctx, op);
   }
@@ -353,8 +397,14 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   const size_t es = ctx->esize();
   const int C = g->C;
   const int Cp = g->Cp;
+  s.used_im2col = im2col_on(ctx, g->layers[0]);
   s.xin.ensure((size_t)B * H * W * Cp * es);
-  launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
+  if (s.used_im2col) {
+    s.im2col[0].ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
+    launch_im2col(ctx->L(), x_f32, B, H, W, C, s.im2col[0].p);
+  } else {
+    launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
+  }
   // concat buffers: cat[k-1] = [up_k output (UP_F[k-1]) | down_{8-k} output (DOWN_F[7-k])] at H/2^(8-k)
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
@@ -452,8 +502,16 @@ static void discriminator_forward(gan_net* d, int slot, const float* inp, const 
   const size_t es = ctx->esize();
   const int C = d->C, C0 = d->Cin0_p;
   s.in0.ensure((size_t)B * H * W * C0 * es);
-  launch_convert(ctx->L(), ctx->dt, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
-  if (tar) launch_convert(ctx->L(), ctx->dt, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
+  s.used_im2col = im2col_on(ctx, d->layers[0]);
+  if (s.used_im2col) {                                   // one im2col K-block per source of concatenate([inp, tar])
+    const size_t ib = (size_t)B * (H / 2) * (W / 2) * 64 * 2;
+    s.im2col[0].ensure(ib);
+    launch_im2col(ctx->L(), inp, B, H, W, C, s.im2col[0].p);
+    if (tar) { s.im2col[1].ensure(ib); launch_im2col(ctx->L(), tar, B, H, W, C, s.im2col[1].p); }
+  } else {
+    launch_convert(ctx->L(), ctx->dt, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
+    if (tar) launch_convert(ctx->L(), ctx->dt, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
+  }
   View in = make_view(s.in0.p, B, H, W, C0);
   int h = H, w = W;
   for (int li = 0; li < 4; ++li) {
@@ -581,6 +639,8 @@ static void adam_apply(gan_adam* o, bool reduced = false) {
   ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
   launch_adam_pack(ctx->L(), ctx->dt, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
   launch_adam_ranges(ctx->L(), a, (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
+  if (n->pack_im2col_tiles > 0)     // first layer's im2col-ordered forward copy (a few thousand weights)
+    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, 1, n->pack_im2col_tiles);
   n->packed_dirty = false;
 }
 static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {

@@ -97,6 +97,9 @@ struct Layer {
   int tag = 0;
   int64_t w_off = -1, g_off = -1, b_off = -1, bias_off = -1, mov_off = -1;
   DevBuf wp_fwd, wp_dgrad;
+  // first layers in bf16/tcgen05 mode: GEMM over im2col buffers (one 64-wide K-block per input source)
+  bool first = false; int nsrc = 1, src_c = 0;
+  DevBuf wp_im2col;
 };
 
 // Saved state of one forward call of a net (the "tape" of that call).
@@ -112,6 +115,8 @@ struct Slot {
   std::vector<DevBuf> cat, dcat, dskip;
   // discriminator
   DevBuf in0, logits, dlogit, din0;
+  DevBuf im2col[2];          // first-layer im2col rows per input source
+  bool used_im2col = false;
   std::vector<DevBuf> act, dact;
 };
 
@@ -129,6 +134,7 @@ struct gan_net {
   bool packed_dirty = true;
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
   int pack_nent = 0, pack_tiles = 0;
+  DevBuf pack_tab_im2col; int pack_im2col_tiles = 0;   // extra forward copy of the first layer in im2col K order
   DevBuf adam_tab, adam_ranges;   // fused Adam+pack tables (AdamPackEntry / AdamRange)
   int adam_nent = 0, adam_tiles = 0, adam_nranges = 0;
 };
