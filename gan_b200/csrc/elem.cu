@@ -936,3 +936,68 @@ void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void*
   k_im2col<<<grid_for(M, 256, 16), 256, 0, L.s>>>(src, B, H, W, C, (bf16*)dst_bf16);
   KLAUNCH(L);
 }
+
+__global__ void __launch_bounds__(256) k_im2col_bf16(const bf16* __restrict__ src, int pitch, int B, int H, int W, int C,
+                                                     bf16* __restrict__ dst) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t M = (int64_t)B * Ho * Wo;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(m % Wo); const int64_t r = m / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    __nv_bfloat16 row[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) row[k] = __float2bfloat16_rn(0.f);
+    for (int kh = 0; kh < 4; ++kh) {
+      const int ih = 2 * oh + kh - 1;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 4; ++kw) {
+        const int iw = 2 * ow + kw - 1;
+        if (iw < 0 || iw >= W) continue;
+        const bf16* sp = src + (((int64_t)n * H + ih) * W + iw) * pitch;
+        for (int c = 0; c < C; ++c) row[(kh * 4 + kw) * C + c] = sp[c];
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + m * 64);
+    const uint4* rv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rv[j];
+  }
+}
+void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H, int W, int C, void* dst_bf16) {
+  GAN_REQUIRE(16 * C <= 64, "im2col supports up to 4 channels");
+  const int64_t M = (int64_t)B * (H / 2) * (W / 2);
+  k_im2col_bf16<<<grid_for(M, 256, 16), 256, 0, L.s>>>((const bf16*)src_bf16, pitch, B, H, W, C, (bf16*)dst_bf16);
+  KLAUNCH(L);
+}
+
+// One thread per output pixel; taps per output parity as in geom_convT4 / oracle direct.CONVT_TAPS.
+__global__ void __launch_bounds__(256) k_col2im_tanh(const bf16* __restrict__ cols, const float* __restrict__ bias, int B,
+                                                     int Hin, int Win, int C, float* __restrict__ out) {
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(q % Wo); const int64_t r = q / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    const int a = oh & 1, b = ow & 1, i = oh >> 1, j = ow >> 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int th = 0; th < 2; ++th) {
+      const int kh = a ? (th ? 2 : 0) : (th ? 3 : 1), dh = a ? (th ? 0 : 1) : (th ? -1 : 0);
+      const int ih = i + dh;
+      if (ih < 0 || ih >= Hin) continue;
+#pragma unroll
+      for (int tw = 0; tw < 2; ++tw) {
+        const int kw = b ? (tw ? 2 : 0) : (tw ? 3 : 1), dw = b ? (tw ? 0 : 1) : (tw ? -1 : 0);
+        const int iw = j + dw;
+        if (iw < 0 || iw >= Win) continue;
+        const bf16* cp = cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * C;
+        for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(cp[c]);
+      }
+    }
+    for (int c = 0; c < C; ++c) out[q * C + c] = tanhf(acc[c] + __ldg(bias + c));
+  }
+}
+void launch_col2im_tanh(Launch L, const void* cols_bf16, const float* bias, int B, int Hin, int Win, int C, float* out_f32) {
+  GAN_REQUIRE(C <= 4, "col2im head supports up to 4 channels");
+  const int64_t total = (int64_t)B * Hin * Win * 4;
+  k_col2im_tanh<<<grid_for(total, 256, 16), 256, 0, L.s>>>((const bf16*)cols_bf16, bias, B, Hin, Win, C, out_f32);
+  KLAUNCH(L);
+}

@@ -126,6 +126,24 @@ static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
   return op;
 }
 
+// Generator head (Conv2DTranspose Cin -> C<=4, bias, tanh) as single-tap GEMMs (bf16 + tcgen05 only):
+//   forward : cols[m][tap*C+co] = x[m,:] . f[tap,co,:]   then col2im + bias + tanh
+//   backward: G = im2col(dz) (the 4x4 s2 unfold of the output gradient);  dW = G^T x ;  dx = G f
+// so the Cin-channel activation is read once instead of once per (class, tap).
+static bool cols_on(const gan_ctx* ctx, const gan_net* n, const Layer& ly) {
+  return n->is_gen && ly.head && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.Cout * 16 <= 64 &&
+         ly.Cin % 64 == 0 && ly.wp_cols.p != nullptr;
+}
+static ConvOp make_op_1tap(View in, int Kc, View out, int Nc, int Nr, const void* B) {
+  ConvOp op; memset(&op, 0, sizeof(op));
+  op.ncls = 1; op.cls[0].ntaps = 1;
+  op.in = in.p; op.in_pitch = in.pitch; op.in_coff = in.coff; op.Hin = in.H; op.Win = in.W;
+  op.out = out.p; op.out_pitch = out.pitch; op.out_coff = out.coff; op.Hout = out.H; op.Wout = out.W;
+  op.N = in.N; op.Hm = in.H; op.Wm = in.W; op.si = 1; op.so = 1;
+  op.Kc = Kc; op.Kr = Kc; op.Nc = Nc; op.Nr = Nr; op.B = B;
+  return op;
+}
+
 static void out_dims(int kind, int Hin, int Win, int& Ho, int& Wo) {
   if (kind == K_CONV_S2) { Ho = Hin / 2; Wo = Win / 2; }
   else if (kind == K_CONV_S1P) { Ho = Hin - 1; Wo = Win - 1; }
@@ -254,7 +272,15 @@ static void pack_weights(gan_net* n) {
     n->pack_tab.ensure(tab.size() * sizeof(PackEntry));
     CUDA_CHECK(cudaMemcpy(n->pack_tab.p, tab.data(), tab.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
     n->pack_nent = (int)tab.size(); n->pack_tiles = tiles;
-    // extra forward copy of the first layer in im2col K order (bf16 mode)
+    // extra packed copies (bf16 mode): the first layer in im2col K order; the generator head as the two
+    // single-tap GEMM operands of its cols formulation
+    std::vector<PackEntry> extra;
+    int xtiles = 0;
+    auto push_extra = [&](PackEntry& e) {
+      e.tiles_k = (e.op.Kc + 31) / 32; e.tiles_n = (e.op.Nc + 31) / 32; e.tile_begin = xtiles;
+      xtiles += e.tiles_k * e.tiles_n * e.op.cls[0].ntaps * e.op.ncls;
+      extra.push_back(e);
+    };
     Layer& l0 = n->layers[0];
     if (l0.first && ctx->dt == DT_BF16 && l0.src_c * 16 <= 64) {
       PackEntry e; memset(&e, 0, sizeof(e));
@@ -265,15 +291,36 @@ static void pack_weights(gan_net* n) {
       po.im2col_c = l0.src_c; po.Ktot = l0.nsrc * 64;
       l0.wp_im2col.ensure((size_t)l0.Cout_p * po.Ktot * ctx->esize());
       e.master = n->params.as<float>() + l0.w_off; e.dst = l0.wp_im2col.p;
-      e.tiles_k = (po.Kc + 31) / 32; e.tiles_n = (po.Nc + 31) / 32; e.tile_begin = 0;
-      n->pack_im2col_tiles = e.tiles_k * e.tiles_n * 16;
-      n->pack_tab_im2col.ensure(sizeof(PackEntry));
-      CUDA_CHECK(cudaMemcpy(n->pack_tab_im2col.p, &e, sizeof(PackEntry), cudaMemcpyHostToDevice));
+      push_extra(e);
+    }
+    Layer& lh = n->layers.back();
+    if (n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout * 16 <= 64 && lh.Cin % 64 == 0) {
+      const int nr = 16 * lh.Cout;                               // 48 real cols rows (tap, co)
+      // master (kh,kw,co,ci) flattened = [n = tap*C+co][ci]
+      PackEntry e; memset(&e, 0, sizeof(e));
+      PackOp& po = e.op;                                         // forward: cols = x * B^T, B[n][ci]
+      po.ncls = 1; po.cls[0].ntaps = 1; po.cls[0].widx[0] = 0;
+      po.Kc = lh.Cin; po.Kr = lh.Cin; po.Nc = 64; po.Nr = nr; po.s_tap = 0; po.s_k = 1; po.s_n = lh.Cin;
+      lh.wp_cols.ensure((size_t)64 * lh.Cin * ctx->esize());
+      e.master = n->params.as<float>() + lh.w_off; e.dst = lh.wp_cols.p;
+      push_extra(e);
+      PackEntry d; memset(&d, 0, sizeof(d));
+      PackOp& pd = d.op;                                         // dgrad: dx = G * B, B[n = ci][k = tap*C+co]
+      pd.ncls = 1; pd.cls[0].ntaps = 1; pd.cls[0].widx[0] = 0;
+      pd.Kc = 64; pd.Kr = nr; pd.Nc = lh.Cin; pd.Nr = lh.Cin; pd.s_tap = 0; pd.s_k = lh.Cin; pd.s_n = 1;
+      lh.wp_dcols.ensure((size_t)lh.Cin * 64 * ctx->esize());
+      d.master = n->params.as<float>() + lh.w_off; d.dst = lh.wp_dcols.p;
+      push_extra(d);
+    }
+    if (!extra.empty()) {
+      n->pack_tab_im2col.ensure(extra.size() * sizeof(PackEntry));
+      CUDA_CHECK(cudaMemcpy(n->pack_tab_im2col.p, extra.data(), extra.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
+      n->pack_im2col_nent = (int)extra.size(); n->pack_im2col_tiles = xtiles;
     }
   }
   launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab.p, n->pack_nent, n->pack_tiles);
   if (n->pack_im2col_tiles > 0)
-    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, 1, n->pack_im2col_tiles);
+    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, n->pack_im2col_nent, n->pack_im2col_tiles);
   n->packed_dirty = false;
 }
 
@@ -294,7 +341,16 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   int Ho, Wo; out_dims(ly.kind, in.H, in.W, Ho, Wo);
   const int B = in.N;
   s.in_views[li] = in; s.out_views[li] = out;
+  if (ly.head && cols_on(ctx, n, ly)) {
+    s.used_cols = true;
+    s.cols.ensure((size_t)B * in.H * in.W * 64 * 2);
+    View cols = make_view(s.cols.p, B, in.H, in.W, 64);
+    run_conv_fwd(ctx, make_op_1tap(in, ly.Cin, cols, 64, 16 * ly.Cout, ly.wp_cols.p));
+    launch_col2im_tanh(ctx->L(), s.cols.p, n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
+    return;
+  }
   if (ly.head) {
+    if (n->is_gen) s.used_cols = false;
     // generator head: bias + tanh -> fp32 image; discriminator head: bias -> fp32 logits
     View y = make_view(nullptr, B, Ho, Wo, ly.Cout_p);
     ConvOp op = make_op(ly, R_FWD, in, y, ly.wp_fwd.p);
@@ -455,7 +511,21 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   {
     int pitch = UP_F[6] + DOWN_F[0];
     View din = make_view(s.dcat[6].p, B, H / 2, W / 2, pitch);
-    layer_backward(g, s, 15, GradSrc{s.dlogit.p, Cp, 0}, GradSrc{nullptr, 0, 0}, din, true);
+    Layer& lh = g->layers[15];
+    if (s.used_cols) {
+      // G = im2col(dz): [B*(H/2)*(W/2)][tap*C+co]; dW (kh,kw,co,ci) = G^T x; dx = G f
+      s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
+      launch_im2col_bf16(ctx->L(), s.dlogit.p, Cp, B, H, W, C, s.gcols.p);
+      View x = s.in_views[15];
+      View G = make_view(s.gcols.p, B, H / 2, W / 2, 64);
+      ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 16 * C, nullptr);
+      wg.dW = gr + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin;
+      run_conv_wgrad(ctx, wg);
+      ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p);
+      run_conv_fwd(ctx, dg);
+    } else {
+      layer_backward(g, s, 15, GradSrc{s.dlogit.p, Cp, 0}, GradSrc{nullptr, 0, 0}, din, true);
+    }
   }
   s.dd8.ensure((size_t)B * (H >> 8) * (W >> 8) * 512 * es);
   for (int k = 7; k >= 1; --k) {
@@ -640,7 +710,7 @@ static void adam_apply(gan_adam* o, bool reduced = false) {
   launch_adam_pack(ctx->L(), ctx->dt, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
   launch_adam_ranges(ctx->L(), a, (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
   if (n->pack_im2col_tiles > 0)     // first layer's im2col-ordered forward copy (a few thousand weights)
-    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, 1, n->pack_im2col_tiles);
+    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, n->pack_im2col_nent, n->pack_im2col_tiles);
   n->packed_dirty = false;
 }
 static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {

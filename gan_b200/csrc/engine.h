@@ -100,6 +100,8 @@ struct Layer {
   // first layers in bf16/tcgen05 mode: GEMM over im2col buffers (one 64-wide K-block per input source)
   bool first = false; int nsrc = 1, src_c = 0;
   DevBuf wp_im2col;
+  // generator head in bf16/tcgen05 mode: Conv2DTranspose as GEMM over `cols` + col2im (see engine.cu)
+  DevBuf wp_cols, wp_dcols;
 };
 
 // Saved state of one forward call of a net (the "tape" of that call).
@@ -116,6 +118,8 @@ struct Slot {
   // discriminator
   DevBuf in0, logits, dlogit, din0;
   DevBuf im2col[2];          // first-layer im2col rows per input source
+  DevBuf cols, gcols;        // generator head: cols = x*W (forward), gcols = im2col(dz) (backward)
+  bool used_cols = false;
   bool used_im2col = false;
   std::vector<DevBuf> act, dact;
 };
@@ -134,7 +138,7 @@ struct gan_net {
   bool packed_dirty = true;
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
   int pack_nent = 0, pack_tiles = 0;
-  DevBuf pack_tab_im2col; int pack_im2col_tiles = 0;   // extra forward copy of the first layer in im2col K order
+  DevBuf pack_tab_im2col; int pack_im2col_tiles = 0, pack_im2col_nent = 0;   // extra packed copies: first layer in im2col K order, head as cols GEMMs
   DevBuf adam_tab, adam_ranges;   // fused Adam+pack tables (AdamPackEntry / AdamRange)
   int adam_nent = 0, adam_tiles = 0, adam_nranges = 0;
 };
