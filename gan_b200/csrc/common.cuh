@@ -58,6 +58,7 @@ struct ConvOp {
   // im2col first layers (bf16/tcgen05 mode): the op is a 1x1 GEMM whose `ntaps` K-blocks of 64 are
   // separate im2col buffers [M][64] (one per input source); k' = t16*im2col_c + c inside a block.
   const void* in_tap[4]; int im2col_c;
+  float* out_rows_f32;           // optional: write the raw fp32 accumulators as rows [out pixel][Nc] (no bf16 output)
 };
 
 // ---- error handling (host) -----------------------------------------------------------------

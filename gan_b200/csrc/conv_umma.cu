@@ -187,6 +187,7 @@ struct alignas(64) UmmaFwdParams {
   int N, Hm, Wm, Nc;
   const float* bias; float* out_f32; int epi, Nr;
   int num_tiles, ncls;
+  int f32out;                        // write fp32 rows to ws (slab 0) instead of bf16 (cols of the generator head)
   float* ws; int ksplit; long long slab;   // split-K: split ks stores fp32 into ws[ks][pix][Nc] (no atomics)
 };
 
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(acc + c, v);
-          if (valid && p.ksplit > 1) {
+          if (valid && (p.ksplit > 1 || p.f32out)) {
             float4* wdst = reinterpret_cast<float4*>(p.ws + (long long)(tile % p.ksplit) * p.slab + pix * p.Nc + n0 + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -405,7 +406,7 @@ bool umma_fwd_supported(const ConvOp& op) {
   if (op.Kc == 16 && op.cls[0].ntaps % 4 != 0) return false;
   if (!view_ok(op.in_pitch, op.in_coff, op.in)) return false;
   if (op.out != nullptr && !view_ok(op.out_pitch, op.out_coff, op.out)) return false;
-  if (op.out == nullptr && op.out_f32 == nullptr) return false;
+  if (op.out == nullptr && op.out_f32 == nullptr && op.out_rows_f32 == nullptr) return false;
   if ((op.epi != EPI_NONE || op.out_f32 != nullptr) && op.Nc != 16) return false;
   if (op.si == 2 && (op.Hin % 2 != 0 || op.Win % 2 != 0)) return false;
   return true;
@@ -471,13 +472,15 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
     fill_fwd_params(P, op, BN, KC);
   }
   P.num_tiles = P.tiles_w * P.tiles_h * P.tiles_n * (op.Nc / BN) * op.ncls;
-  P.ksplit = 1; P.ws = nullptr;
+  P.ksplit = 1; P.ws = nullptr; P.f32out = 0;
+  if (op.out_rows_f32 != nullptr) { P.ws = op.out_rows_f32; P.f32out = 1; P.slab = 0; }
   // split-K for layers with too few output tiles to fill the chip (the 1x1..8x8 bottleneck layers:
   // a serial 128-k-block loop on 4..128 CTAs is pure TMA->MMA latency): k-ranges go to separate CTAs,
   // fp32 atomics into a workspace, one conversion pass to bf16.
   const int nk = (KC == 64) ? op.cls[0].ntaps * (op.Kc / 64) : op.cls[0].ntaps / 4;
   const size_t out_elems = (size_t)op.N * op.Hout * op.Wout * op.Nc;
-  if (op.splitk_ws != nullptr && BN >= 64 && BN <= 128 && P.num_tiles <= 74 && op.epi == EPI_NONE && op.out_f32 == nullptr) {
+  if (op.splitk_ws != nullptr && BN >= 64 && BN <= 128 && P.num_tiles <= 74 && op.epi == EPI_NONE && op.out_f32 == nullptr &&
+      op.out_rows_f32 == nullptr) {
     int ks = (2 * 148) / P.num_tiles;
     if (ks > nk / 8) ks = nk / 8;
     while (ks >= 2 && out_elems * 4 * ks > op.splitk_ws_bytes) --ks;

@@ -970,7 +970,7 @@ void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H,
 }
 
 // One thread per output pixel; taps per output parity as in geom_convT4 / oracle direct.CONVT_TAPS.
-__global__ void __launch_bounds__(256) k_col2im_tanh(const bf16* __restrict__ cols, const float* __restrict__ bias, int B,
+__global__ void __launch_bounds__(256) k_col2im_tanh(const float* __restrict__ cols, const float* __restrict__ bias, int B,
                                                      int Hin, int Win, int C, float* __restrict__ out) {
   const int Ho = 2 * Hin, Wo = 2 * Win;
   const int64_t total = (int64_t)B * Ho * Wo;
@@ -988,16 +988,16 @@ __global__ void __launch_bounds__(256) k_col2im_tanh(const bf16* __restrict__ co
         const int kw = b ? (tw ? 2 : 0) : (tw ? 3 : 1), dw = b ? (tw ? 0 : 1) : (tw ? -1 : 0);
         const int iw = j + dw;
         if (iw < 0 || iw >= Win) continue;
-        const bf16* cp = cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * C;
-        for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(cp[c]);
+        const float* cp = cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * C;
+        for (int c = 0; c < C; ++c) acc[c] += __ldg(cp + c);
       }
     }
     for (int c = 0; c < C; ++c) out[q * C + c] = tanhf(acc[c] + __ldg(bias + c));
   }
 }
-void launch_col2im_tanh(Launch L, const void* cols_bf16, const float* bias, int B, int Hin, int Win, int C, float* out_f32) {
+void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32) {
   GAN_REQUIRE(C <= 4, "col2im head supports up to 4 channels");
   const int64_t total = (int64_t)B * Hin * Win * 4;
-  k_col2im_tanh<<<grid_for(total, 256, 16), 256, 0, L.s>>>((const bf16*)cols_bf16, bias, B, Hin, Win, C, out_f32);
+  k_col2im_tanh<<<grid_for(total, 256, 16), 256, 0, L.s>>>(cols, bias, B, Hin, Win, C, out_f32);
   KLAUNCH(L);
 }

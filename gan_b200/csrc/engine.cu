@@ -343,10 +343,12 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   s.in_views[li] = in; s.out_views[li] = out;
   if (ly.head && cols_on(ctx, n, ly)) {
     s.used_cols = true;
-    s.cols.ensure((size_t)B * in.H * in.W * 64 * 2);
-    View cols = make_view(s.cols.p, B, in.H, in.W, 64);
-    run_conv_fwd(ctx, make_op_1tap(in, ly.Cin, cols, 64, 16 * ly.Cout, ly.wp_cols.p));
-    launch_col2im_tanh(ctx->L(), s.cols.p, n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
+    s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);            // fp32 rows: the 4-term col2im sum is not pre-rounded
+    View cols = make_view(nullptr, B, in.H, in.W, 64);
+    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 16 * ly.Cout, ly.wp_cols.p);
+    cop.out_rows_f32 = s.cols.as<float>();
+    run_conv_fwd(ctx, cop);
+    launch_col2im_tanh(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
     return;
   }
   if (ly.head) {

@@ -17,9 +17,9 @@ void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* 
 void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16);
 // Same rows from a bf16 image with pixel pitch `pitch` (generator-head gradient dz): G[m][t*C + c]
 void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H, int W, int C, void* dst_bf16);
-// Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*C + co] (bf16, 64 per input-grid point m) ->
+// Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*C + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
-void launch_col2im_tanh(Launch L, const void* cols_bf16, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
+void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
 void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64_t P, int C, float* dst);
 // dst view = sum over `nslab` fp32 slabs [nslab][P][C] (deterministic split-K reduction)
 void launch_sum_slabs(Launch L, int dt, const float* slabs, int nslab, int64_t P, int C, void* dst, int pitch, int coff);
