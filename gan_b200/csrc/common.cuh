@@ -56,8 +56,9 @@ struct ConvOp {
   // optional fp32 workspace for split-K forward launches (small-M layers): [out pixels][Nc]
   float* splitk_ws; size_t splitk_ws_bytes;
   // im2col first layers (bf16/tcgen05 mode): the op is a 1x1 GEMM whose `ntaps` K-blocks of 64 are
-  // separate im2col buffers [M][64] (one per input source); k' = t16*im2col_c + c inside a block.
+  // separate im2col buffers [M][64] (one per input source); k' = tap16*4 + c inside a block, c < im2col_c.
   const void* in_tap[4]; int im2col_c;
+  int n_slot4_c;                 // wgrad: output column n = tap*4 + c (c < n_slot4_c real) maps to master row tap*n_slot4_c + c
   float* out_rows_f32;           // optional: write the raw fp32 accumulators as rows [out pixel][Nc] (no bf16 output)
 };
 

@@ -518,7 +518,8 @@ struct alignas(64) UmmaWgradParams {
   int splits;
   float* dW; long long s_tap, s_k, s_n;
   int Nc, Kr, Nr;
-  int im2col_c;            // >0: rows are im2col K-blocks (t = source, kc = tap16*c + channel)
+  int im2col_c;            // >0: rows are im2col K-blocks (t = source, kc = tap16*4 + channel slot)
+  int n_slot4_c;           // >0: columns are (tap16*4 + channel slot) of a cols matrix
 };
 
 constexpr int WG_STAGES = 3;
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
       float* dst = p.dW + (long long)p.widx[cls][t & 15] * p.s_tap + (long long)kc * p.s_k + (long long)n0 * p.s_n;
       if (p.im2col_c > 0) {
         const int ic = p.im2col_c;
-        row_ok = t < p.ntaps[cls] && kc < 16 * ic;
-        dst = p.dW + (long long)(kc / ic) * p.s_tap + (long long)(t * ic + kc % ic) * p.s_k + (long long)n0 * p.s_n;
+        row_ok = t < p.ntaps[cls] && (kc & 3) < ic;
+        dst = p.dW + (long long)(kc >> 2) * p.s_tap + (long long)(t * ic + (kc & 3)) * p.s_k + (long long)n0 * p.s_n;
       }
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
@@ -633,8 +634,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
           if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c + j < p.Nr) atomicAdd(dst + (long long)(c + j) * p.s_n, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) {
+              const int nn = n0 + c + j;
+              if (p.n_slot4_c > 0) {      // cols column (tap*4 + slot) -> master row tap*C + slot
+                if ((nn & 3) < p.n_slot4_c)
+                  atomicAdd(p.dW + (long long)kc * p.s_k + (long long)((nn >> 2) * p.n_slot4_c + (nn & 3)) * p.s_n, __uint_as_float(v[j]));
+              } else if (nn < p.Nr) atomicAdd(dst + (long long)(c + j) * p.s_n, __uint_as_float(v[j]));
+            }
           }
         }
       } else {
@@ -698,6 +704,7 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   P.Kc = op.Kc;
   P.dW = op.dW; P.s_tap = op.s_tap; P.s_k = op.s_k; P.s_n = op.s_n; P.Nc = op.Nc; P.Kr = op.Kr; P.Nr = op.Nr;
   P.im2col_c = op.in_tap[0] != nullptr ? op.im2col_c : 0;
+  P.n_slot4_c = op.n_slot4_c;
   const int ntaps = op.cls[0].ntaps;
   const int mblocks = (ntaps * op.Kc + 127) / 128;
   const int ntiles = op.Nc / BN;

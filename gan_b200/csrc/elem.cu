@@ -736,10 +736,7 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
   const ClassGeom& cg = op.cls[ci];
   const float* __restrict__ src = E.master + (int64_t)cg.widx[t] * op.s_tap;
   T* __restrict__ dst = (T*)E.dst + cg.b_off;
-  const int64_t Ktot = op.im2col_c ? op.Ktot : (int64_t)ntaps * op.Kc;
-  const int ic = op.im2col_c;
-  // packed K index of channel kc of tap t
-  auto kidx = [&](int kc) -> int64_t { return ic ? (int64_t)(kc / ic) * 64 + (int64_t)t * ic + kc % ic : (int64_t)t * op.Kc + kc; };
+  const int64_t Ktot = (int64_t)ntaps * op.Kc;
   const int k0 = tk * 32, n0 = tn * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   if (op.s_n == 1) {
@@ -753,7 +750,7 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
       int n = n0 + r, kc = k0 + tx;
-      if (n < op.Nc && kc < (ic ? op.Kr : op.Kc)) dst[(int64_t)n * Ktot + kidx(kc)] = from_f<T>(tile[tx][r]);
+      if (n < op.Nc && kc < op.Kc) dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(tile[tx][r]);
     }
   } else {
     // master contiguous along kc (s_k == 1): straight tile copy
@@ -762,7 +759,7 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
       int n = n0 + r, kc = k0 + tx;
       if (n < op.Nc && kc < op.Kc) {
         float v = (kc < op.Kr && n < op.Nr) ? src[(int64_t)kc * op.s_k + (int64_t)n * op.s_n] : 0.f;
-        if (!ic || kc < op.Kr) dst[(int64_t)n * Ktot + kidx(kc)] = from_f<T>(v);
+        dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(v);
       }
     }
   }
@@ -814,8 +811,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
   const int a0 = ta * APT, b0 = tb * APT;
   const int tx = threadIdx.x & (APT - 1), ty = threadIdx.x >> 6;          // 64 x 4
   const int cF = E.invF[widx] >> 4, tF = E.invF[widx] & 15, cD = E.invD[widx] >> 4, tD = E.invD[widx] & 15;
-  const int ic = E.im2col_c;
-  T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (ic ? (long long)tF * ic : (long long)tF * E.KcF);   // + co*KtotF + ci
+  T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
   T* __restrict__ dD = (T*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
   const long long base = E.w_off + (long long)widx * E.A * E.B;
   const int bi = b0 + tx;
@@ -854,7 +850,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
     const int r = ty + 4 * i;                 // row of the transposed tile = b index
     const int bj = b0 + r, ai = a0 + tx;
     if (ai < E.A && bj < E.B) {
-      if (E.conv2d) dF[(long long)bj * E.KtotF + (ic ? (ai / ic) * 64 + ai % ic : ai)] = from_f<T>(tile[tx][r]);   // co = b, ci = a
+      if (E.conv2d) dF[(long long)bj * E.KtotF + ai] = from_f<T>(tile[tx][r]);   // co = b, ci = a
       else dD[(long long)bj * E.KtotD + ai] = from_f<T>(tile[tx][r]);            // ci = b, co = a
     }
   }
@@ -902,74 +898,79 @@ void launch_sum_slabs(Launch L, int dt, const float* slabs, int nslab, int64_t P
 }
 
 // ---------------------------------------------------------------------------------------------
-// im2col of the first layer (Conv2D 4x4 s2 'same' on 1..4-channel images, base_gan.py:141,180):
-// one thread per output pixel writes one full 128-byte row [16 taps x C | zero pad].
+// Small special weight layouts (first-layer im2col order, head cols operands): dst[i] = master[idx[i]]
+// through a device index table built once on the host (idx < 0 -> 0).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_im2col(const float* __restrict__ src, int B, int H, int W, int C,
+template <typename T>
+__global__ void k_gather_pack(const float* __restrict__ master, const int* __restrict__ idx, int n, T* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int j = idx[i];
+    dst[i] = from_f<T>(j >= 0 ? master[j] : 0.f);
+  }
+}
+void launch_gather_pack(Launch L, int dt, const float* master, const int* idx_dev, int n, void* dst) {
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    k_gather_pack<T><<<grid_for(n, 256, 2), 256, 0, L.s>>>(master, idx_dev, n, (T*)dst);
+  });
+  KLAUNCH(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col of a 4x4 stride-2 'same' window over a 1..4-channel image (first layers base_gan.py:141,180;
+// unfold of the generator-head gradient): one thread per output-grid point writes one 128-byte row
+// [16 taps x 4 channel slots] (slots >= C are zero), entirely from registers.
+// ---------------------------------------------------------------------------------------------
+template <typename TS, int C>
+__global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int pitch, int B, int H, int W,
                                                 bf16* __restrict__ dst) {
   const int Ho = H / 2, Wo = W / 2;
   const int64_t M = (int64_t)B * Ho * Wo;
   for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
     const int ow = (int)(m % Wo); const int64_t r = m / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
-    __nv_bfloat16 row[64];
+    uint2 row[16];
 #pragma unroll
-    for (int k = 0; k < 64; ++k) row[k] = __float2bfloat16_rn(0.f);
     for (int kh = 0; kh < 4; ++kh) {
       const int ih = 2 * oh + kh - 1;
-      if (ih < 0 || ih >= H) continue;
+#pragma unroll
       for (int kw = 0; kw < 4; ++kw) {
         const int iw = 2 * ow + kw - 1;
-        if (iw < 0 || iw >= W) continue;
-        const float* sp = src + (((int64_t)n * H + ih) * W + iw) * C;
-        for (int c = 0; c < C; ++c) row[(kh * 4 + kw) * C + c] = __float2bfloat16_rn(__ldg(sp + c));
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+          const TS* sp = src + (((int64_t)n * H + ih) * W + iw) * pitch;
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[c] = to_f(sp[c]);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        row[kh * 4 + kw] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       }
     }
     uint4* o = reinterpret_cast<uint4*>(dst + m * 64);
-    const uint4* rv = reinterpret_cast<const uint4*>(row);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = rv[j];
+    for (int j = 0; j < 8; ++j) o[j] = make_uint4(row[2 * j].x, row[2 * j].y, row[2 * j + 1].x, row[2 * j + 1].y);
   }
+}
+template <typename TS>
+static void im2col_dispatch(Launch L, const TS* src, int pitch, int B, int H, int W, int C, void* dst) {
+  GAN_REQUIRE(C >= 1 && C <= 4, "im2col supports 1..4 channels per source");
+  const int64_t M = (int64_t)B * (H / 2) * (W / 2);
+  const int grid = grid_for(M, 256, 16);
+  bf16* d = (bf16*)dst;
+  if (C == 1) k_im2col<TS, 1><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  else if (C == 2) k_im2col<TS, 2><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  else if (C == 3) k_im2col<TS, 3><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  else k_im2col<TS, 4><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  KLAUNCH(L);
 }
 void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16) {
-  GAN_REQUIRE(16 * C <= 64, "im2col first layer supports up to 4 channels per source");
-  const int64_t M = (int64_t)B * (H / 2) * (W / 2);
-  k_im2col<<<grid_for(M, 256, 16), 256, 0, L.s>>>(src, B, H, W, C, (bf16*)dst_bf16);
-  KLAUNCH(L);
-}
-
-__global__ void __launch_bounds__(256) k_im2col_bf16(const bf16* __restrict__ src, int pitch, int B, int H, int W, int C,
-                                                     bf16* __restrict__ dst) {
-  const int Ho = H / 2, Wo = W / 2;
-  const int64_t M = (int64_t)B * Ho * Wo;
-  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
-    const int ow = (int)(m % Wo); const int64_t r = m / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
-    __nv_bfloat16 row[64];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) row[k] = __float2bfloat16_rn(0.f);
-    for (int kh = 0; kh < 4; ++kh) {
-      const int ih = 2 * oh + kh - 1;
-      if (ih < 0 || ih >= H) continue;
-      for (int kw = 0; kw < 4; ++kw) {
-        const int iw = 2 * ow + kw - 1;
-        if (iw < 0 || iw >= W) continue;
-        const bf16* sp = src + (((int64_t)n * H + ih) * W + iw) * pitch;
-        for (int c = 0; c < C; ++c) row[(kh * 4 + kw) * C + c] = sp[c];
-      }
-    }
-    uint4* o = reinterpret_cast<uint4*>(dst + m * 64);
-    const uint4* rv = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = rv[j];
-  }
+  im2col_dispatch<float>(L, src, C, B, H, W, C, dst_bf16);
 }
 void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H, int W, int C, void* dst_bf16) {
-  GAN_REQUIRE(16 * C <= 64, "im2col supports up to 4 channels");
-  const int64_t M = (int64_t)B * (H / 2) * (W / 2);
-  k_im2col_bf16<<<grid_for(M, 256, 16), 256, 0, L.s>>>((const bf16*)src_bf16, pitch, B, H, W, C, (bf16*)dst_bf16);
-  KLAUNCH(L);
+  im2col_dispatch<bf16>(L, (const bf16*)src_bf16, pitch, B, H, W, C, dst_bf16);
 }
 
-// One thread per output pixel; taps per output parity as in geom_convT4 / oracle direct.CONVT_TAPS.
+// col2im of the transposed-conv head: one thread per output pixel gathers its 4 contributing taps
+// (one aligned float4 each) from cols[m][tap*4 + co]; taps per output parity as geom_convT4.
 __global__ void __launch_bounds__(256) k_col2im_tanh(const float* __restrict__ cols, const float* __restrict__ bias, int B,
                                                      int Hin, int Win, int C, float* __restrict__ out) {
   const int Ho = 2 * Hin, Wo = 2 * Win;
@@ -988,8 +989,8 @@ __global__ void __launch_bounds__(256) k_col2im_tanh(const float* __restrict__ c
         const int kw = b ? (tw ? 2 : 0) : (tw ? 3 : 1), dw = b ? (tw ? 0 : 1) : (tw ? -1 : 0);
         const int iw = j + dw;
         if (iw < 0 || iw >= Win) continue;
-        const float* cp = cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * C;
-        for (int c = 0; c < C; ++c) acc[c] += __ldg(cp + c);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * 4));
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
       }
     }
     for (int c = 0; c < C; ++c) out[q * C + c] = tanhf(acc[c] + __ldg(bias + c));

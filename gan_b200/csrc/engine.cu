@@ -107,7 +107,7 @@ static ConvOp make_op(const Layer& ly, int role, View x, View y, const void* wpa
 // First layers as a GEMM over im2col rows (bf16 + tcgen05 engine only; the FFMA cross-check and the
 // fp32 mode keep the generic tap path).
 static bool im2col_on(const gan_ctx* ctx, const Layer& ly) {
-  return ly.first && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.src_c * 16 <= 64 && ly.Cout_p % 64 == 0;
+  return ly.first && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.src_c <= 4 && ly.Cout_p % 64 == 0;
 }
 // role: R_FWD (y = z written) or R_WGRAD (y = dz read).  M-space = output grid of the layer.
 static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
@@ -131,7 +131,7 @@ static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
 //   backward: G = im2col(dz) (the 4x4 s2 unfold of the output gradient);  dW = G^T x ;  dx = G f
 // so the Cin-channel activation is read once instead of once per (class, tap).
 static bool cols_on(const gan_ctx* ctx, const gan_net* n, const Layer& ly) {
-  return n->is_gen && ly.head && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.Cout * 16 <= 64 &&
+  return n->is_gen && ly.head && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.Cout <= 4 &&
          ly.Cin % 64 == 0 && ly.wp_cols.p != nullptr;
 }
 static ConvOp make_op_1tap(View in, int Kc, View out, int Nc, int Nr, const void* B) {
@@ -272,55 +272,45 @@ static void pack_weights(gan_net* n) {
     n->pack_tab.ensure(tab.size() * sizeof(PackEntry));
     CUDA_CHECK(cudaMemcpy(n->pack_tab.p, tab.data(), tab.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
     n->pack_nent = (int)tab.size(); n->pack_tiles = tiles;
-    // extra packed copies (bf16 mode): the first layer in im2col K order; the generator head as the two
-    // single-tap GEMM operands of its cols formulation
-    std::vector<PackEntry> extra;
-    int xtiles = 0;
-    auto push_extra = [&](PackEntry& e) {
-      e.tiles_k = (e.op.Kc + 31) / 32; e.tiles_n = (e.op.Nc + 31) / 32; e.tile_begin = xtiles;
-      xtiles += e.tiles_k * e.tiles_n * e.op.cls[0].ntaps * e.op.ncls;
-      extra.push_back(e);
+    // extra packed copies (bf16 mode) through index tables: the first layer in im2col K order
+    // (k = source*64 + tap*4 + channel slot); the generator head as the two single-tap GEMM operands
+    // of its cols formulation (n = tap*4 + channel slot)
+    auto add_gather = [&](const std::vector<int>& idx, DevBuf& dstbuf) {
+      n->gathers.emplace_back();
+      gan_net::GatherTab& gt = n->gathers.back();
+      dstbuf.ensure(idx.size() * ctx->esize());
+      gt.idx.ensure(idx.size() * sizeof(int));
+      CUDA_CHECK(cudaMemcpy(gt.idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+      gt.dst = dstbuf.p; gt.n = (int)idx.size();
     };
     Layer& l0 = n->layers[0];
-    if (l0.first && ctx->dt == DT_BF16 && l0.src_c * 16 <= 64) {
-      PackEntry e; memset(&e, 0, sizeof(e));
-      PackOp& po = e.op;
-      po.ncls = 1; po.cls[0] = geom_conv16(1);
-      po.Kc = l0.Cin; po.Kr = l0.Cin; po.Nc = l0.Cout_p; po.Nr = l0.Cout;
-      po.s_tap = (int64_t)l0.Cin * l0.Cout; po.s_k = l0.Cout; po.s_n = 1;
-      po.im2col_c = l0.src_c; po.Ktot = l0.nsrc * 64;
-      l0.wp_im2col.ensure((size_t)l0.Cout_p * po.Ktot * ctx->esize());
-      e.master = n->params.as<float>() + l0.w_off; e.dst = l0.wp_im2col.p;
-      push_extra(e);
+    if (l0.first && ctx->dt == DT_BF16 && l0.src_c <= 4) {
+      const int C = l0.src_c, Kt = l0.nsrc * 64;
+      std::vector<int> idx((size_t)l0.Cout_p * Kt, -1);
+      for (int nn = 0; nn < l0.Cout; ++nn)
+        for (int sidx = 0; sidx < l0.nsrc; ++sidx)
+          for (int t = 0; t < 16; ++t)
+            for (int c = 0; c < C; ++c)
+              idx[(size_t)nn * Kt + sidx * 64 + t * 4 + c] = (int)(l0.w_off + ((int64_t)t * l0.Cin + sidx * C + c) * l0.Cout + nn);
+      add_gather(idx, l0.wp_im2col);
     }
     Layer& lh = n->layers.back();
-    if (n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout * 16 <= 64 && lh.Cin % 64 == 0) {
-      const int nr = 16 * lh.Cout;                               // 48 real cols rows (tap, co)
-      // master (kh,kw,co,ci) flattened = [n = tap*C+co][ci]
-      PackEntry e; memset(&e, 0, sizeof(e));
-      PackOp& po = e.op;                                         // forward: cols = x * B^T, B[n][ci]
-      po.ncls = 1; po.cls[0].ntaps = 1; po.cls[0].widx[0] = 0;
-      po.Kc = lh.Cin; po.Kr = lh.Cin; po.Nc = 64; po.Nr = nr; po.s_tap = 0; po.s_k = 1; po.s_n = lh.Cin;
-      lh.wp_cols.ensure((size_t)64 * lh.Cin * ctx->esize());
-      e.master = n->params.as<float>() + lh.w_off; e.dst = lh.wp_cols.p;
-      push_extra(e);
-      PackEntry d; memset(&d, 0, sizeof(d));
-      PackOp& pd = d.op;                                         // dgrad: dx = G * B, B[n = ci][k = tap*C+co]
-      pd.ncls = 1; pd.cls[0].ntaps = 1; pd.cls[0].widx[0] = 0;
-      pd.Kc = 64; pd.Kr = nr; pd.Nc = lh.Cin; pd.Nr = lh.Cin; pd.s_tap = 0; pd.s_k = lh.Cin; pd.s_n = 1;
-      lh.wp_dcols.ensure((size_t)lh.Cin * 64 * ctx->esize());
-      d.master = n->params.as<float>() + lh.w_off; d.dst = lh.wp_dcols.p;
-      push_extra(d);
-    }
-    if (!extra.empty()) {
-      n->pack_tab_im2col.ensure(extra.size() * sizeof(PackEntry));
-      CUDA_CHECK(cudaMemcpy(n->pack_tab_im2col.p, extra.data(), extra.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
-      n->pack_im2col_nent = (int)extra.size(); n->pack_im2col_tiles = xtiles;
+    if (n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout <= 4 && lh.Cin % 64 == 0) {
+      const int C = lh.Cout, Ci = lh.Cin;           // master (kh,kw,co,ci): row tap*C+co, column ci
+      std::vector<int> fc((size_t)64 * Ci, -1), dc((size_t)Ci * 64, -1);
+      for (int t = 0; t < 16; ++t)
+        for (int co = 0; co < C; ++co)
+          for (int ci = 0; ci < Ci; ++ci) {
+            const int m = (int)(lh.w_off + ((int64_t)t * C + co) * Ci + ci);
+            fc[(size_t)(t * 4 + co) * Ci + ci] = m;      // forward  B[n = tap*4+co][ci]
+            dc[(size_t)ci * 64 + t * 4 + co] = m;        // dgrad    B[n = ci][k = tap*4+co]
+          }
+      add_gather(fc, lh.wp_cols);
+      add_gather(dc, lh.wp_dcols);
     }
   }
   launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab.p, n->pack_nent, n->pack_tiles);
-  if (n->pack_im2col_tiles > 0)
-    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, n->pack_im2col_nent, n->pack_im2col_tiles);
+  for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), ctx->dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
   n->packed_dirty = false;
 }
 
@@ -345,7 +335,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     s.used_cols = true;
     s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);            // fp32 rows: the 4-term col2im sum is not pre-rounded
     View cols = make_view(nullptr, B, in.H, in.W, 64);
-    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 16 * ly.Cout, ly.wp_cols.p);
+    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p);
     cop.out_rows_f32 = s.cols.as<float>();
     run_conv_fwd(ctx, cop);
     launch_col2im_tanh(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
@@ -520,8 +510,8 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
       launch_im2col_bf16(ctx->L(), s.dlogit.p, Cp, B, H, W, C, s.gcols.p);
       View x = s.in_views[15];
       View G = make_view(s.gcols.p, B, H / 2, W / 2, 64);
-      ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 16 * C, nullptr);
-      wg.dW = gr + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin;
+      ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 64, nullptr);
+      wg.dW = gr + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = C;
       run_conv_wgrad(ctx, wg);
       ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p);
       run_conv_fwd(ctx, dg);
@@ -711,8 +701,8 @@ static void adam_apply(gan_adam* o, bool reduced = false) {
   ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
   launch_adam_pack(ctx->L(), ctx->dt, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
   launch_adam_ranges(ctx->L(), a, (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
-  if (n->pack_im2col_tiles > 0)     // first layer's im2col-ordered forward copy (a few thousand weights)
-    launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab_im2col.p, n->pack_im2col_nent, n->pack_im2col_tiles);
+  // the few small special layouts (first-layer im2col order, head cols operands)
+  for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), ctx->dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
   n->packed_dirty = false;
 }
 static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {

@@ -138,7 +138,9 @@ struct gan_net {
   bool packed_dirty = true;
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
   int pack_nent = 0, pack_tiles = 0;
-  DevBuf pack_tab_im2col; int pack_im2col_tiles = 0, pack_im2col_nent = 0;   // extra packed copies: first layer in im2col K order, head as cols GEMMs
+  // extra packed copies through index tables: first layer in im2col K order, head as cols GEMM operands
+  struct GatherTab { DevBuf idx; void* dst = nullptr; int n = 0; };
+  std::vector<GatherTab> gathers;
   DevBuf adam_tab, adam_ranges;   // fused Adam+pack tables (AdamPackEntry / AdamRange)
   int adam_nent = 0, adam_tiles = 0, adam_nranges = 0;
 };

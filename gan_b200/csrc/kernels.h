@@ -13,11 +13,13 @@ struct Launch {
 
 // ---- elem.cu --------------------------------------------------------------------------------
 void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* dst, int pitch, int coff);
-// fp32 NHWC image -> bf16 im2col rows of the 4x4 stride-2 'same' first layer: dst[m][t*C + c], 64 per row
+// dst[i] = master[idx[i]] (idx < 0 -> 0): small special weight layouts via a device index table
+void launch_gather_pack(Launch L, int dt, const float* master, const int* idx_dev, int n, void* dst);
+// fp32 NHWC image -> bf16 im2col rows of the 4x4 stride-2 'same' window: dst[m][t*4 + c], 64 per row (slots >= C zero)
 void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16);
-// Same rows from a bf16 image with pixel pitch `pitch` (generator-head gradient dz): G[m][t*C + c]
+// Same rows from a bf16 image with pixel pitch `pitch` (generator-head gradient dz): G[m][t*4 + c]
 void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H, int W, int C, void* dst_bf16);
-// Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*C + co] (fp32, 64 per input-grid point m) ->
+// Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*4 + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
 void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
 void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64_t P, int C, float* dst);
@@ -53,8 +55,7 @@ void launch_loss_finalize(Launch L, const float* loss_ws, LossMix mix, float* ou
 void launch_adam(Launch L, float* p, const float* g, float* m, float* v, int64_t n, const long long* t_dev, double lr,
                  double b1, double b2, float eps, float gscale);
 void launch_bump(Launch L, long long* t64, uint32_t* c32, uint32_t by);   // device-resident step / dropout-call counters
-struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc, Kr, Nr; int64_t s_tap, s_k, s_n; int im2col_c, Ktot; };   // Kc/Nc padded, Kr/Nr real
-// im2col_c > 0 (first layers, forward role): packed K index of (tap t, channel ci) = (ci/im2col_c)*64 + t*im2col_c + ci%im2col_c
+struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc, Kr, Nr; int64_t s_tap, s_k, s_n; };   // Kc/Nc padded, Kr/Nr real
 void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op);
 // All layers / roles of a net in ONE launch: 32x32 tiles, transposed through shared memory when the
 // master layout is contiguous along the packed N index.  `tab` is a device array of PackEntry.
@@ -72,7 +73,7 @@ struct AdamPackEntry {
   int KcF, KtotF, KcD, KtotD;
   long long boffF[4], boffD[4];
   int8_t invF[16], invD[16];          // master tap index -> (class << 4) | tap-in-class for each role
-  int tiles_a, tiles_b, tile_begin, im2col_c;
+  int tiles_a, tiles_b, tile_begin, pad1;
 };
 struct AdamRange { long long off; int n, pad; };
 struct AdamArgs { float* p; const float* g; float* m; float* v; const long long* t_dev; double lr, b1, b2; float eps, gscale; };
