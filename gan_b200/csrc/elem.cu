@@ -1002,3 +1002,62 @@ void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, i
   k_col2im_tanh<<<grid_for(total, 256, 16), 256, 0, L.s>>>(cols, bias, B, Hin, Win, C, out_f32);
   KLAUNCH(L);
 }
+
+__global__ void __launch_bounds__(256) k_dhead_gather(const float* __restrict__ cols, const float* __restrict__ bias, int B,
+                                                      int Hin, int Win, float* __restrict__ logits) {
+  const int Ho = Hin - 1, Wo = Win - 1;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  const float b0 = __ldg(bias);
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(q % Wo); const int64_t r = q / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    float acc = b0;
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const int i = oh + kh - 1;
+      if (i < 0 || i >= Hin) continue;
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) {
+        const int j = ow + kw - 1;
+        if (j < 0 || j >= Win) continue;
+        acc += __ldg(cols + (((int64_t)n * Hin + i) * Win + j) * 64 + (kh * 4 + kw) * 4);
+      }
+    }
+    logits[q] = acc;
+  }
+}
+void launch_dhead_gather(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, float* logits) {
+  const int64_t total = (int64_t)B * (Hin - 1) * (Win - 1);
+  k_dhead_gather<<<grid_for(total, 256, 8), 256, 0, L.s>>>(cols, bias, B, Hin, Win, logits);
+  KLAUNCH(L);
+}
+
+__global__ void __launch_bounds__(256) k_dhead_unfold(const bf16* __restrict__ dl, int pitch, int B, int Hin, int Win,
+                                                      bf16* __restrict__ dst) {
+  const int Ho = Hin - 1, Wo = Win - 1;
+  const int64_t M = (int64_t)B * Hin * Win;
+  const bf16 zero = __float2bfloat16_rn(0.f);
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(m % Win); const int64_t r = m / Win; const int i = (int)(r % Hin); const int n = (int)(r / Hin);
+    uint2 row[16];
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const int oh = i - kh + 1;
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) {
+        const int ow = j - kw + 1;
+        bf16 v = zero;
+        if (oh >= 0 && oh < Ho && ow >= 0 && ow < Wo) v = dl[(((int64_t)n * Ho + oh) * Wo + ow) * pitch];
+        __nv_bfloat162 lo; lo.x = v; lo.y = zero;
+        row[kh * 4 + kw] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), 0u);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + m * 64);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) o[t] = make_uint4(row[2 * t].x, row[2 * t].y, row[2 * t + 1].x, row[2 * t + 1].y);
+  }
+}
+void launch_dhead_unfold(Launch L, const void* dlogit_bf16, int pitch, int B, int Hin, int Win, void* dst_bf16) {
+  const int64_t M = (int64_t)B * Hin * Win;
+  k_dhead_unfold<<<grid_for(M, 256, 8), 256, 0, L.s>>>((const bf16*)dlogit_bf16, pitch, B, Hin, Win, (bf16*)dst_bf16);
+  KLAUNCH(L);
+}

@@ -134,6 +134,10 @@ static bool cols_on(const gan_ctx* ctx, const gan_net* n, const Layer& ly) {
   return n->is_gen && ly.head && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.Cout <= 4 &&
          ly.Cin % 64 == 0 && ly.wp_cols.p != nullptr;
 }
+static bool dcols_on(const gan_ctx* ctx, const gan_net* n, const Layer& ly) {
+  return !n->is_gen && ly.head && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.Cout == 1 &&
+         ly.Cin % 64 == 0 && ly.wp_cols.p != nullptr;
+}
 static ConvOp make_op_1tap(View in, int Kc, View out, int Nc, int Nr, const void* B) {
   ConvOp op; memset(&op, 0, sizeof(op));
   op.ncls = 1; op.cls[0].ntaps = 1;
@@ -308,6 +312,18 @@ static void pack_weights(gan_net* n) {
       add_gather(fc, lh.wp_cols);
       add_gather(dc, lh.wp_dcols);
     }
+    if (!n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout == 1 && lh.Cin % 64 == 0) {
+      const int Ci = lh.Cin;                        // master (kh,kw,ci,1): element tap*Ci + ci
+      std::vector<int> fc((size_t)64 * Ci, -1), dc((size_t)Ci * 64, -1);
+      for (int t = 0; t < 16; ++t)
+        for (int ci = 0; ci < Ci; ++ci) {
+          const int m = (int)(lh.w_off + (int64_t)t * Ci + ci);
+          fc[(size_t)(t * 4) * Ci + ci] = m;        // forward  B[n = tap*4][ci]
+          dc[(size_t)ci * 64 + t * 4] = m;          // dgrad    B[n = ci][k = tap*4]
+        }
+      add_gather(fc, lh.wp_cols);
+      add_gather(dc, lh.wp_dcols);
+    }
   }
   launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab.p, n->pack_nent, n->pack_tiles);
   for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), ctx->dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
@@ -341,8 +357,19 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     launch_col2im_tanh(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
     return;
   }
+  if (ly.head && dcols_on(ctx, n, ly)) {
+    // discriminator head in cols form: the 512-channel activation is read once instead of once per tap
+    s.used_cols = true;
+    s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);
+    View cols = make_view(nullptr, B, in.H, in.W, 64);
+    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p);
+    cop.out_rows_f32 = s.cols.as<float>();
+    run_conv_fwd(ctx, cop);
+    launch_dhead_gather(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, (float*)out.p);
+    return;
+  }
   if (ly.head) {
-    if (n->is_gen) s.used_cols = false;
+    s.used_cols = false;
     // generator head: bias + tanh -> fp32 image; discriminator head: bias -> fp32 logits
     View y = make_view(nullptr, B, Ho, Wo, ly.Cout_p);
     ConvOp op = make_op(ly, R_FWD, in, y, ly.wp_fwd.p);
@@ -599,6 +626,20 @@ static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool w
     if (li > 0) { s.dact[li - 1].ensure((size_t)B * in.H * in.W * in.C * es); din.p = s.dact[li - 1].p; }
     else if (want_input_grad) { s.din0.ensure((size_t)B * in.H * in.W * in.C * es); din.p = s.din0.p; }
     GradSrc src = (li == 4) ? GradSrc{s.dlogit.p, d->layers[4].Cout_p, 0} : GradSrc{s.dact[li].p, d->layers[li].Cout, 0};
+    if (li == 4 && s.used_cols) {
+      // Gd = stride-1 unfold of dlogit over the 31x31 activation grid; dW = Gd^T a; da = Gd w
+      Layer& lh = d->layers[4];
+      s.gcols.ensure((size_t)B * in.H * in.W * 64 * 2);
+      launch_dhead_unfold(ctx->L(), s.dlogit.p, lh.Cout_p, B, in.H, in.W, s.gcols.p);
+      View G = make_view(s.gcols.p, B, in.H, in.W, 64);
+      if (want_wgrad) {
+        ConvOp wg = make_op_1tap(in, lh.Cin, G, 64, 64, nullptr);
+        wg.dW = d->grads.as<float>() + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = 1;
+        run_conv_wgrad(ctx, wg);
+      }
+      run_conv_fwd(ctx, make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p));
+      continue;
+    }
     layer_backward(d, s, li, src, GradSrc{nullptr, 0, 0}, din, want_wgrad);
   }
 }

@@ -22,6 +22,12 @@ void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H,
 // Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*4 + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
 void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
+// Discriminator head (ZeroPad + Conv2D 4x4 s1, 512 -> 1, bias; base_gan.py:157-161) in cols form:
+//   cols[m'][tap*4] = a[m',:] . w[tap,:]  (GEMM over the 31x31 activation grid), then
+//   logits[n,oh,ow] = bias + sum_tap cols[(oh+kh-1, ow+kw-1)][tap*4]
+void launch_dhead_gather(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, float* logits);
+// Gd[m'=(n,i,j)][tap*4] = dlogit[n, i-kh+1, j-kw+1] (0 outside): the stride-1 unfold of the logit gradient
+void launch_dhead_unfold(Launch L, const void* dlogit_bf16, int pitch, int B, int Hin, int Win, void* dst_bf16);
 void launch_export(Launch L, int dt, const void* src, int pitch, int coff, int64_t P, int C, float* dst);
 // dst view = sum over `nslab` fp32 slabs [nslab][P][C] (deterministic split-K reduction)
 void launch_sum_slabs(Launch L, int dt, const float* slabs, int nslab, int64_t P, int C, void* dst, int pitch, int coff);
