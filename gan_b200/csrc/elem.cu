@@ -924,37 +924,36 @@ void launch_gather_pack(Launch L, int dt, const float* master, const int* idx_de
 template <typename TS, int C>
 __global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int pitch, int B, int H, int W,
                                                 bf16* __restrict__ dst) {
+  // 8 threads per output-grid point, each builds one 16-byte chunk (2 taps x 4 channel slots): a warp
+  // stores 4 consecutive 128-byte rows, fully coalesced.
   const int Ho = H / 2, Wo = W / 2;
-  const int64_t M = (int64_t)B * Ho * Wo;
-  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t total = (int64_t)B * Ho * Wo * 8;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = g >> 3; const int j = (int)(g & 7);
     const int ow = (int)(m % Wo); const int64_t r = m / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
-    uint2 row[16];
+    const int kh = j >> 1, kw0 = (j & 1) * 2;
+    const int ih = 2 * oh + kh - 1;
+    uint32_t w[4];
 #pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-      const int ih = 2 * oh + kh - 1;
+    for (int e = 0; e < 2; ++e) {
+      const int iw = 2 * ow + kw0 + e - 1;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const TS* sp = src + (((int64_t)n * H + ih) * W + iw) * pitch;
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int iw = 2 * ow + kw - 1;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-          const TS* sp = src + (((int64_t)n * H + ih) * W + iw) * pitch;
-#pragma unroll
-          for (int c = 0; c < C; ++c) v[c] = to_f(sp[c]);
-        }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-        row[kh * 4 + kw] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        for (int c = 0; c < C; ++c) v[c] = to_f(sp[c]);
       }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      w[2 * e] = *reinterpret_cast<uint32_t*>(&lo); w[2 * e + 1] = *reinterpret_cast<uint32_t*>(&hi);
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + m * 64);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = make_uint4(row[2 * j].x, row[2 * j].y, row[2 * j + 1].x, row[2 * j + 1].y);
+    *reinterpret_cast<uint4*>(dst + m * 64 + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 template <typename TS>
 static void im2col_dispatch(Launch L, const TS* src, int pitch, int B, int H, int W, int C, void* dst) {
   GAN_REQUIRE(C >= 1 && C <= 4, "im2col supports 1..4 channels per source");
   const int64_t M = (int64_t)B * (H / 2) * (W / 2);
-  const int grid = grid_for(M, 256, 16);
+  const int grid = grid_for(M * 8, 256, 16);
   bf16* d = (bf16*)dst;
   if (C == 1) k_im2col<TS, 1><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
   else if (C == 2) k_im2col<TS, 2><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);

@@ -114,9 +114,9 @@ static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
   ConvOp op; memset(&op, 0, sizeof(op));
   op.ncls = 1;
   op.cls[0].ntaps = ly.nsrc;
-  for (int t = 0; t < ly.nsrc; ++t) { op.cls[0].widx[t] = (int8_t)t; op.in_tap[t] = s.im2col[t].p; }
+  for (int t = 0; t < ly.nsrc; ++t) { op.cls[0].widx[t] = (int8_t)t; op.in_tap[t] = s.im2col[t]; }
   op.im2col_c = ly.src_c;
-  op.in = s.im2col[0].p; op.in_pitch = 64; op.in_coff = 0; op.Hin = y.H; op.Win = y.W;
+  op.in = s.im2col[0]; op.in_pitch = 64; op.in_coff = 0; op.Hin = y.H; op.Win = y.W;
   op.out = y.p; op.out_pitch = y.pitch; op.out_coff = y.coff; op.Hout = y.H; op.Wout = y.W;
   op.N = y.N; op.Hm = y.H; op.Wm = y.W; op.si = 1; op.so = 1;
   op.Kc = 64; op.Kr = 64; op.Nc = ly.Cout_p; op.Nr = ly.Cout;
@@ -146,6 +146,18 @@ static ConvOp make_op_1tap(View in, int Kc, View out, int Nc, int Nr, const void
   op.N = in.N; op.Hm = in.H; op.Wm = in.W; op.si = 1; op.so = 1;
   op.Kc = Kc; op.Kr = Kc; op.Nc = Nc; op.Nr = Nr; op.B = B;
   return op;
+}
+
+// im2col rows of a step input, computed once per step and shared by every first layer that reads it.
+static const void* cached_im2col(gan_ctx* ctx, const float* src, int B, int H, int W, int C) {
+  for (auto& e : ctx->im2col_cache)
+    if (e.src == src && e.epoch == ctx->step_epoch && e.B == B && e.H == H && e.W == W && e.C == C) return e.buf.p;
+  gan_ctx::Im2colEntry& e = ctx->im2col_cache[ctx->im2col_next];
+  ctx->im2col_next = (ctx->im2col_next + 1) % 6;
+  e.buf.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
+  launch_im2col(ctx->L(), src, B, H, W, C, e.buf.p);
+  e.src = src; e.B = B; e.H = H; e.W = W; e.C = C; e.epoch = ctx->step_epoch;
+  return e.buf.p;
 }
 
 static void out_dims(int kind, int Hin, int Win, int& Ho, int& Wo) {
@@ -475,8 +487,7 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   s.used_im2col = im2col_on(ctx, g->layers[0]);
   s.xin.ensure((size_t)B * H * W * Cp * es);
   if (s.used_im2col) {
-    s.im2col[0].ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
-    launch_im2col(ctx->L(), x_f32, B, H, W, C, s.im2col[0].p);
+    s.im2col[0] = cached_im2col(ctx, x_f32, B, H, W, C);
   } else {
     launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
   }
@@ -593,10 +604,8 @@ static void discriminator_forward(gan_net* d, int slot, const float* inp, const 
   s.in0.ensure((size_t)B * H * W * C0 * es);
   s.used_im2col = im2col_on(ctx, d->layers[0]);
   if (s.used_im2col) {                                   // one im2col K-block per source of concatenate([inp, tar])
-    const size_t ib = (size_t)B * (H / 2) * (W / 2) * 64 * 2;
-    s.im2col[0].ensure(ib);
-    launch_im2col(ctx->L(), inp, B, H, W, C, s.im2col[0].p);
-    if (tar) { s.im2col[1].ensure(ib); launch_im2col(ctx->L(), tar, B, H, W, C, s.im2col[1].p); }
+    s.im2col[0] = cached_im2col(ctx, inp, B, H, W, C);
+    if (tar) s.im2col[1] = cached_im2col(ctx, tar, B, H, W, C);
   } else {
     launch_convert(ctx->L(), ctx->dt, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
     if (tar) launch_convert(ctx->L(), ctx->dt, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
@@ -786,6 +795,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   const float* x = stage_in(ctx, 0, x_in, img_bytes);
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
   loss_ws_reset(ctx);
+  ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(d); }
 
   generator_forward(g, 0, x, B, H, W);                                   // gen_output           (:200)
@@ -841,6 +851,7 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   const float* x = stage_in(ctx, 0, x_in, img_bytes);
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
   loss_ws_reset(ctx);
+  ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy); }
 
   generator_forward(g, 0, x, B, H, W);  const float* fake_y = g->slots[0].out_f32.as<float>();     // (:220)
@@ -1213,6 +1224,7 @@ int gan_generator_forward(gan_net* g, const float* x, int batch, float* out) {
   CUDA_CHECK(cudaSetDevice(ctx->device));
   size_t bytes = (size_t)batch * g->H * g->W * g->C * 4;
   const float* xd = stage_in(ctx, 0, x, bytes);
+  ctx->step_epoch++; ctx->im2col_next = 0;
   generator_forward(g, 0, xd, batch, g->H, g->W);
   bump_calls(ctx);
   copy_out(ctx, out, g->slots[0].out_f32.as<float>(), bytes);
@@ -1228,6 +1240,7 @@ int gan_discriminator_forward(gan_net* d, const float* inp, const float* tar, in
   size_t bytes = (size_t)batch * height * width * d->C * 4;
   const float* id = stage_in(ctx, 0, inp, bytes);
   const float* td = tar ? stage_in(ctx, 1, tar, bytes) : nullptr;
+  ctx->step_epoch++; ctx->im2col_next = 0;
   discriminator_forward(d, 0, id, td, batch, height, width);
   copy_out(ctx, logits, d->slots[0].logits.as<float>(), (size_t)logits_count(d->slots[0]) * 4);
   API_END

@@ -47,6 +47,11 @@ struct gan_ctx {
   uint64_t launches = 0;
   DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk, splitk_ws;
   DevBuf stage[4];
+  // im2col rows of step inputs shared between nets (x feeds G.down1, D(real).down1 and D(fake).down1)
+  struct Im2colEntry { const void* src = nullptr; int B = 0, H = 0, W = 0, C = 0; uint64_t epoch = 0; DevBuf buf; };
+  Im2colEntry im2col_cache[6];
+  uint64_t step_epoch = 1;
+  int im2col_next = 0;
   // input prefetch (tf.data-style): H2D of the NEXT step's images on a copy stream while this step computes
   DevBuf prefetch_buf[2];
   const void* prefetch_src[2] = {nullptr, nullptr};
@@ -117,7 +122,7 @@ struct Slot {
   std::vector<DevBuf> cat, dcat, dskip;
   // discriminator
   DevBuf in0, logits, dlogit, din0;
-  DevBuf im2col[2];          // first-layer im2col rows per input source
+  const void* im2col[2] = {nullptr, nullptr};   // first-layer im2col rows per input source (ctx cache entries)
   DevBuf cols, gcols;        // generator head: cols = x*W (forward), gcols = im2col(dz) (backward)
   bool used_cols = false;
   bool used_im2col = false;
