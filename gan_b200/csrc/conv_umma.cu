@@ -625,6 +625,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         row_ok = t < p.ntaps[cls] && (kc & 3) < ic;
         dst = p.dW + (long long)(kc >> 2) * p.s_tap + (long long)(t * ic + (kc & 3)) * p.s_k + (long long)n0 * p.s_n;
       }
+      const bool vec_ok = p.s_n == 1 && p.n_slot4_c == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
       if (BN >= 32) {
@@ -632,7 +633,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
-          if (row_ok) {
+          if (row_ok && vec_ok && n0 + c + 32 <= p.Nr) {
+            // 16-byte vector reductions: a quarter of the L2 atomic transactions of the scalar form
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + j), "r"(v[j]), "r"(v[j + 1]),
+                           "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+          } else if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int nn = n0 + c + j;
