@@ -153,6 +153,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert GLOBAL_BATCH % world == 0
     B = GLOBAL_BATCH // world
+    if args.shard_of:
+        assert world == 1
+        B = GLOBAL_BATCH // args.shard_of
 
     cfg = {"img_size": SIZE, "channels": str(CH), "learning_rate": 2e-4, "beta_1": 0.5, "beta_2": 0.999,
            "lambda": LAMBDA, "generator_loss": "l1", "seed": SEED, "precision": "bf16", "device": local,
@@ -208,6 +211,8 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = GLOBAL_BATCH * args.steps / (ms_total * 1e-3)
+    if args.shard_of:
+        value = B * args.steps / (ms_total * 1e-3)
     last_losses = [float(v) for v in ctx.last_losses(4)]
 
     # ---- e2e: host (pinned) inputs, H2D + loss read-back inside the timed region ----------------
@@ -288,6 +293,8 @@ def run_ours(args):
                         "d2h_bytes_per_step": 16 * world, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches * world),
                 "roofline": roof, "families": fam, "cpu_baseline": cpu, "last_losses": last_losses}
+        if args.shard_of:
+            line["diagnostic"] = f"one rank's shard of a {args.shard_of}-rank job on one GPU, no collective; not a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -302,6 +309,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--shard-of", type=int, default=0,
+                    help="diagnostic: on ONE GPU run the per-rank shard of a W-rank job (batch = global/W, no collective); "
+                         "the line is tagged diagnostic and is not a bench value")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
