@@ -8,6 +8,7 @@
 // fp32 math with double-precision final reductions, no atomics on the value paths except the
 // tiny bias-gradient sums.
 #include "kernels.h"
+#include <cstdlib>
 
 #define NSM 148
 
@@ -467,6 +468,199 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small BatchNorm layers (the U-Net bottleneck; every layer of a small per-GPU batch): the three
+// launches of the chain above are latency-bound there, so ONE kernel does the whole layer.  A block
+// owns one 16-byte channel vector: it pulls its [P][V] slab into shared memory with cp.async (all
+// loads in flight at once), reduces in double, and applies from shared memory.
+// ---------------------------------------------------------------------------------------------
+#define BNS_THREADS 512
+#define BNS_MAX_SMEM (192 * 1024)
+
+template <int V>
+__device__ __forceinline__ void bns_block_sums(const float (&s)[V], const float (&q)[V], double (*red)[2 * V], double& S,
+                                               double& Q) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    float a = warp_sum(s[k]), b = warp_sum(q[k]);
+    if (lane == 0) { red[warp][k] = (double)a; red[warp][V + k] = (double)b; }
+  }
+  __syncthreads();
+  S = 0.0; Q = 0.0;
+  if (threadIdx.x < V) {
+#pragma unroll
+    for (int w = 0; w < BNS_THREADS / 32; ++w) { S += red[w][threadIdx.x]; Q += red[w][V + threadIdx.x]; }
+  }
+}
+
+template <typename T, bool DROP>
+__global__ void __launch_bounds__(BNS_THREADS) k_bn_small_fwd(
+    const T* __restrict__ z, uint32_t P, uint32_t HW, int C, float eps, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ inv, float* __restrict__ scale,
+    float* __restrict__ shift, float* mov_mean, float* mov_var, float momentum, int act, DropKey dk, T* __restrict__ out,
+    int out_pitch, int out_coff) {
+  constexpr int V = VecIO<T>::N;
+  extern __shared__ uint4 slab[];                       // [P] vectors of this block's V channels
+  __shared__ double red[BNS_THREADS / 32][2 * V];
+  __shared__ float par[3 * V];
+  const int c0 = blockIdx.x * V;
+  for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) cp_async16(&slab[p], z + (size_t)p * C + c0, true);
+  cp_async_commit();
+  cp_async_wait<0>();                                   // a thread only ever reads the slots it filled itself
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
+    float v[V];
+    unpack16(slab[p], v, (const T*)nullptr);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+  }
+  double S, Q;
+  bns_block_sums<V>(s, q, red, S, Q);
+  if (threadIdx.x < V) {                                // same arithmetic as k_stats_finalize
+    const int c = c0 + threadIdx.x;
+    const double n = (double)P;
+    double m = S / n;
+    double var = Q / n - m * m;
+    if (var < 0.0) var = 0.0;
+    double iv = 1.0 / sqrt(var + (double)eps);
+    float sc = (float)((double)gamma[c] * iv), sf = beta[c];
+    mean[c] = (float)m; inv[c] = (float)iv; scale[c] = sc; shift[c] = sf;
+    par[threadIdx.x] = (float)m; par[V + threadIdx.x] = sc; par[2 * V + threadIdx.x] = sf;
+    if (mov_mean != nullptr) {
+      double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+      mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * (float)m;
+      mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)unbiased;
+    }
+  }
+  __syncthreads();
+  float mu[V], sc[V], sf[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { mu[k] = par[k]; sc[k] = par[V + k]; sf[k] = par[2 * V + k]; }
+  const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
+  for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
+    float v[V];
+    unpack16(slab[p], v, (const T*)nullptr);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = fmaf(v[k] - mu[k], sc[k], sf[k]);
+    if (DROP) {
+      uint32_t smp = p / HW, e0 = (p - smp * HW) * C + c0;
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = dropout_keep(dk, call, smp, e0 + k) ? 2.f * v[k] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = act_fwd(v[k], act);
+    VecIO<T>::store(out + (size_t)p * out_pitch + out_coff + c0, v);
+  }
+}
+
+template <typename T, bool DROP>
+__global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
+    const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t P, uint32_t HW, int C, const float* __restrict__ mean,
+    const float* __restrict__ inv, const float* __restrict__ scale, const float* __restrict__ shift, int act, DropKey dk,
+    float* __restrict__ c1, float* __restrict__ c2, float* dgamma, float* dbeta, T* __restrict__ dz) {
+  constexpr int V = VecIO<T>::N;
+  extern __shared__ uint4 slab[];                       // [narr][P]
+  __shared__ double red[BNS_THREADS / 32][2 * V];
+  __shared__ float par[2 * V];
+  const int c0 = blockIdx.x * V;
+  const bool has_d2 = d2.p != nullptr;
+  for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
+    cp_async16(&slab[p], z + (size_t)p * C + c0, true);
+    cp_async16(&slab[P + p], (const T*)d1.p + (size_t)p * d1.pitch + d1.coff + c0, true);
+    if (has_d2) cp_async16(&slab[2 * P + p], (const T*)d2.p + (size_t)p * d2.pitch + d2.coff + c0, true);
+  }
+  cp_async_commit();
+  float mu[V], sc[V], sf[V], iv[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    mu[k] = __ldg(mean + c0 + k); sc[k] = __ldg(scale + c0 + k); sf[k] = __ldg(shift + c0 + k); iv[k] = __ldg(inv + c0 + k);
+  }
+  const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
+  cp_async_wait<0>();
+  // g = (d1 + d2) * act'(u) * dropout'
+  auto grad_at = [&](uint32_t p, float (&xc)[V], float (&gg)[V]) {
+    float v[V], gr[V];
+    unpack16(slab[p], v, (const T*)nullptr);
+    unpack16(slab[P + p], gr, (const T*)nullptr);
+    if (has_d2) {
+      float h[V];
+      unpack16(slab[2 * P + p], h, (const T*)nullptr);
+#pragma unroll
+      for (int k = 0; k < V; ++k) gr[k] += h[k];
+    }
+    uint32_t smp = 0, e0 = 0;
+    if (DROP) { smp = p / HW; e0 = (p - smp * HW) * C + c0; }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      xc[k] = v[k] - mu[k];
+      float uu = fmaf(xc[k], sc[k], sf[k]);
+      float g = gr[k] * act_bwd(uu, act);
+      if (DROP) g = dropout_keep(dk, call, smp, e0 + k) ? 2.f * g : 0.f;
+      gg[k] = g;
+    }
+  };
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
+    float xc[V], gg[V];
+    grad_at(p, xc, gg);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { s[k] += gg[k]; q[k] = fmaf(gg[k], xc[k], q[k]); }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) q[k] *= iv[k];
+  double S, Q;
+  bns_block_sums<V>(s, q, red, S, Q);
+  if (threadIdx.x < V) {                                // same arithmetic as k_bwd_finalize
+    const int c = c0 + threadIdx.x;
+    const double n = (double)P;
+    float a = (float)(S / n), b = (float)(Q / n);
+    c1[c] = a; c2[c] = b;
+    par[threadIdx.x] = a; par[V + threadIdx.x] = b;
+    atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
+  }
+  __syncthreads();
+  float k1[V], k2[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { k1[k] = par[k]; k2[k] = par[V + k]; }
+  for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
+    float xc[V], gg[V], o[V];
+    grad_at(p, xc, gg);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = sc[k] * (gg[k] - k1[k] - xc[k] * iv[k] * k2[k]);
+    VecIO<T>::store(dz + (size_t)p * C + c0, o);
+  }
+}
+
+static bool g_bn_small = [] { const char* e = getenv("GAN_B200_BN_SMALL"); return !(e && e[0] == '0'); }();   // dev A/B switch
+void set_bn_small(bool on) { g_bn_small = on; }
+static inline bool bn_small_fits(int G, int64_t P, int narr) {
+  return g_bn_small && G == 1 && P >= 1 && (size_t)P * narr * 16 <= (size_t)BNS_MAX_SMEM;
+}
+
+bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int HW, int C, float eps, const float* gamma,
+                         const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
+                         float* mov_var, float momentum, int act, DropKey dk, void* out, int out_pitch, int out_coff) {
+  if (!bn_small_fits(1, P, 1)) return false;
+  dispatch_dt(dt, [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    constexpr int V = VecIO<T>::N;
+    GAN_REQUIRE(C % V == 0, "channel count must be a multiple of the vector width");
+    static bool once = (set_smem(k_bn_small_fwd<T, true>, BNS_MAX_SMEM), set_smem(k_bn_small_fwd<T, false>, BNS_MAX_SMEM), true);
+    (void)once;
+    auto kern = dk.enabled ? k_bn_small_fwd<T, true> : k_bn_small_fwd<T, false>;
+    kern<<<C / V, BNS_THREADS, (size_t)P * 16, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)HW, C, eps, gamma, beta, mean, inv,
+                                                      scale, shift, mov_mean, mov_var, momentum, act, dk, (T*)out, out_pitch,
+                                                      out_coff);
+  });
+  KLAUNCH(L);
+  return true;
+}
+
 void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz) {
@@ -482,6 +676,15 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
     static bool once = (set_smem(k_bwd_reduce<T, true>, smem_max), set_smem(k_bwd_reduce<T, false>, smem_max),
                         set_smem(k_bwd_apply<T, true>, smem_max), set_smem(k_bwd_apply<T, false>, smem_max), true);
     (void)once;
+    if (norm == NORM_BATCH && bn_small_fits(G, P, narr)) {
+      static bool once2 = (set_smem(k_bn_small_bwd<T, true>, BNS_MAX_SMEM), set_smem(k_bn_small_bwd<T, false>, BNS_MAX_SMEM), true);
+      (void)once2;
+      auto kern = dk.enabled ? k_bn_small_bwd<T, true> : k_bn_small_bwd<T, false>;
+      kern<<<C / VecIO<T>::N, BNS_THREADS, (size_t)P * narr * 16, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)HW, C, mean,
+                                                                         inv, scale, shift, act, dk, c1, c2, dgamma, dbeta, (T*)dz);
+      KLAUNCH(L);
+      return;
+    }
     if (norm != NORM_NONE) {
       auto kred = dk.enabled ? k_bwd_reduce<T, true> : k_bwd_reduce<T, false>;
       kred<<<dim3(nchunk, G), 256, smem, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean, inv,
