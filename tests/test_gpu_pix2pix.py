@@ -77,7 +77,7 @@ def _grad_errors(dev, ref64, ref32):
     return out
 
 
-@pytest.mark.parametrize("batch,channels", [(1, 3), (2, 3), (2, 1)])
+@pytest.mark.parametrize("batch,channels", [(1, 3), (2, 3), (2, 1), (3, 3)])
 def test_fp32_step_matches_oracle(batch, channels):
     """fp32 path, one train step: losses <=1e-4 vs the float64 oracle; every gradient tensor within
     max(1e-4, GRAD_FACTOR x the float32 oracle's own deviation from float64) — at batch >= 2 the discriminator's
