@@ -67,9 +67,17 @@ SIGNATURES = {
                                           C.c_int, _vp]),
     "gan_ctx_last_losses": (C.c_int, [_vp, _vp, C.c_int]),
     "gan_ctx_prefetch": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    "gan_preprocess_images": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "gan_ctx_prefetch_images": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(_vp), C.POINTER(_vp)]),
     "gan_op_conv": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int]),
 }
+
+
+class ImageXform(C.Structure):
+    """``gan_image_xform`` of include/gan_b200.h."""
+    _fields_ = [(n, C.c_int) for n in ("src_h", "src_w", "col0", "cols", "pre", "mid", "crop_y", "crop_x", "flip")]
 
 
 class GanError(RuntimeError):
@@ -103,6 +111,8 @@ def ptr_of(x):
     """Address of a host numpy array or of a torch tensor (host or CUDA); NHWC float32 contiguous."""
     if x is None:
         return None
+    if hasattr(x, "ptr") and hasattr(x, "data_ptr"):   # input_pipeline.DeviceBatch: borrowed device float32 batch
+        return C.c_void_p(x.ptr)
     if hasattr(x, "data_ptr"):                 # torch.Tensor (allocation only; never used for math)
         if str(x.dtype) != "torch.float32" or not x.is_contiguous():
             raise GanError("tensors must be contiguous float32")

@@ -1263,3 +1263,45 @@ void launch_dhead_unfold(Launch L, const void* dlogit_bf16, int pitch, int B, in
   k_dhead_unfold<<<grid_for(M, 256, 8), 256, 0, L.s>>>((const bf16*)dlogit_bf16, pitch, B, Hin, Win, (bf16*)dst_bf16);
   KLAUNCH(L);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Input pipeline: split + nearest resize(s) + crop + flip + normalize as one gather over uint8
+// images (base_gan.py:45-61, pix2pix.py:34-112, cycle_gan.py:38-85).  One thread = 4 consecutive
+// output floats of one row (16-byte store); HBM-bound on the fp32 output.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nn_src(int o, int in, int out) {
+  // tf.image.resize(method=NEAREST_NEIGHBOR) of TF2: half-pixel centres, float32 arithmetic
+  const float scale = __fdiv_rn((float)in, (float)out);
+  const int i = (int)floorf(__fmul_rn((float)o + 0.5f, scale));
+  return i < in - 1 ? i : in - 1;
+}
+__global__ void __launch_bounds__(256) k_preprocess(const uint8_t* __restrict__ img, int64_t stride,
+                                                    const ImageXform* __restrict__ xf, int B, int C, int S,
+                                                    float* __restrict__ out) {
+  const int quads = S * C / 4;
+  const int64_t total = (int64_t)B * S * quads;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(t % quads); const int64_t rr = t / quads; const int i = (int)(rr % S); const int n = (int)(rr / S);
+    const ImageXform x = xf[n];
+    const int g1h = x.pre > 0 ? x.pre : x.src_h, g1w = x.pre > 0 ? x.pre : x.cols;
+    int r = x.mid > 0 ? nn_src(i + x.crop_y, g1h, x.mid) : nn_src(i, g1h, S);
+    if (x.pre > 0) r = nn_src(r, x.src_h, x.pre);
+    const uint8_t* row = img + (int64_t)n * stride + ((int64_t)r * x.src_w + x.col0) * C;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = q * 4 + e; const int j = idx / C, ch = idx - j * C;
+      const int jj = x.flip ? S - 1 - j : j;
+      int c = x.mid > 0 ? nn_src(jj + x.crop_x, g1w, x.mid) : nn_src(jj, g1w, S);
+      if (x.pre > 0) c = nn_src(c, x.cols, x.pre);
+      o[e] = __fsub_rn(__fdiv_rn((float)row[c * C + ch], 127.5f), 1.0f);
+    }
+    reinterpret_cast<float4*>(out)[t] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+void launch_preprocess(Launch L, const uint8_t* img, int64_t stride, const ImageXform* xf_dev, int B, int C, int S, float* out) {
+  GAN_REQUIRE((S * C) % 4 == 0, "out_size * channels must be a multiple of 4");
+  const int64_t total = (int64_t)B * S * (S * C / 4);
+  k_preprocess<<<grid_for(total, 256, 8), 256, 0, L.s>>>(img, stride, xf_dev, B, C, S, out);
+  KLAUNCH(L);
+}

@@ -1333,16 +1333,12 @@ int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, ga
   API_END
 }
 
+static void ensure_copy_stream(gan_ctx* ctx);
 int gan_ctx_prefetch(gan_ctx* ctx, const float* x_host, const float* y_host, int64_t bytes_each) {
   API_BEGIN
   GAN_REQUIRE(ctx && x_host && y_host && bytes_each > 0, "bad argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
-  if (!ctx->copy_stream) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->prefetch_done, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->prefetch_consumed, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventRecord(ctx->prefetch_consumed, ctx->stream));
-  }
+  ensure_copy_stream(ctx);
   // the previous batch is moved out of the prefetch buffers at the very start of the step that consumes
   // it; the new copy only has to wait for that device-to-device move, not for the whole step
   CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->prefetch_consumed, 0));
@@ -1351,6 +1347,85 @@ int gan_ctx_prefetch(gan_ctx* ctx, const float* x_host, const float* y_host, int
   CUDA_CHECK(cudaMemcpyAsync(ctx->prefetch_buf[1].p, y_host, (size_t)bytes_each, cudaMemcpyDefault, ctx->copy_stream));
   CUDA_CHECK(cudaEventRecord(ctx->prefetch_done, ctx->copy_stream));
   ctx->prefetch_src[0] = x_host; ctx->prefetch_src[1] = y_host; ctx->prefetch_bytes = (size_t)bytes_each;
+  API_END
+}
+
+static void check_xforms(const gan_image_xform* xf, int batch, int out_size, int64_t stride, int channels) {
+  for (int n = 0; n < batch; ++n) {
+    const gan_image_xform& x = xf[n];
+    GAN_REQUIRE(x.src_h >= 1 && x.src_w >= 1 && x.cols >= 1 && x.col0 >= 0 && x.col0 + x.cols <= x.src_w, "bad image window");
+    GAN_REQUIRE((int64_t)x.src_h * x.src_w * channels <= stride, "image does not fit its stride");
+    GAN_REQUIRE(x.pre >= 0 && x.mid >= 0 && (x.mid == 0 || x.mid >= out_size), "bad resize sizes");
+    GAN_REQUIRE(x.mid == 0 ? (x.crop_y == 0 && x.crop_x == 0)
+                           : (x.crop_y >= 0 && x.crop_x >= 0 && x.crop_y + out_size <= x.mid && x.crop_x + out_size <= x.mid),
+                "crop window outside the resized image");
+  }
+}
+static void ensure_copy_stream(gan_ctx* ctx) {
+  if (ctx->copy_stream) return;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->prefetch_done, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->prefetch_consumed, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(ctx->prefetch_consumed, ctx->stream));
+}
+// uint8 images (host or device) + transforms -> fp32 images at `out` (device), all on stream `st`
+static void preprocess_on(gan_ctx* ctx, cudaStream_t st, int slot, const uint8_t* images, int64_t stride, const gan_image_xform* xf,
+                          int batch, int channels, int out_size, float* out_dev, const uint8_t* reuse_src, const uint8_t* reuse_dev,
+                          const uint8_t** staged) {
+  static_assert(sizeof(gan_image_xform) == sizeof(ImageXform), "transform layouts must match");
+  const uint8_t* src = images;
+  if (images == reuse_src && reuse_dev != nullptr) src = reuse_dev;            // same host batch already on the device
+  else if (!is_device_ptr(images)) {
+    ctx->u8_stage[slot].ensure((size_t)batch * stride);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->u8_stage[slot].p, images, (size_t)batch * stride, cudaMemcpyHostToDevice, st));
+    src = (const uint8_t*)ctx->u8_stage[slot].p;
+  }
+  if (staged) *staged = src;
+  ctx->xf_dev[slot].ensure((size_t)batch * sizeof(ImageXform));
+  CUDA_CHECK(cudaMemcpyAsync(ctx->xf_dev[slot].p, xf, (size_t)batch * sizeof(ImageXform), cudaMemcpyHostToDevice, st));
+  Launch L = ctx->L(); L.s = st;
+  launch_preprocess(L, src, stride, (const ImageXform*)ctx->xf_dev[slot].p, batch, channels, out_size, out_dev);
+}
+
+int gan_preprocess_images(gan_ctx* ctx, const uint8_t* images, int64_t image_stride, int batch, int channels, int out_size,
+                          const gan_image_xform* xf, float* out) {
+  API_BEGIN
+  GAN_REQUIRE(ctx && images && xf && out, "null argument");
+  GAN_REQUIRE(batch >= 1 && channels >= 1 && channels <= 4 && out_size >= 1 && image_stride >= 1, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  check_xforms(xf, batch, out_size, image_stride, channels);
+  const size_t out_bytes = (size_t)batch * out_size * out_size * channels * 4;
+  float* dst = out;
+  if (!is_device_ptr(out)) { ctx->stage[2].ensure(out_bytes); dst = ctx->stage[2].as<float>(); }
+  // pageable xf copies are staged by the runtime before the call returns; the stream is synchronised below anyway
+  preprocess_on(ctx, ctx->stream, 0, images, image_stride, xf, batch, channels, out_size, dst, nullptr, nullptr, nullptr);
+  if (dst != out) CUDA_CHECK(cudaMemcpyAsync(out, dst, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int gan_ctx_prefetch_images(gan_ctx* ctx, const uint8_t* images_a, int64_t stride_a, const gan_image_xform* xf_a,
+                            const uint8_t* images_b, int64_t stride_b, const gan_image_xform* xf_b, int batch, int channels,
+                            int out_size, const float** a_dev, const float** b_dev) {
+  API_BEGIN
+  GAN_REQUIRE(ctx && images_a && images_b && xf_a && xf_b && a_dev && b_dev, "null argument");
+  GAN_REQUIRE(batch >= 1 && channels >= 1 && channels <= 4 && out_size >= 1 && stride_a >= 1 && stride_b >= 1, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  check_xforms(xf_a, batch, out_size, stride_a, channels);
+  check_xforms(xf_b, batch, out_size, stride_b, channels);
+  ensure_copy_stream(ctx);
+  const size_t bytes = (size_t)batch * out_size * out_size * channels * 4;
+  // the previous prefetched batch leaves these buffers at the start of the step that consumes it
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->prefetch_consumed, 0));
+  ctx->prefetch_buf[0].ensure(bytes); ctx->prefetch_buf[1].ensure(bytes);
+  const uint8_t* staged_a = nullptr;
+  preprocess_on(ctx, ctx->copy_stream, 0, images_a, stride_a, xf_a, batch, channels, out_size, ctx->prefetch_buf[0].as<float>(),
+                nullptr, nullptr, &staged_a);
+  preprocess_on(ctx, ctx->copy_stream, 1, images_b, stride_b, xf_b, batch, channels, out_size, ctx->prefetch_buf[1].as<float>(),
+                stride_a == stride_b ? images_a : nullptr, staged_a, nullptr);
+  CUDA_CHECK(cudaEventRecord(ctx->prefetch_done, ctx->copy_stream));
+  ctx->prefetch_src[0] = ctx->prefetch_buf[0].p; ctx->prefetch_src[1] = ctx->prefetch_buf[1].p; ctx->prefetch_bytes = bytes;
+  *a_dev = ctx->prefetch_buf[0].as<float>(); *b_dev = ctx->prefetch_buf[1].as<float>();
   API_END
 }
 

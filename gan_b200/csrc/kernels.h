@@ -102,3 +102,7 @@ bool umma_wgrad_supported(const ConvOp& op);
 void launch_conv_fwd_umma(Launch L, const ConvOp& op);
 void launch_conv_wgrad_umma(Launch L, const ConvOp& op);
 void umma_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
+
+// on-device input pipeline (layout identical to gan_image_xform in include/gan_b200.h)
+struct ImageXform { int src_h, src_w, col0, cols, pre, mid, crop_y, crop_x, flip; };
+void launch_preprocess(Launch L, const uint8_t* img, int64_t stride, const ImageXform* xf_dev, int B, int C, int S, float* out);

@@ -6,7 +6,7 @@ import time
 
 import numpy as np
 
-from . import _ffi
+from . import _ffi, input_pipeline
 from .base_gan import GAN, LossValue, _as_f32
 from .utils import cyclegan_losses
 
@@ -58,6 +58,32 @@ class CycleGAN(GAN):
         if not sync:
             return None
         return tuple(LossValue(v) for v in losses)
+
+    # -- input pipeline on the device (reference cycle_gan.py:38-85) --------------------------------
+    def process_images(self, images, train: bool, rng=None, out=None):
+        """``process_images_train`` / ``process_images_pred`` (cycle_gan.py:64-85) for a batch of decoded
+        uint8 images: ``load(resize=True)`` resizes to img_size first (base_gan.py:41-43), then
+        img_size+30 + random crop + random mirror when ``train`` (independent draws per image,
+        cycle_gan.py:46-62), normalize.  One gather kernel on the device."""
+        s, c = int(self.config['img_size']), int(self.config['channels'])
+        return input_pipeline.preprocess(self.ctx, input_pipeline.pack_images(list(images)), self._xforms(images, train, rng), c, s, out)
+
+    def _xforms(self, images, train, rng):
+        s = int(self.config['img_size'])
+        xfs = []
+        for im in images:
+            crop, flip = (0, 0), False
+            if train:
+                cy, cx, flip = input_pipeline.draw_jitter(rng, s)
+                crop = (cy, cx)
+            xfs.append(input_pipeline.xform(im.shape[0], im.shape[1], 0, im.shape[1], s, train, crop, flip, pre=s))
+        return xfs
+
+    def prefetch_images(self, packed_x, images_x, packed_y, images_y, train: bool, rng=None):
+        """Prefetching form: device batches (real_x, real_y) for the next ``train_step``."""
+        s, c = int(self.config['img_size']), int(self.config['channels'])
+        return input_pipeline.prefetch(self.ctx, packed_x[0], packed_x[1], self._xforms(images_x, train, rng),
+                                       packed_y[0], packed_y[1], self._xforms(images_y, train, rng), c, s)
 
     def generate_images(self, model, test_input, path_filename: str = None):
         """Forward call of reference cycle_gan.py:179-186."""

@@ -5,11 +5,12 @@ of scope."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
 
-from . import _ffi
+from . import _ffi, input_pipeline
 from .base_gan import GAN, LossValue, _as_f32
 from .utils import pix2pix_losses
 
@@ -58,6 +59,86 @@ class Pix2Pix(GAN):
         if not sync:
             return None
         return tuple(LossValue(v) for v in losses)
+
+    # -- input pipeline on the device (reference pix2pix.py:34-112) ---------------------------------
+    def split_img(self, image):
+        """Reference pix2pix.py:34-55 on a decoded (H, 2W, C) uint8 pair image (or a file name):
+        returns the two column windows as ((col0, cols), (col0, cols)) = (input, real)."""
+        if isinstance(image, str):
+            image = input_pipeline.load(image, int(self.config['channels']))
+        w = image.shape[1] // 2
+        left, right = (0, w), (w, image.shape[1] - w)
+        return (left, right) if self.config.get('input_img_orient', 'left') == 'left' else (right, left)
+
+    def process_images(self, pairs, train: bool, rng=None, out=None):
+        """``process_images_train`` / ``process_images_pred`` (pix2pix.py:92-112) for a batch of decoded
+        uint8 pair images: split, nearest resize (to img_size+30 and random crop + mirror when
+        ``train``), normalize — one gather kernel per output on the device.  Returns
+        (input_image, real_image) as (B, S, S, C) float32 arrays."""
+        s, c = int(self.config['img_size']), int(self.config['channels'])
+        xa, xb = self._pair_xforms(pairs, train, rng)
+        packed = input_pipeline.pack_images(pairs)
+        a = input_pipeline.preprocess(self.ctx, packed, xa, c, s, None if out is None else out[0])
+        b = input_pipeline.preprocess(self.ctx, packed, xb, c, s, None if out is None else out[1])
+        return a, b
+
+    def _pair_xforms(self, pairs, train, rng):
+        s = int(self.config['img_size'])
+        xa, xb = [], []
+        for im in pairs:
+            (c0a, na), (c0b, nb) = self.split_img(im)
+            crop, flip = (0, 0), False
+            if train:
+                cy, cx, flip = input_pipeline.draw_jitter(rng, s)     # one draw per PAIR (pix2pix.py:57-69,80-88)
+                crop = (cy, cx)
+            xa.append(input_pipeline.xform(im.shape[0], im.shape[1], c0a, na, s, train, crop, flip))
+            xb.append(input_pipeline.xform(im.shape[0], im.shape[1], c0b, nb, s, train, crop, flip))
+        return xa, xb
+
+    def prefetch_pairs(self, packed, pairs_meta, train: bool, rng=None):
+        """Prefetching form for the training loop: ``packed`` = (uint8 buffer, stride) from
+        ``input_pipeline.pack_images`` (pin it), ``pairs_meta`` = the decoded images (only shapes are
+        used).  Returns two device batches for the next ``train_step``."""
+        s, c = int(self.config['img_size']), int(self.config['channels'])
+        xa, xb = self._pair_xforms(pairs_meta, train, rng)
+        buf, stride = packed
+        return input_pipeline.prefetch(self.ctx, buf, stride, xa, buf, stride, xb, c, s)
+
+    def image_pipeline(self, predict: bool = False):
+        """Reference pix2pix.py:114-165: file listing, the seeded train/val/test split and batching;
+        decoding is PIL on the host, every pixel operation runs on the device.  Yields (input,
+        target) float32 batches."""
+        import random
+        cfg = self.config
+        contents = input_pipeline.list_images(cfg['data'])
+        assert contents, "No images found in data directory!"
+        full = lambda names: [os.path.join(cfg['data'], i) for i in names]   # noqa: E731
+        if predict:
+            return self._batches(full(contents), 1, False, squeeze=True), None, None
+        random.seed(cfg['seed'])
+        test = random.sample(contents, cfg['test_img'])
+        val_obs = np.ceil((len(contents) - cfg['test_img']) * cfg['validation_size'])
+        val = random.sample([i for i in contents if i not in test], int(val_obs))
+        train = [i for i in contents if i not in test and i not in val]
+        train = random.sample(train, len(train))
+        bs = cfg['batch_size']
+        return (self._batches(full(train), bs, True), self._batches(full(val), bs, False),
+                self._batches(full(test), bs, False))
+
+    def _batches(self, files, batch_size, train, squeeze=False):
+        rng = np.random.default_rng(int(self.config.get('seed', 123)) + 2)
+        c = int(self.config['channels'])
+
+        class _DS:
+            def __iter__(ds):
+                for i in range(0, len(files), batch_size):
+                    pairs = [input_pipeline.load(f, c) for f in files[i:i + batch_size]]
+                    a, b = self.process_images(pairs, train, rng)
+                    yield (a[0], b[0]) if squeeze else (a, b)
+
+            def __len__(ds):
+                return (len(files) + batch_size - 1) // batch_size
+        return _DS()
 
     def generate_images(self, model, test_input, tar=None, path_filename: str = None):
         """Forward call of reference pix2pix.py:220-228 (``model(test_input, training=True)``);

@@ -147,6 +147,38 @@ GAN_API int gan_ctx_last_losses(gan_ctx* ctx, float* out, int n);
  * computes.  The next train step recognises the same host pointers and uses the device copies. */
 GAN_API int gan_ctx_prefetch(gan_ctx* ctx, const float* x_host, const float* y_host, int64_t bytes_each);
 
+/* ---- on-device input pipeline -------------------------------------------------
+ * Replaces the per-image tf.data map of the reference: split_img (pix2pix.py:34-55), resize
+ * (base_gan.py:45-53, NEAREST_NEIGHBOR), random_crop + flip_left_right (pix2pix.py:57-90,
+ * cycle_gan.py:38-62) and normalize (base_gan.py:56-61), as ONE gather kernel over decoded uint8
+ * images.  The random draws (crop offset in [0,30], flip) are made by the caller, as the host RNG
+ * of tf.data is not part of the arithmetic.
+ *
+ * out[n,i,j,c] = src_n[row(i), col0 + col(j'), c] / 127.5 - 1,   j' = flip ? S-1-j : j
+ *   mid > 0 (train): index (i+crop_y, j'+crop_x) of the mid x mid nearest-resized image,
+ *   mid == 0 (val/test/predict): index (i, j') of the S x S nearest-resized image,
+ *   pre > 0 (cycle_gan.py load(resize=True)): the image is first nearest-resized to pre x pre.
+ * Nearest index (tf.image.resize v2, half-pixel centres, float32): min(floor((o+0.5)*in/out), in-1). */
+typedef struct {
+  int src_h, src_w;      /* decoded image size in pixels (HWC uint8, src_w * channels bytes per row) */
+  int col0, cols;        /* column window that forms the image (split_img: one half) */
+  int pre;               /* >0: first resize to pre x pre */
+  int mid;               /* >0: resize to mid x mid (img_size + 30), then crop */
+  int crop_y, crop_x;    /* crop offset inside the mid x mid image, 0 <= crop <= mid - out_size */
+  int flip;              /* mirror left-right */
+} gan_image_xform;
+/* images: host or device, image n at images + n*image_stride bytes; xf: host array [batch];
+ * out: host or device float32 (batch, out_size, out_size, channels). Runs on the context stream. */
+GAN_API int gan_preprocess_images(gan_ctx* ctx, const uint8_t* images, int64_t image_stride, int batch, int channels,
+                          int out_size, const gan_image_xform* xf, float* out);
+/* Prefetching form: uint8 copy + gather for the NEXT step's two batches run on the copy stream while
+ * the current step computes (host->device traffic is the uint8 bytes, a quarter of the float32
+ * images).  Returns two device pointers; pass exactly those as input_image/target (real_x/real_y) of
+ * the next train step.  images_b may equal images_a (Pix2Pix pairs: one copy, two column windows). */
+GAN_API int gan_ctx_prefetch_images(gan_ctx* ctx, const uint8_t* images_a, int64_t stride_a, const gan_image_xform* xf_a,
+                            const uint8_t* images_b, int64_t stride_b, const gan_image_xform* xf_b,
+                            int batch, int channels, int out_size, const float** a_dev, const float** b_dev);
+
 /* ---- single-operator entry points (parity tests of each kernel family) --------------------
  * kind: 0 = Conv2D 4x4 s2 'same', 1 = ZeroPad(1)+Conv2D 4x4 s1 'valid', 2 = Conv2DTranspose 4x4 s2 'same'
  * role: 0 = forward  (a = x (B,H,W,Cin),     b = kernel,            out = y)

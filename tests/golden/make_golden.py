@@ -62,7 +62,7 @@ def cyclegan_case(batch, channels, size=256):
     return out
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--pipeline" not in sys.argv:     # `--pipeline`: only the input-pipeline fixture
     np.savez(os.path.join(HERE, "pix2pix_b1_c3.npz"), **pix2pix_case(1, 3, 2))
     np.savez(os.path.join(HERE, "pix2pix_b2_c1.npz"), **pix2pix_case(2, 1, 1))
     np.savez(os.path.join(HERE, "cyclegan_b1_c3.npz"), **cyclegan_case(1, 3))
@@ -71,3 +71,23 @@ if __name__ == "__main__":
     w = O.philox4x32_10(c, c + 1, c + 2, c + 3, 0xDEADBEEF, 0x12345678)
     np.savez(os.path.join(HERE, "philox_kat.npz"), w0=w[0], w1=w[1], w2=w[2], w3=w[3])
     print("golden written")
+
+
+def make_pipeline_golden():
+    """Input-pipeline fixture (oracle/pipeline_oracle.py): a 37x90x3 pair and a 50x41x3 image through
+    the four per-image paths at img_size 16."""
+    from oracle import pipeline_oracle as P
+    rng = np.random.default_rng(2024)
+    pair = rng.integers(0, 256, size=(37, 90, 3), dtype=np.uint8)
+    image = rng.integers(0, 256, size=(50, 41, 3), dtype=np.uint8)
+    cy, cx, flip = 11, 29, True
+    a, b = P.pix2pix_process_train(pair, 'left', 16, cy, cx, flip)
+    pa, pb = P.pix2pix_process_pred(pair, 'right', 16)
+    np.savez_compressed(os.path.join(HERE, "pipeline_small.npz"), pair=pair, image=image, cy=cy, cx=cx, flip=flip,
+                        p2p_train_a=a, p2p_train_b=b, p2p_pred_a=pa, p2p_pred_b=pb,
+                        cyc_train=P.cyclegan_process_train(image, 16, cy, cx, flip),
+                        cyc_pred=P.cyclegan_process_pred(image, 16))
+
+
+if __name__ == "__main__" and "--pipeline" in sys.argv:
+    make_pipeline_golden()
