@@ -1269,39 +1269,47 @@ void launch_dhead_unfold(Launch L, const void* dlogit_bf16, int pitch, int B, in
 // images (base_gan.py:45-61, pix2pix.py:34-112, cycle_gan.py:38-85).  One thread = 4 consecutive
 // output floats of one row (16-byte store); HBM-bound on the fp32 output.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int nn_src(int o, int in, int out) {
-  // tf.image.resize(method=NEAREST_NEIGHBOR) of TF2: half-pixel centres, float32 arithmetic
-  const float scale = __fdiv_rn((float)in, (float)out);
+__device__ __forceinline__ int nn_src(int o, float scale, int in) {
+  // tf.image.resize(method=NEAREST_NEIGHBOR) of TF2: half-pixel centres, float32 arithmetic;
+  // scale = (float)in / (float)out, divided once per image on the host (same IEEE float32 quotient)
   const int i = (int)floorf(__fmul_rn((float)o + 0.5f, scale));
   return i < in - 1 ? i : in - 1;
 }
+// grid = (quads of a row / 256, S rows, B images): no index divisions; the 256-entry normalize table
+// (v / 127.5 - 1, correctly rounded) is built once per block.
+template <int C>
 __global__ void __launch_bounds__(256) k_preprocess(const uint8_t* __restrict__ img, int64_t stride,
-                                                    const ImageXform* __restrict__ xf, int B, int C, int S,
-                                                    float* __restrict__ out) {
+                                                    const ImageXformDev* __restrict__ xf, int S, float* __restrict__ out) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fsub_rn(__fdiv_rn((float)threadIdx.x, 127.5f), 1.0f);
+  __syncthreads();
   const int quads = S * C / 4;
-  const int64_t total = (int64_t)B * S * quads;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(t % quads); const int64_t rr = t / quads; const int i = (int)(rr % S); const int n = (int)(rr / S);
-    const ImageXform x = xf[n];
-    const int g1h = x.pre > 0 ? x.pre : x.src_h, g1w = x.pre > 0 ? x.pre : x.cols;
-    int r = x.mid > 0 ? nn_src(i + x.crop_y, g1h, x.mid) : nn_src(i, g1h, S);
-    if (x.pre > 0) r = nn_src(r, x.src_h, x.pre);
-    const uint8_t* row = img + (int64_t)n * stride + ((int64_t)r * x.src_w + x.col0) * C;
-    float o[4];
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= quads) return;
+  const int i = blockIdx.y, n = blockIdx.z;
+  const ImageXformDev x = xf[n];
+  const int g1h = x.pre > 0 ? x.pre : x.src_h, g1w = x.pre > 0 ? x.pre : x.cols;
+  int r = x.mid > 0 ? nn_src(i + x.crop_y, x.sy1, g1h) : nn_src(i, x.sy1, g1h);
+  if (x.pre > 0) r = nn_src(r, x.sy0, x.src_h);
+  const uint8_t* row = img + (int64_t)n * stride + ((int64_t)r * x.src_w + x.col0) * C;
+  float o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = q * 4 + e; const int j = idx / C, ch = idx - j * C;
-      const int jj = x.flip ? S - 1 - j : j;
-      int c = x.mid > 0 ? nn_src(jj + x.crop_x, g1w, x.mid) : nn_src(jj, g1w, S);
-      if (x.pre > 0) c = nn_src(c, x.cols, x.pre);
-      o[e] = __fsub_rn(__fdiv_rn((float)row[c * C + ch], 127.5f), 1.0f);
-    }
-    reinterpret_cast<float4*>(out)[t] = make_float4(o[0], o[1], o[2], o[3]);
+  for (int e = 0; e < 4; ++e) {
+    const int idx = q * 4 + e; const int j = idx / C, ch = idx - j * C;
+    const int jj = x.flip ? S - 1 - j : j;
+    int c = x.mid > 0 ? nn_src(jj + x.crop_x, x.sx1, g1w) : nn_src(jj, x.sx1, g1w);
+    if (x.pre > 0) c = nn_src(c, x.sx0, x.cols);
+    o[e] = lut[row[c * C + ch]];
   }
+  reinterpret_cast<float4*>(out)[((int64_t)n * S + i) * quads + q] = make_float4(o[0], o[1], o[2], o[3]);
 }
-void launch_preprocess(Launch L, const uint8_t* img, int64_t stride, const ImageXform* xf_dev, int B, int C, int S, float* out) {
+void launch_preprocess(Launch L, const uint8_t* img, int64_t stride, const ImageXformDev* xf_dev, int B, int C, int S, float* out) {
   GAN_REQUIRE((S * C) % 4 == 0, "out_size * channels must be a multiple of 4");
-  const int64_t total = (int64_t)B * S * (S * C / 4);
-  k_preprocess<<<grid_for(total, 256, 8), 256, 0, L.s>>>(img, stride, xf_dev, B, C, S, out);
+  GAN_REQUIRE(S <= 65535 && B <= 65535, "image size / batch exceed the launch grid");
+  const dim3 grid((S * C / 4 + 255) / 256, S, B);
+  if (C == 1) k_preprocess<1><<<grid, 256, 0, L.s>>>(img, stride, xf_dev, S, out);
+  else if (C == 2) k_preprocess<2><<<grid, 256, 0, L.s>>>(img, stride, xf_dev, S, out);
+  else if (C == 3) k_preprocess<3><<<grid, 256, 0, L.s>>>(img, stride, xf_dev, S, out);
+  else k_preprocess<4><<<grid, 256, 0, L.s>>>(img, stride, xf_dev, S, out);
   KLAUNCH(L);
 }

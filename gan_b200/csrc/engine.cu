@@ -1372,7 +1372,6 @@ static void ensure_copy_stream(gan_ctx* ctx) {
 static void preprocess_on(gan_ctx* ctx, cudaStream_t st, int slot, const uint8_t* images, int64_t stride, const gan_image_xform* xf,
                           int batch, int channels, int out_size, float* out_dev, const uint8_t* reuse_src, const uint8_t* reuse_dev,
                           const uint8_t** staged) {
-  static_assert(sizeof(gan_image_xform) == sizeof(ImageXform), "transform layouts must match");
   const uint8_t* src = images;
   if (images == reuse_src && reuse_dev != nullptr) src = reuse_dev;            // same host batch already on the device
   else if (!is_device_ptr(images)) {
@@ -1381,10 +1380,21 @@ static void preprocess_on(gan_ctx* ctx, cudaStream_t st, int slot, const uint8_t
     src = (const uint8_t*)ctx->u8_stage[slot].p;
   }
   if (staged) *staged = src;
-  ctx->xf_dev[slot].ensure((size_t)batch * sizeof(ImageXform));
-  CUDA_CHECK(cudaMemcpyAsync(ctx->xf_dev[slot].p, xf, (size_t)batch * sizeof(ImageXform), cudaMemcpyHostToDevice, st));
+  std::vector<ImageXformDev> dev(batch);
+  for (int n = 0; n < batch; ++n) {
+    const gan_image_xform& x = xf[n];
+    ImageXformDev& d = dev[n];
+    d.src_h = x.src_h; d.src_w = x.src_w; d.col0 = x.col0; d.cols = x.cols; d.pre = x.pre; d.mid = x.mid;
+    d.crop_y = x.crop_y; d.crop_x = x.crop_x; d.flip = x.flip;
+    const int g1h = x.pre > 0 ? x.pre : x.src_h, g1w = x.pre > 0 ? x.pre : x.cols, tgt = x.mid > 0 ? x.mid : out_size;
+    d.sy1 = (float)g1h / (float)tgt; d.sx1 = (float)g1w / (float)tgt;           // float32 quotients, as TF computes them
+    d.sy0 = x.pre > 0 ? (float)x.src_h / (float)x.pre : 1.f; d.sx0 = x.pre > 0 ? (float)x.cols / (float)x.pre : 1.f;
+  }
+  ctx->xf_dev[slot].ensure((size_t)batch * sizeof(ImageXformDev));
+  // pageable source: the runtime has staged the bytes when cudaMemcpyAsync returns
+  CUDA_CHECK(cudaMemcpyAsync(ctx->xf_dev[slot].p, dev.data(), (size_t)batch * sizeof(ImageXformDev), cudaMemcpyHostToDevice, st));
   Launch L = ctx->L(); L.s = st;
-  launch_preprocess(L, src, stride, (const ImageXform*)ctx->xf_dev[slot].p, batch, channels, out_size, out_dev);
+  launch_preprocess(L, src, stride, (const ImageXformDev*)ctx->xf_dev[slot].p, batch, channels, out_size, out_dev);
 }
 
 int gan_preprocess_images(gan_ctx* ctx, const uint8_t* images, int64_t image_stride, int batch, int channels, int out_size,
@@ -1397,10 +1407,13 @@ int gan_preprocess_images(gan_ctx* ctx, const uint8_t* images, int64_t image_str
   const size_t out_bytes = (size_t)batch * out_size * out_size * channels * 4;
   float* dst = out;
   if (!is_device_ptr(out)) { ctx->stage[2].ensure(out_bytes); dst = ctx->stage[2].as<float>(); }
-  // pageable xf copies are staged by the runtime before the call returns; the stream is synchronised below anyway
   preprocess_on(ctx, ctx->stream, 0, images, image_stride, xf, batch, channels, out_size, dst, nullptr, nullptr, nullptr);
-  if (dst != out) CUDA_CHECK(cudaMemcpyAsync(out, dst, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  // device `out`: asynchronous on the context stream (the pageable transform array has been staged by the
+  // runtime when cudaMemcpyAsync returns); host `out`: copied back and synchronised
+  if (dst != out) {
+    CUDA_CHECK(cudaMemcpyAsync(out, dst, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
   API_END
 }
 

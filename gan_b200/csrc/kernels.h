@@ -103,6 +103,11 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op);
 void launch_conv_wgrad_umma(Launch L, const ConvOp& op);
 void umma_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
 
-// on-device input pipeline (layout identical to gan_image_xform in include/gan_b200.h)
-struct ImageXform { int src_h, src_w, col0, cols, pre, mid, crop_y, crop_x, flip; };
-void launch_preprocess(Launch L, const uint8_t* img, int64_t stride, const ImageXform* xf_dev, int B, int C, int S, float* out);
+// on-device input pipeline: gan_image_xform (include/gan_b200.h) plus the float32 resize scales in/out of
+// each stage, divided once per image on the host
+struct ImageXformDev {
+  int src_h, src_w, col0, cols, pre, mid, crop_y, crop_x, flip;
+  float sy1, sx1;     // last resize (to mid, or straight to the output size): source extent / target extent
+  float sy0, sx0;     // pre > 0: src_h / pre, cols / pre
+};
+void launch_preprocess(Launch L, const uint8_t* img, int64_t stride, const ImageXformDev* xf_dev, int B, int C, int S, float* out);

@@ -54,6 +54,11 @@ def pack_images(images):
     return buf, stride
 
 
+def _addr(t):
+    """Address of a uint8 buffer: numpy array, or torch tensor (pinned host or CUDA)."""
+    return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)
+
+
 def _xf_array(xfs):
     arr = (_ffi.ImageXform * len(xfs))(*xfs)
     return arr
@@ -61,12 +66,13 @@ def _xf_array(xfs):
 
 def preprocess(ctx, packed, xfs, channels: int, img_size: int, out=None):
     """Synchronous form: ``packed`` = (uint8 buffer, stride) from ``pack_images``.  Returns
-    (B, S, S, C) float32 in [-1, 1] (numpy, or fills ``out`` which may be a CUDA torch tensor)."""
+    (B, S, S, C) float32 in [-1, 1] (numpy, or fills ``out`` which may be a CUDA torch tensor — then the
+    call only enqueues the work on the context stream)."""
     buf, stride = packed
     b = len(xfs)
     if out is None:
         out = np.empty((b, img_size, img_size, channels), dtype=np.float32)
-    _ffi.check(_ffi.lib().gan_preprocess_images(ctx.handle, C.c_void_p(buf.ctypes.data), stride, b, channels, img_size,
+    _ffi.check(_ffi.lib().gan_preprocess_images(ctx.handle, _addr(buf), stride, b, channels, img_size,
                                                 C.cast(_xf_array(xfs), C.c_void_p), _ffi.ptr_of(out)))
     return out
 
@@ -89,9 +95,8 @@ def prefetch(ctx, buf_a, stride_a, xfs_a, buf_b, stride_b, xfs_b, channels: int,
     should be pinned) until that step has been enqueued."""
     b = len(xfs_a)
     pa, pb = C.c_void_p(), C.c_void_p()
-    addr = lambda t: C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)   # noqa: E731
-    _ffi.check(_ffi.lib().gan_ctx_prefetch_images(ctx.handle, addr(buf_a), stride_a, C.cast(_xf_array(xfs_a), C.c_void_p),
-                                                  addr(buf_b), stride_b, C.cast(_xf_array(xfs_b), C.c_void_p), b, channels,
+    _ffi.check(_ffi.lib().gan_ctx_prefetch_images(ctx.handle, _addr(buf_a), stride_a, C.cast(_xf_array(xfs_a), C.c_void_p),
+                                                  _addr(buf_b), stride_b, C.cast(_xf_array(xfs_b), C.c_void_p), b, channels,
                                                   img_size, C.byref(pa), C.byref(pb)))
     shape = (b, img_size, img_size, channels)
     return DeviceBatch(pa.value, shape), DeviceBatch(pb.value, shape)
