@@ -109,6 +109,10 @@ class CycleGAN(GAN):
                     val_losses[k].append(v.numpy().tolist())
             for k in keys:
                 val_cost_functions[k].append(sum(val_losses[k]) / len(val_losses[k]))
+            # every 5 epochs and at the last one: save weights (reference cycle_gan.py:342-350)
+            last = (epoch + 1) == self.config['epochs']
+            if checkpoint_manager is not None and (((epoch + 1) % 5 == 0) or last):
+                checkpoint_manager.save()
             print(f'\nCumulative training duration at end of epoch {epoch + 1}: {(time.time() - start) / 60:.2f} min')
         return train_cost_functions, val_cost_functions
 

@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's ``Pix2Pix`` (reference pix2pix.py:26-339), hot path only:
 ``__init__``, ``generator_loss``, ``train_step``, the forward call of ``generate_images`` /
-``predict`` and the ``fit`` epoch loop.  The input pipeline, plotting and TF checkpoints are out
-of scope."""
+``predict``, the ``fit`` epoch loop with its checkpoint cadence, and the input pipeline with every
+pixel operation on the device.  Plotting and the TF tensor-bundle format are out of scope (SURVEY.md §2
+rows 8, 11, 12); ``gan_b200.checkpoint`` is the own weight/optimizer format."""
 from __future__ import annotations
 
 import ctypes as C
@@ -167,6 +168,10 @@ class Pix2Pix(GAN):
                     val_losses[k].append(v.numpy().tolist())
             for k in keys:
                 val_cost_functions[k].append(sum(val_losses[k]) / len(val_losses[k]))
+            # every 5 epochs and at the last one: save weights (reference pix2pix.py:308-317)
+            last = (epoch + 1) == self.config['epochs']
+            if checkpoint_manager is not None and (((epoch + 1) % 5 == 0) or last):
+                checkpoint_manager.save()
             print(f'\nCumulative training duration at end of epoch {epoch + 1}: {(time.time() - start) / 60:.2f} min')
         return train_cost_functions, val_cost_functions
 

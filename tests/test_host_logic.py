@@ -86,3 +86,26 @@ def test_data_parallel_host_path_world2_gloo():
         p.join(timeout=240)
         assert p.exitcode == 0
     assert q.get(timeout=10) < 1e-12
+
+
+def test_checkpoint_manager_numbering_and_rotation(tmp_path):
+    """CheckpointManager (role of tf.train.CheckpointManager, pix2pix.py:418): numbered files, newest
+    wins, old ones rotate out — host logic only, the tensor payload is stubbed."""
+    import numpy as np
+    from gan_b200 import checkpoint as ck
+
+    class Stub(ck.Checkpoint):
+        def __init__(self):
+            self._objects, self.ctx = {}, None
+
+        def _collect(self):
+            return {"x": np.arange(3)}
+    mgr = ck.CheckpointManager(Stub(), str(tmp_path), max_to_keep=1)
+    assert mgr.latest_checkpoint is None
+    p1 = mgr.save(); p2 = mgr.save()
+    assert p2.endswith("ckpt-2.npz") and ck.latest_checkpoint(str(tmp_path)) == p2
+    import os
+    assert not os.path.exists(p1) and [os.path.basename(f) for f in mgr.checkpoints] == ["ckpt-2.npz"]
+    (tmp_path / "ckpt-10.npz").write_bytes(open(p2, "rb").read())
+    assert ck.latest_checkpoint(str(tmp_path)).endswith("ckpt-10.npz")          # numeric, not lexicographic, order
+    assert not any(f.endswith(".tmp.npz") for f in os.listdir(tmp_path))
