@@ -526,7 +526,7 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
 // (activation dtype); ref/l1_coef: + l1_coef*sign(out-ref).  Accumulates into g->grads.
 // `final_call`: this is the last contribution to g->grads in the step, so finished gradient ranges
 // can be all-reduced on the communication stream while the rest of the sweep still runs (buckets in
-// backward-completion order: [up5..last], [up1..up4], [down1..down8]).
+// backward-completion order: [up5..last], [up1..up4], [down5..down8], [down1..down4]).
 static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, const float* ref_f32, float l1_coef,
                                bool want_input_grad, bool final_call = false) {
   gan_ctx* ctx = g->ctx;
@@ -592,8 +592,11 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
       din.p = s.dxin.p;
     }
     layer_backward(g, s, j - 1, a, b, din, true);
+    // down5..down8 hold 16.8 M of the down path's 19.5 M parameters: reduce them under down4..down1
+    if (final_call && ctx->world > 1 && j == 5)
+      comm_allreduce_async(ctx, gr + g->layers[4].w_off, g->layers[8].w_off - g->layers[4].w_off);
   }
-  if (final_call && ctx->world > 1) comm_allreduce_async(ctx, gr, g->layers[8].w_off);
+  if (final_call && ctx->world > 1) comm_allreduce_async(ctx, gr, g->layers[4].w_off);
 }
 
 // inp/tar: device fp32 (B,H,W,C); tar may be nullptr when target == false.
