@@ -1152,6 +1152,76 @@ __global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int 
     *reinterpret_cast<uint4*>(dst + m * 64 + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+// Generator-head backward fused with the unfold of its result (bf16 cols path): computes
+// dz = (d1 + d2 + l1_coef*sign(out - ref)) * (1 - out^2) for the 2 taps of this thread's chunk straight from the
+// fp32 output / target images and writes the slot-4 row chunk; dz itself never exists in HBM.  Every
+// image pixel appears in 4 rows; the bias gradient counts it once, in the row where it is an inner tap.
+template <int C>
+__global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict__ out, const float* __restrict__ ref,
+                                                        GradSrc d1, GradSrc d2, float l1_coef, int B, int H, int W,
+                                                        bf16* __restrict__ dst, float* dbias) {
+  __shared__ float sh[8];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)B * Ho * Wo * 8;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = g >> 3; const int j = (int)(g & 7);
+    const int ow = (int)(m % Wo); const int64_t r = m / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    const int kh = j >> 1, kw0 = (j & 1) * 2;
+    const int ih = 2 * oh + kh - 1;
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kw = kw0 + e, iw = 2 * ow + kw - 1;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const int64_t p = ((int64_t)n * H + ih) * W + iw;
+        const bool owner = (kh == 1 || kh == 2) && (kw == 1 || kw == 2);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float o = out[p * C + c];
+          float d = 0.f;
+          if (d1.p != nullptr) d += to_f(((const bf16*)d1.p)[p * d1.pitch + d1.coff + c]);
+          if (d2.p != nullptr) d += to_f(((const bf16*)d2.p)[p * d2.pitch + d2.coff + c]);
+          if (ref != nullptr) {
+            const float df = o - ref[p * C + c];
+            d += l1_coef * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+          }
+          v[c] = to_f(from_f<bf16>(d * (1.f - o * o)));
+          if (owner) bsum[c] += v[c];
+        }
+      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      w[2 * e] = *reinterpret_cast<uint32_t*>(&lo); w[2 * e + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    *reinterpret_cast<uint4*>(dst + m * 64 + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    float v = warp_sum(bsum[k]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += sh[wi];
+      atomicAdd(dbias + k, t);
+    }
+  }
+}
+void launch_ghead_bwd_cols(Launch L, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
+                           int H, int W, int C, void* gcols_bf16, float* dbias) {
+  GAN_REQUIRE(C >= 1 && C <= 4, "generator head supports up to 4 output channels");
+  const int64_t M = (int64_t)B * (H / 2) * (W / 2);
+  const int grid = grid_for(M * 8, 256, 16);
+  bf16* d = (bf16*)gcols_bf16;
+  if (C == 1) k_ghead_bwd_cols<1><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+  else if (C == 2) k_ghead_bwd_cols<2><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+  else if (C == 3) k_ghead_bwd_cols<3><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+  else k_ghead_bwd_cols<4><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+  KLAUNCH(L);
+}
+
 template <typename TS>
 static void im2col_dispatch(Launch L, const TS* src, int pitch, int B, int H, int W, int C, void* dst) {
   GAN_REQUIRE(C >= 1 && C <= 4, "im2col supports 1..4 channels per source");
@@ -1166,9 +1236,6 @@ static void im2col_dispatch(Launch L, const TS* src, int pitch, int B, int H, in
 }
 void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16) {
   im2col_dispatch<float>(L, src, C, B, H, W, C, dst_bf16);
-}
-void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H, int W, int C, void* dst_bf16) {
-  im2col_dispatch<bf16>(L, (const bf16*)src_bf16, pitch, B, H, W, C, dst_bf16);
 }
 
 // col2im of the transposed-conv head: one thread per output pixel gathers its 4 contributing taps

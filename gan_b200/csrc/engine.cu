@@ -536,9 +536,15 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   float* gr = g->grads.as<float>();
   // head
   const int Cp = g->Cp;
-  s.dlogit.ensure((size_t)B * H * W * Cp * es);
-  launch_ghead_bwd(ctx->L(), ctx->dt, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
-                   gr + g->layers[15].bias_off);
+  if (s.used_cols) {
+    s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
+    launch_ghead_bwd_cols(ctx->L(), s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, B, H, W, C, s.gcols.p,
+                          gr + g->layers[15].bias_off);
+  } else {
+    s.dlogit.ensure((size_t)B * H * W * Cp * es);
+    launch_ghead_bwd(ctx->L(), ctx->dt, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
+                     gr + g->layers[15].bias_off);
+  }
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
     s.dcat[k - 1].ensure((size_t)B * hs * ws * (UP_F[k - 1] + DOWN_F[7 - k]) * es);
@@ -549,8 +555,6 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
     Layer& lh = g->layers[15];
     if (s.used_cols) {
       // G = im2col(dz): [B*(H/2)*(W/2)][tap*C+co]; dW (kh,kw,co,ci) = G^T x; dx = G f
-      s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
-      launch_im2col_bf16(ctx->L(), s.dlogit.p, Cp, B, H, W, C, s.gcols.p);
       View x = s.in_views[15];
       View G = make_view(s.gcols.p, B, H / 2, W / 2, 64);
       ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 64, nullptr);

@@ -18,7 +18,6 @@ void launch_gather_pack(Launch L, int dt, const float* master, const int* idx_de
 // fp32 NHWC image -> bf16 im2col rows of the 4x4 stride-2 'same' window: dst[m][t*4 + c], 64 per row (slots >= C zero)
 void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16);
 // Same rows from a bf16 image with pixel pitch `pitch` (generator-head gradient dz): G[m][t*4 + c]
-void launch_im2col_bf16(Launch L, const void* src_bf16, int pitch, int B, int H, int W, int C, void* dst_bf16);
 // Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*4 + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
 void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
@@ -54,6 +53,9 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz);
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
+// head backward written directly as slot-4 rows of the cols operand (bf16 path; dz is never materialised)
+void launch_ghead_bwd_cols(Launch L, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
+                           int H, int W, int C, void* gcols_bf16, float* dbias);
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
                       float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias);
 // BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
