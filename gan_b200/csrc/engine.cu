@@ -12,6 +12,8 @@
 #include <mutex>
 #include <functional>
 #include "engine.h"
+
+uint64_t g_alloc_epoch = 0;
 #include "../../include/gan_b200.h"
 
 static thread_local std::string g_last_error;
@@ -945,6 +947,11 @@ static void run_step_graphed(gan_ctx* ctx, const std::string& key, const float* 
   }
   const float* xs = ctx->stage[0].as<float>(); const float* ys = ctx->stage[1].as<float>();
   gan_ctx::GraphEntry& ge = ctx->graph_cache[key];
+  if (ge.exec != nullptr && ge.alloc_epoch != g_alloc_epoch) {
+    // a buffer was re-allocated since the capture (a larger batch came by): the graph's pointers may be stale
+    cudaGraphExecDestroy(ge.exec);
+    ge.exec = nullptr; ge.warm = 0;
+  }
   if (ge.exec != nullptr) {
     CUDA_CHECK(cudaGraphLaunch(ge.exec, ctx->stream));
     ctx->launches += ge.launches;
@@ -965,6 +972,7 @@ static void run_step_graphed(gan_ctx* ctx, const std::string& key, const float* 
     ge.launches = ctx->launches - l0;
     ge.gen_calls = ctx->call_counter - c0;
     CUDA_CHECK(cudaGraphInstantiate(&ge.exec, graph, 0));
+    ge.alloc_epoch = g_alloc_epoch;
     cudaGraphDestroy(graph);
     CUDA_CHECK(cudaGraphLaunch(ge.exec, ctx->stream));   // the capture itself executed nothing
   }

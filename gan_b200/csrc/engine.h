@@ -5,6 +5,10 @@
 #include <map>
 #include "kernels.h"
 
+// Bumped whenever a device buffer is re-allocated: captured CUDA graphs hold raw pointers, so a graph
+// captured under an older epoch must not be replayed (run_step_graphed re-captures it).
+extern uint64_t g_alloc_epoch;
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -17,6 +21,7 @@ struct DevBuf {
   // grows only; contents are NOT preserved on growth
   void ensure(size_t n) {
     if (n <= bytes) return;
+    if (p) ++g_alloc_epoch;               // an address that a captured graph may have baked in goes away
     release();
     CUDA_CHECK(cudaMalloc(&p, n));
     CUDA_CHECK(cudaMemset(p, 0, n));
@@ -65,7 +70,7 @@ struct gan_ctx {
   DevBuf call_dev;
   uint32_t gen_calls_pending = 0;
   // captured train steps, keyed on (nets, batch, training)
-  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int warm = 0; uint32_t gen_calls = 0; };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int warm = 0; uint32_t gen_calls = 0; uint64_t alloc_epoch = 0; };
   std::map<std::string, GraphEntry> graph_cache;
   // profiling
   int profile = 0;

@@ -102,3 +102,29 @@ def test_bad_arguments_return_error_codes_and_leave_the_context_usable():
     out = m.train_step(x, y, True)
     assert all(np.isfinite(float(v)) for v in out)
     m.ctx.close()
+
+
+def test_graph_replay_survives_buffer_growth_from_a_larger_batch():
+    """Captured CUDA graphs hold raw device pointers.  A later, larger batch re-allocates the activation
+    buffers; the small-batch graph must then be re-captured, not replayed with stale addresses (the ragged
+    last batch of an epoch followed by full batches is exactly this sequence)."""
+    m, _, _ = _build("bf16")
+    m.ctx.set_graphs(True)
+    x2, y2 = _inputs(2, 3, seed=31)
+    x4, y4 = _inputs(4, 3, seed=32)
+    c0 = m.ctx.call_counter()
+    first = None
+    for _ in range(3):                                    # eager, capture, replay at batch 2
+        m.ctx.set_rng(SEED, c0)                           # (set_rng drops the graphs: each pass re-captures) 
+        first = [float(v) for v in m.train_step(x2, y2, False)]
+    a = [float(v) for v in m.train_step(x2, y2, False)]   # eager
+    b = [float(v) for v in m.train_step(x2, y2, False)]   # capture + launch
+    for _ in range(3):
+        m.train_step(x4, y4, False)                       # grows every activation buffer
+    c_before = m.ctx.call_counter()
+    got = [float(v) for v in m.train_step(x2, y2, False)]         # must not replay the stale graph
+    m.ctx.set_graphs(False)
+    m.ctx.set_rng(SEED, c_before)
+    want = [float(v) for v in m.train_step(x2, y2, False)]        # eager reference at the same dropout counter
+    assert got == want and all(np.isfinite(v) for v in a + b + first)
+    m.ctx.close()
