@@ -131,9 +131,16 @@ class Context:
         return out
 
     def close(self):
+        """Destroy the context and every net / optimizer created from it (their handles become invalid)."""
         if self._h:
             _ffi.lib().gan_ctx_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown: the library may already be gone)
+            pass
 
 
 def nccl_unique_id() -> bytes:

@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cmath>
 #include <mutex>
+#include <set>
+#include <memory>
+#include <algorithm>
 #include <functional>
 #include "engine.h"
 
@@ -990,6 +993,28 @@ extern "C" {
 const char* gan_last_error(void) { return g_last_error.c_str(); }
 int gan_version(void) { return 100; }
 
+// Ownership: a context owns the nets and optimizers created from it.  Destroying a net also destroys the
+// optimizers bound to it; destroying the context destroys everything.  Handles are tracked so that a
+// second destroy of the same handle is rejected instead of freeing twice.
+static std::mutex g_live_mu;
+static std::set<const void*> g_live;
+static void live_add(const void* h) { std::lock_guard<std::mutex> l(g_live_mu); g_live.insert(h); }
+static bool live_take(const void* h) { std::lock_guard<std::mutex> l(g_live_mu); return g_live.erase(h) == 1; }
+static void destroy_adam(gan_adam* o) {
+  if (!live_take(o)) return;
+  { auto& v = o->net->ctx->adams; v.erase(std::remove(v.begin(), v.end(), o), v.end()); }
+  delete o;
+}
+static void destroy_net(gan_net* n) {
+  if (!live_take(n)) return;
+  gan_ctx* ctx = n->ctx;
+  std::vector<gan_adam*> bound;
+  for (gan_adam* o : ctx->adams) if (o->net == n) bound.push_back(o);
+  for (gan_adam* o : bound) destroy_adam(o);
+  ctx->nets.erase(std::remove(ctx->nets.begin(), ctx->nets.end(), n), ctx->nets.end());
+  delete n;
+}
+
 int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
   API_BEGIN
   GAN_REQUIRE(out != nullptr, "null out");
@@ -1011,15 +1036,26 @@ int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
   CUDA_CHECK(cudaMallocHost((void**)&c->loss_host, 16 * 4));
   c->call_dev.ensure(16);
   umma_init();
+  live_add(c);
   *out = c;
   API_END
 }
+// Captured step graphs are keyed by the addresses of the nets/optimizers they were captured for and hold
+// their device pointers: drop them whenever one of those objects (or the seed) goes away.
+static void drop_graphs(gan_ctx* ctx) {
+  for (auto& kv : ctx->graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  ctx->graph_cache.clear();
+}
+
 int gan_ctx_destroy(gan_ctx* ctx) {
   API_BEGIN
   if (!ctx) return GAN_OK;
+  GAN_REQUIRE(live_take(ctx), "unknown or already destroyed context");
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& kv : ctx->graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  drop_graphs(ctx);
+  while (!ctx->adams.empty()) destroy_adam(ctx->adams.back());
+  while (!ctx->nets.empty()) destroy_net(ctx->nets.back());
   comm_destroy(ctx);
   cudaFreeHost(ctx->loss_host);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->prefetch_done); cudaEventDestroy(ctx->prefetch_consumed); }
@@ -1039,8 +1075,7 @@ int gan_ctx_set_rng(gan_ctx* ctx, uint64_t seed, uint32_t call_counter) {
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->seed = seed; ctx->call_counter = call_counter; ctx->gen_calls_pending = 0;
   CUDA_CHECK(cudaMemcpy(ctx->call_dev.p, &call_counter, 4, cudaMemcpyHostToDevice));
-  for (auto& kv : ctx->graph_cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  ctx->graph_cache.clear();      // the seed is baked into captured kernels
+  drop_graphs(ctx);              // the seed is baked into captured kernels
   API_END
 }
 int gan_ctx_get_call_counter(gan_ctx* ctx, uint32_t* out) { *out = ctx->call_counter; return GAN_OK; }
@@ -1092,6 +1127,7 @@ int gan_generator_create(gan_ctx* ctx, int norm_type, int height, int width, int
   GAN_REQUIRE(height >= 256 && width >= 256 && height % 256 == 0 && width % 256 == 0, "image size must be a multiple of 256");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   gan_net* n = new gan_net();
+  std::unique_ptr<gan_net> guard(n);          // freed if construction throws
   n->ctx = ctx; n->is_gen = true; n->norm = norm_type; n->H = height; n->W = width; n->C = channels; n->Cin0 = channels;
   n->Cp = pad_c(ctx, channels); n->Cin0_p = n->Cp;
   int cin = channels;
@@ -1106,6 +1142,7 @@ int gan_generator_create(gan_ctx* ctx, int norm_type, int height, int width, int
   }
   add_layer(n, "last", K_CONVT_S2, cin, channels, NORM_NONE, ACT_TANH, true, false, 0, true);   // base_gan.py:201-204
   finish_net(n);
+  guard.release(); ctx->nets.push_back(n); live_add(n);
   *out = n;
   API_END
 }
@@ -1117,6 +1154,7 @@ int gan_discriminator_create(gan_ctx* ctx, int norm_type, int channels, int targ
   GAN_REQUIRE(channels >= 1 && channels <= 4, "channels must be 1..4");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   gan_net* n = new gan_net();
+  std::unique_ptr<gan_net> guard(n);          // freed if construction throws
   n->ctx = ctx; n->is_gen = false; n->norm = norm_type; n->C = channels; n->target = target != 0;
   n->Cin0 = target ? 2 * channels : channels;
   n->Cp = pad_c(ctx, channels); n->Cin0_p = pad_c(ctx, n->Cin0);
@@ -1127,13 +1165,18 @@ int gan_discriminator_create(gan_ctx* ctx, int norm_type, int channels, int targ
   n->tensors[n->tensors.size() - 2].name = "norm.gamma"; n->tensors[n->tensors.size() - 1].name = "norm.beta";
   add_layer(n, "last", K_CONV_S1P, 512, 1, NORM_NONE, ACT_NONE, true, false, 0, true);           // :157-161
   finish_net(n);
+  guard.release(); ctx->nets.push_back(n); live_add(n);
   *out = n;
   API_END
 }
 
 int gan_net_destroy(gan_net* net) {
   API_BEGIN
-  if (net) { cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); delete net; }
+  if (net) {
+    { std::lock_guard<std::mutex> l(g_live_mu); GAN_REQUIRE(g_live.count(net) == 1, "unknown or already destroyed net"); }
+    cudaSetDevice(net->ctx->device); cudaStreamSynchronize(net->ctx->stream); drop_graphs(net->ctx);
+    destroy_net(net);
+  }
   API_END
 }
 
@@ -1271,15 +1314,21 @@ int gan_adam_create(gan_net* net, double lr, double beta1, double beta2, double 
   GAN_REQUIRE(net && out, "null argument");
   CUDA_CHECK(cudaSetDevice(net->ctx->device));
   gan_adam* o = new gan_adam();
+  std::unique_ptr<gan_adam> guard(o);
   o->net = net; o->lr = lr; o->b1 = beta1; o->b2 = beta2; o->eps = eps;
   o->m.ensure((size_t)(net->nparams + 4) * 4); o->v.ensure((size_t)(net->nparams + 4) * 4);
   o->t_dev.ensure(16);
+  guard.release(); net->ctx->adams.push_back(o); live_add(o);
   *out = o;
   API_END
 }
 int gan_adam_destroy(gan_adam* opt) {
   API_BEGIN
-  if (opt) { cudaSetDevice(opt->net->ctx->device); cudaStreamSynchronize(opt->net->ctx->stream); delete opt; }
+  if (opt) {
+    { std::lock_guard<std::mutex> l(g_live_mu); GAN_REQUIRE(g_live.count(opt) == 1, "unknown or already destroyed optimizer"); }
+    cudaSetDevice(opt->net->ctx->device); cudaStreamSynchronize(opt->net->ctx->stream); drop_graphs(opt->net->ctx);
+    destroy_adam(opt);
+  }
   API_END
 }
 int gan_adam_get_step(gan_adam* opt, int64_t* t) { *t = opt->t; return GAN_OK; }

@@ -55,6 +55,9 @@ struct gan_ctx {
   // im2col rows of step inputs shared between nets (x feeds G.down1, D(real).down1 and D(fake).down1)
   struct Im2colEntry { const void* src = nullptr; int B = 0, H = 0, W = 0, C = 0; uint64_t epoch = 0; DevBuf buf; };
   Im2colEntry im2col_cache[6];
+  // every net / optimizer created from this context (destroyed with it)
+  std::vector<struct gan_net*> nets;
+  std::vector<struct gan_adam*> adams;
   uint64_t step_epoch = 1;
   int im2col_next = 0;
   // input prefetch (tf.data-style): H2D of the NEXT step's images on a copy stream while this step computes

@@ -54,6 +54,9 @@ GAN_API int gan_version(void);
 /* ---- context ------------------------------------------------------------------------------ */
 /* Replaces the implicit TF runtime/device placement (base_gan.py:16-19). */
 GAN_API int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out);
+/* Ownership: a context owns every net and optimizer created from it and destroys them with itself;
+ * gan_net_destroy also destroys the optimizers bound to that net.  Destroying a handle twice (or a handle
+ * whose owner is gone) returns GAN_ERR_INVALID instead of freeing twice. */
 GAN_API int gan_ctx_destroy(gan_ctx* ctx);
 GAN_API int gan_ctx_sync(gan_ctx* ctx);
 /* Dropout(0.5) is always active in the reference (base_gan.py:118, training=True everywhere);

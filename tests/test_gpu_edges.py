@@ -128,3 +128,21 @@ def test_graph_replay_survives_buffer_growth_from_a_larger_batch():
     want = [float(v) for v in m.train_step(x2, y2, False)]        # eager reference at the same dropout counter
     assert got == want and all(np.isfinite(v) for v in a + b + first)
     m.ctx.close()
+
+
+def test_handle_ownership_and_double_destroy():
+    """The context owns its nets and optimizers (include/gan_b200.h): destroying a net takes its optimizer
+    with it, a second destroy of any handle is an error code, closing the context frees the rest."""
+    from gan_b200 import _ffi
+    m, _, _ = _build("bf16")
+    lib = _ffi.lib()
+    x, y = _inputs(1, 3)
+    m.train_step(x, y, True)                              # binds both optimizers
+    g, g_opt = m.generator.handle, m.generator_optimizer._h
+    d_opt = m.discriminator_optimizer._h
+    assert lib.gan_adam_destroy(d_opt) == 0 and lib.gan_adam_destroy(d_opt) == -1
+    assert lib.gan_net_destroy(g) == 0                    # takes g_opt with it
+    assert lib.gan_adam_destroy(g_opt) == -1 and lib.gan_net_destroy(g) == -1
+    h = m.ctx.handle
+    m.ctx.close()                                         # frees the discriminator
+    assert lib.gan_ctx_destroy(h) == -1
