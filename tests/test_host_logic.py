@@ -109,3 +109,32 @@ def test_checkpoint_manager_numbering_and_rotation(tmp_path):
     (tmp_path / "ckpt-10.npz").write_bytes(open(p2, "rb").read())
     assert ck.latest_checkpoint(str(tmp_path)).endswith("ckpt-10.npz")          # numeric, not lexicographic, order
     assert not any(f.endswith(".tmp.npz") for f in os.listdir(tmp_path))
+
+
+def test_input_pipeline_host_side_descriptions():
+    """Host half of the device input pipeline (gan_b200/input_pipeline.py): the random draws of
+    random_jitter (pix2pix.py:66-90) stay in range, transforms describe train vs prediction paths the way
+    the reference applies them, ragged images pack into one strided buffer.  No device work."""
+    import numpy as np
+    from gan_b200 import input_pipeline as ip
+
+    rng = np.random.default_rng(0)
+    draws = [ip.draw_jitter(rng, 256) for _ in range(2000)]
+    assert all(0 <= cy <= 30 and 0 <= cx <= 30 for cy, cx, _ in draws)
+    assert {cy for cy, _, _ in draws} == set(range(31)) and {cx for _, cx, _ in draws} == set(range(31))
+    flips = sum(f for _, _, f in draws)
+    assert 850 < flips < 1150                                   # mirror with probability 1/2
+
+    t = ip.xform(300, 500, 250, 250, 256, True, (7, 9), True)
+    assert (t.src_h, t.src_w, t.col0, t.cols, t.pre, t.mid, t.crop_y, t.crop_x, t.flip) == (300, 500, 250, 250, 0, 286, 7, 9, 1)
+    p = ip.xform(300, 500, 0, 250, 256, False, (7, 9), True)    # prediction path ignores the draws
+    assert (p.mid, p.crop_y, p.crop_x, p.flip) == (0, 0, 0, 0)
+    c = ip.xform(199, 301, 0, 301, 256, True, (0, 30), False, pre=256)   # CycleGAN load(resize=True)
+    assert (c.pre, c.mid, c.crop_x) == (256, 286, 30)
+
+    ims = [np.full((4, 6, 3), 1, np.uint8), np.full((5, 8, 3), 2, np.uint8)]
+    buf, stride = ip.pack_images(ims)
+    assert stride == 120 and buf.shape == (2, 120) and buf[0, :72].min() == 1 and buf[0, 72:].max() == 0 and buf[1].min() == 2
+    import pytest
+    with pytest.raises(ValueError):
+        ip.pack_images([np.zeros((4, 4, 3), np.float32)])
