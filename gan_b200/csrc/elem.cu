@@ -496,15 +496,21 @@ __device__ __forceinline__ void bns_block_sums(const float (&s)[V], const float 
 
 template <typename T, bool DROP>
 __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_fwd(
-    const T* __restrict__ z, uint32_t P, uint32_t HW, int C, float eps, const float* __restrict__ gamma,
+    const T* __restrict__ z_all, uint32_t P, uint32_t HW, int C, float eps, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ inv, float* __restrict__ scale,
-    float* __restrict__ shift, float* mov_mean, float* mov_var, float momentum, int act, DropKey dk, T* __restrict__ out,
+    float* __restrict__ shift, float* mov_mean, float* mov_var, float momentum, int act, DropKey dk, T* __restrict__ out_all,
     int out_pitch, int out_coff) {
+  // P = pixels of one normalisation group; blockIdx.y = group (BatchNorm: one group = the whole batch;
+  // InstanceNorm: one group per sample)
   constexpr int V = VecIO<T>::N;
   extern __shared__ uint4 slab[];                       // [P] vectors of this block's V channels
   __shared__ double red[BNS_THREADS / 32][2 * V];
   __shared__ float par[3 * V];
   const int c0 = blockIdx.x * V;
+  const uint32_t g = blockIdx.y;
+  const size_t gi = (size_t)g * C;                      // row of this group in the statistics arrays
+  const T* z = z_all + (size_t)g * P * C;
+  T* out = out_all + (size_t)g * P * out_pitch;
   for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) cp_async16(&slab[p], z + (size_t)p * C + c0, true);
   cp_async_commit();
   cp_async_wait<0>();                                   // a thread only ever reads the slots it filled itself
@@ -527,7 +533,7 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_fwd(
     if (var < 0.0) var = 0.0;
     double iv = 1.0 / sqrt(var + (double)eps);
     float sc = (float)((double)gamma[c] * iv), sf = beta[c];
-    mean[c] = (float)m; inv[c] = (float)iv; scale[c] = sc; shift[c] = sf;
+    mean[gi + c] = (float)m; inv[gi + c] = (float)iv; scale[gi + c] = sc; shift[gi + c] = sf;
     par[threadIdx.x] = (float)m; par[V + threadIdx.x] = sc; par[2 * V + threadIdx.x] = sf;
     if (mov_mean != nullptr) {
       double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
@@ -546,7 +552,8 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_fwd(
 #pragma unroll
     for (int k = 0; k < V; ++k) v[k] = fmaf(v[k] - mu[k], sc[k], sf[k]);
     if (DROP) {
-      uint32_t smp = p / HW, e0 = (p - smp * HW) * C + c0;
+      const uint32_t pgl = g * P + p;
+      uint32_t smp = pgl / HW, e0 = (pgl - smp * HW) * C + c0;
 #pragma unroll
       for (int k = 0; k < V; ++k) v[k] = dropout_keep(dk, call, smp, e0 + k) ? 2.f * v[k] : 0.f;
     }
@@ -558,25 +565,31 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_fwd(
 
 template <typename T, bool DROP>
 __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
-    const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t P, uint32_t HW, int C, const float* __restrict__ mean,
+    const T* __restrict__ z_all, GradSrc d1, GradSrc d2, uint32_t P, uint32_t HW, int C, const float* __restrict__ mean,
     const float* __restrict__ inv, const float* __restrict__ scale, const float* __restrict__ shift, int act, DropKey dk,
-    float* __restrict__ c1, float* __restrict__ c2, float* dgamma, float* dbeta, T* __restrict__ dz) {
+    float* __restrict__ c1, float* __restrict__ c2, float* dgamma, float* dbeta, T* __restrict__ dz_all) {
   constexpr int V = VecIO<T>::N;
   extern __shared__ uint4 slab[];                       // [narr][P]
   __shared__ double red[BNS_THREADS / 32][2 * V];
   __shared__ float par[2 * V];
   const int c0 = blockIdx.x * V;
+  const uint32_t g = blockIdx.y;                        // normalisation group (see k_bn_small_fwd)
+  const size_t gi = (size_t)g * C;
+  const size_t p_base = (size_t)g * P;
+  const T* z = z_all + p_base * C;
+  T* dz = dz_all + p_base * C;
   const bool has_d2 = d2.p != nullptr;
   for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
     cp_async16(&slab[p], z + (size_t)p * C + c0, true);
-    cp_async16(&slab[P + p], (const T*)d1.p + (size_t)p * d1.pitch + d1.coff + c0, true);
-    if (has_d2) cp_async16(&slab[2 * P + p], (const T*)d2.p + (size_t)p * d2.pitch + d2.coff + c0, true);
+    cp_async16(&slab[P + p], (const T*)d1.p + (p_base + p) * d1.pitch + d1.coff + c0, true);
+    if (has_d2) cp_async16(&slab[2 * P + p], (const T*)d2.p + (p_base + p) * d2.pitch + d2.coff + c0, true);
   }
   cp_async_commit();
   float mu[V], sc[V], sf[V], iv[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    mu[k] = __ldg(mean + c0 + k); sc[k] = __ldg(scale + c0 + k); sf[k] = __ldg(shift + c0 + k); iv[k] = __ldg(inv + c0 + k);
+    mu[k] = __ldg(mean + gi + c0 + k); sc[k] = __ldg(scale + gi + c0 + k); sf[k] = __ldg(shift + gi + c0 + k);
+    iv[k] = __ldg(inv + gi + c0 + k);
   }
   const uint32_t call = DROP ? __ldg(dk.call_dev) + dk.call_off : 0u;
   cp_async_wait<0>();
@@ -592,7 +605,7 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
       for (int k = 0; k < V; ++k) gr[k] += h[k];
     }
     uint32_t smp = 0, e0 = 0;
-    if (DROP) { smp = p / HW; e0 = (p - smp * HW) * C + c0; }
+    if (DROP) { const uint32_t pgl = g * P + p; smp = pgl / HW; e0 = (pgl - smp * HW) * C + c0; }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       xc[k] = v[k] - mu[k];
@@ -619,7 +632,7 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
     const int c = c0 + threadIdx.x;
     const double n = (double)P;
     float a = (float)(S / n), b = (float)(Q / n);
-    c1[c] = a; c2[c] = b;
+    c1[gi + c] = a; c2[gi + c] = b;
     par[threadIdx.x] = a; par[V + threadIdx.x] = b;
     atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
   }
@@ -638,14 +651,15 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
 
 static bool g_bn_small = [] { const char* e = getenv("GAN_B200_BN_SMALL"); return !(e && e[0] == '0'); }();   // dev A/B switch
 void set_bn_small(bool on) { g_bn_small = on; }
-static inline bool bn_small_fits(int G, int64_t P, int narr) {
-  return g_bn_small && G == 1 && P >= 1 && (size_t)P * narr * 16 <= (size_t)BNS_MAX_SMEM;
+static inline bool bn_small_fits(int G, int64_t P, int narr) {     // P = all pixels, G groups of P / G
+  return g_bn_small && G >= 1 && G <= 65535 && P >= G && (size_t)(P / G) * narr * 16 <= (size_t)BNS_MAX_SMEM;
 }
 
-bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int HW, int C, float eps, const float* gamma,
+bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int HW, int C, float eps, const float* gamma,
                          const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
                          float* mov_var, float momentum, int act, DropKey dk, void* out, int out_pitch, int out_coff) {
-  if (!bn_small_fits(1, P, 1)) return false;
+  if (!bn_small_fits(G, P, 1)) return false;
+  const int64_t Pg = P / G;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     constexpr int V = VecIO<T>::N;
@@ -653,7 +667,7 @@ bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int HW, int
     static bool once = (set_smem(k_bn_small_fwd<T, true>, BNS_MAX_SMEM), set_smem(k_bn_small_fwd<T, false>, BNS_MAX_SMEM), true);
     (void)once;
     auto kern = dk.enabled ? k_bn_small_fwd<T, true> : k_bn_small_fwd<T, false>;
-    kern<<<C / V, BNS_THREADS, (size_t)P * 16, L.s>>>((const T*)z, (uint32_t)P, (uint32_t)HW, C, eps, gamma, beta, mean, inv,
+    kern<<<dim3(C / V, G), BNS_THREADS, (size_t)Pg * 16, L.s>>>((const T*)z, (uint32_t)Pg, (uint32_t)HW, C, eps, gamma, beta, mean, inv,
                                                       scale, shift, mov_mean, mov_var, momentum, act, dk, (T*)out, out_pitch,
                                                       out_coff);
   });
@@ -676,11 +690,11 @@ void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, in
     static bool once = (set_smem(k_bwd_reduce<T, true>, smem_max), set_smem(k_bwd_reduce<T, false>, smem_max),
                         set_smem(k_bwd_apply<T, true>, smem_max), set_smem(k_bwd_apply<T, false>, smem_max), true);
     (void)once;
-    if (norm == NORM_BATCH && bn_small_fits(G, P, narr)) {
+    if (norm != NORM_NONE && bn_small_fits(G, P, narr)) {
       static bool once2 = (set_smem(k_bn_small_bwd<T, true>, BNS_MAX_SMEM), set_smem(k_bn_small_bwd<T, false>, BNS_MAX_SMEM), true);
       (void)once2;
       auto kern = dk.enabled ? k_bn_small_bwd<T, true> : k_bn_small_bwd<T, false>;
-      kern<<<C / VecIO<T>::N, BNS_THREADS, (size_t)P * narr * 16, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)HW, C, mean,
+      kern<<<dim3(C / VecIO<T>::N, G), BNS_THREADS, (size_t)Pg * narr * 16, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, mean,
                                                                          inv, scale, shift, act, dk, c1, c2, dgamma, dbeta, (T*)dz);
       KLAUNCH(L);
       return;

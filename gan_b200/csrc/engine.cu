@@ -416,8 +416,8 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
   float* pr = n->params.as<float>();
   float* mm = (ly.mov_off >= 0) ? n->mov.as<float>() + ly.mov_off : nullptr;
-  if (ly.norm == NORM_BATCH &&
-      launch_bn_small_fwd(ctx->L(), ctx->dt, z.p, P, Ho * Wo, ly.Cout, BN_EPS, pr + ly.g_off, pr + ly.b_off, st, st + gc,
+  if (launch_bn_small_fwd(ctx->L(), ctx->dt, z.p, P, G, Ho * Wo, ly.Cout, ly.norm == NORM_BATCH ? BN_EPS : IN_EPS,
+                          pr + ly.g_off, pr + ly.b_off, st, st + gc,
                           st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM, ly.act, dk, out.p,
                           out.pitch, out.coff))
     return;

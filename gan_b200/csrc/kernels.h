@@ -39,8 +39,9 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
                        const float* gamma, const float* beta, float* mean, float* inv, float* scale,
                        float* shift, float* mov_mean, float* mov_var, float momentum);
 // out = act(dropout(z*scale+shift)); scale == nullptr => identity affine (no-norm layers).
-// One-kernel BatchNorm layer for small tensors; returns false (nothing launched) when the slab does not fit.
-bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int HW, int C, float eps, const float* gamma,
+// One-kernel BatchNorm / InstanceNorm layer (G groups of P/G pixels) for small groups; returns false (nothing
+// launched) when a group's slab does not fit in shared memory.
+bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int HW, int C, float eps, const float* gamma,
                          const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
                          float* mov_var, float momentum, int act, DropKey dk, void* out, int out_pitch, int out_coff);
 void set_bn_small(bool on);
