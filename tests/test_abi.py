@@ -44,3 +44,16 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_image_xform_struct_matches_the_header():
+    """ctypes mirror of gan_image_xform: same field names, order and size as include/gan_b200.h."""
+    import re
+    import ctypes as C
+    from gan_b200 import _ffi
+    hdr = open(os.path.join(ROOT, "include", "gan_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} gan_image_xform;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r"int ([^;]+);", body) for n in decl.split(",")]
+    assert names == [f[0] for f in _ffi.ImageXform._fields_]
+    assert C.sizeof(_ffi.ImageXform) == 4 * len(names)
