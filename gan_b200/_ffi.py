@@ -62,6 +62,7 @@ SIGNATURES = {
     "gan_adam_set_step": (C.c_int, [_vp, C.c_int64]),
     "gan_adam_get_state": (C.c_int, [_vp, C.c_int, _vp]),
     "gan_adam_set_state": (C.c_int, [_vp, C.c_int, _vp]),
+    "gan_adam_set_hyper": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "gan_pix2pix_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]),
     "gan_cyclegan_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float,
                                           C.c_int, _vp]),

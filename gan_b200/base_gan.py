@@ -39,6 +39,7 @@ class Context:
 
     def __init__(self, device: int = 0, precision: str = "bf16", seed: int = 123):
         self.precision = precision
+        self.seed = int(seed)
         self._h = C.c_void_p()
         _ffi.check(_ffi.lib().gan_ctx_create(int(device), _PRECISIONS[precision], C.c_uint64(seed), C.byref(self._h)))
         self.device = device
@@ -55,6 +56,7 @@ class Context:
         _ffi.check(_ffi.lib().gan_ctx_set_dropout(self._h, int(bool(enabled))))
 
     def set_rng(self, seed: int, call_counter: int = 0):
+        self.seed = int(seed)
         _ffi.check(_ffi.lib().gan_ctx_set_rng(self._h, C.c_uint64(seed), C.c_uint32(call_counter)))
 
     def call_counter(self) -> int:
@@ -278,6 +280,7 @@ class Adam:
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
         self._h = None
         self._model = None
+        self._deferred = None      # checkpoint state restored before the slots existed (applied by bind)
 
     def bind(self, model: Model):
         if self._h is None:
@@ -285,14 +288,37 @@ class Adam:
             _ffi.check(_ffi.lib().gan_adam_create(model.handle, self.learning_rate, self.beta_1, self.beta_2,
                                                   self.epsilon, C.byref(h)))
             self._h, self._model = h, model
+            if self._deferred is not None:
+                state, self._deferred = self._deferred, None
+                self._apply_state(state)
         elif self._model is not model:
             raise ValueError("optimizer already bound to another model")
         return self._h
 
+    def set_hyper(self, learning_rate, beta_1, beta_2, epsilon):
+        """Replace the hyper-parameters (a restored checkpoint carries its own, as a TF checkpoint does)."""
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        if self._h is not None:
+            _ffi.check(_ffi.lib().gan_adam_set_hyper(self._h, learning_rate, beta_1, beta_2, epsilon))
+
+    def _apply_state(self, state):
+        """state = {'iterations': t, 'slots': {'m/<var>': array, 'v/<var>': array}}; missing slots stay zero."""
+        for i, which in enumerate(("m", "v")):
+            parts = []
+            for var in self._model.trainable_variables:
+                a = state["slots"].get(f"{which}/{var.name}")
+                if a is not None and a.shape != var.shape:
+                    raise ValueError(f"{which}/{var.name}: shape {a.shape} != {var.shape}")
+                parts.append(np.zeros(int(np.prod(var.shape)), np.float32) if a is None
+                             else np.asarray(a, np.float32).reshape(-1))
+            flat = np.ascontiguousarray(np.concatenate(parts))
+            _ffi.check(_ffi.lib().gan_adam_set_state(self._h, i, _ffi.ptr_of(flat)))
+        _ffi.check(_ffi.lib().gan_adam_set_step(self._h, C.c_int64(int(state["iterations"]))))
+
     @property
     def iterations(self) -> int:
         if self._h is None:
-            return 0
+            return int(self._deferred["iterations"]) if self._deferred is not None else 0
         t = C.c_int64()
         _ffi.check(_ffi.lib().gan_adam_get_step(self._h, C.byref(t)))
         return t.value

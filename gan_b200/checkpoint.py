@@ -85,8 +85,12 @@ class Checkpoint:
 
     def write(self, file_prefix: str) -> str:
         path = file_prefix + ".npz"
-        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        tmp = path + ".tmp.npz"
+        if self.ctx is not None and getattr(self.ctx, "rank", 0) != 0:
+            return path                                     # data parallel: replicas are identical, rank 0 writes
+        d = os.path.dirname(os.path.abspath(path))
+        os.makedirs(d, exist_ok=True)
+        # np.savez appends ".npz" to names without it; the leading dot keeps the glob "ckpt-*.npz" from matching
+        tmp = os.path.join(d, f".{os.path.basename(file_prefix)}.{os.getpid()}.tmp.npz")
         np.savez(tmp, **self._collect())
         os.replace(tmp, path)                               # a crash never leaves a half-written checkpoint
         return path
@@ -94,10 +98,13 @@ class Checkpoint:
     save = write
 
     # -- restore ---------------------------------------------------------------------------------
-    def restore(self, path: str, models_for_optimizers: dict | None = None) -> _Status:
+    def restore(self, path: str, models_for_optimizers: dict | None = None, restore_rng: bool = True) -> _Status:
         """Load ``path`` (as returned by ``write`` / ``latest_checkpoint``).  Adam slots need the optimizer
         to be bound to its model: pass ``{'generator_optimizer': model, ...}`` or bind beforehand
-        (``train_step`` binds at first use).  Keys present on only one side are reported, not fatal."""
+        (``train_step`` binds at first use); an optimizer that is still unbound keeps its slots and applies them
+        when it is bound (TF's deferred restoration), which is what the reference's predict flow relies on
+        (pix2pix.py:400-411).  Saved hyper-parameters replace the optimizer's.  The dropout call counter of the
+        saved run is restored unless ``restore_rng=False``.  Keys present on only one side are reported, not fatal."""
         if path is None:
             raise ValueError("no checkpoint to restore (latest_checkpoint returned None)")
         data = np.load(path)
@@ -116,32 +123,37 @@ class Checkpoint:
                     missing.append(f"{name}/iterations")
                     continue
                 model = (models_for_optimizers or {}).get(name, obj._model)
-                if model is None:
-                    raise ValueError(f"{name}: bind the optimizer to its model (or pass models_for_optimizers) before restoring")
-                h = obj.bind(model)
+                # tf.train.Checkpoint restores the saved hyper-parameters silently (they are checkpointed variables)
                 lr, b1, b2, eps = (float(x) for x in data[f"{name}/hyper"])
-                if (lr, b1, b2, eps) != (obj.learning_rate, obj.beta_1, obj.beta_2, obj.epsilon):
-                    raise ValueError(f"{name}: checkpoint hyper-parameters {(lr, b1, b2, eps)} differ from the optimizer's")
+                obj.set_hyper(lr, b1, b2, eps)
                 used.update({f"{name}/hyper", f"{name}/iterations"})
-                slots = {}
+                slot_keys = {k for k in keys if k.startswith(f"{name}/m/") or k.startswith(f"{name}/v/")}
+                if model is None:
+                    # The reference restores into a fresh model before any train_step (pix2pix.py:400-411): the
+                    # optimizer has no slots yet.  As TF does (deferred restoration), keep the values and apply
+                    # them when the optimizer is bound; until then they count as consumed-later, not as errors.
+                    obj._deferred = {"iterations": int(data[f"{name}/iterations"]),
+                                     "slots": {k[len(name) + 1:]: np.asarray(data[k], np.float32) for k in slot_keys}}
+                    used.update(slot_keys)
+                    continue
+                obj.bind(model)
+                state = {"iterations": int(data[f"{name}/iterations"]), "slots": {}}
                 for which in ("m", "v"):
-                    parts = []
                     for var in model.trainable_variables:
                         k = f"{name}/{which}/{var.name}"
                         if k in keys:
-                            a = data[k]
-                            if a.shape != var.shape:
-                                raise ValueError(f"{k}: shape {a.shape} != {var.shape}")
-                            parts.append(np.asarray(a, np.float32).reshape(-1)); used.add(k)
+                            if data[k].shape != var.shape:
+                                raise ValueError(f"{k}: shape {data[k].shape} != {var.shape}")
+                            state["slots"][f"{which}/{var.name}"] = np.asarray(data[k], np.float32); used.add(k)
                         else:
-                            missing.append(k); parts.append(np.zeros(int(np.prod(var.shape)), np.float32))
-                    slots[which] = np.ascontiguousarray(np.concatenate(parts))
-                _ffi.check(_ffi.lib().gan_adam_set_state(h, 0, _ffi.ptr_of(slots["m"])))
-                _ffi.check(_ffi.lib().gan_adam_set_state(h, 1, _ffi.ptr_of(slots["v"])))
-                _ffi.check(_ffi.lib().gan_adam_set_step(h, C.c_int64(int(data[f"{name}/iterations"]))))
+                            missing.append(k)
+                obj._apply_state(state)
         if "__meta__" in data.files and self.ctx is not None:
             meta = json.loads(bytes(data["__meta__"]).decode())
             self.last_meta = meta
+            # the dropout stream continues where the saved run stopped (same seed, saved call counter)
+            if restore_rng and "call_counter" in meta:
+                self.ctx.set_rng(self.ctx.seed, int(meta["call_counter"]))
         return _Status(missing, sorted(keys - used))
 
 
@@ -169,13 +181,14 @@ class CheckpointManager:
 
     @property
     def checkpoints(self):
-        fs = glob.glob(os.path.join(self.directory, "ckpt-*.npz"))
+        fs = [f for f in glob.glob(os.path.join(self.directory, "ckpt-*.npz")) if re.search(r"ckpt-(\d+)\.npz$", f)]
         return sorted(fs, key=lambda f: int(re.search(r"ckpt-(\d+)\.npz$", f).group(1)))
 
     def save(self) -> str:
         self._n += 1
         path = self.checkpoint.write(os.path.join(self.directory, f"ckpt-{self._n}"))
         if self.max_to_keep:
-            for old in self.checkpoints[:-self.max_to_keep]:
-                os.remove(old)
+            if getattr(self.checkpoint.ctx, "rank", 0) == 0:
+                for old in self.checkpoints[:-self.max_to_keep]:
+                    os.remove(old)
         return path

@@ -60,6 +60,9 @@ struct ConvOp {
   const void* in_tap[4]; int im2col_c;
   int n_slot4_c;                 // wgrad: output column n = tap*4 + c (c < n_slot4_c real) maps to master row tap*n_slot4_c + c
   float* out_rows_f32;           // optional: write the raw fp32 accumulators as rows [out pixel][Nc] (no bf16 output)
+  // algorithmic (unpadded) GEMM K per class / N for the roofline accounting when the stored operand carries
+  // zero slots (im2col / cols rows hold 16 taps x 4 channel slots); 0 = ntaps*Kr / Nr
+  int real_k, real_n;
 };
 
 // ---- error handling (host) -----------------------------------------------------------------

@@ -127,6 +127,7 @@ static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
   op.Kc = 64; op.Kr = 64; op.Nc = ly.Cout_p; op.Nr = ly.Cout;
   op.s_tap = (int64_t)ly.Cin * ly.Cout; op.s_k = ly.Cout; op.s_n = 1;      // Conv2D master (kh,kw,ci,co)
   op.B = ly.wp_im2col.p;
+  op.real_k = 16 * ly.Cin;                 // every source contributes 16 taps x src_c real channels
   (void)role;
   return op;
 }
@@ -181,9 +182,15 @@ struct ProfScope {
   }
   ~ProfScope() { if (on) { cudaEventRecord(e.b, ctx->stream); ctx->prof.push_back(e); } }
 };
+// Algorithmic FLOPs of one launch: 2*M*N*K of the UNPADDED layer — real channel counts
+// Kr/Nr, and for the slot-4 operands of the image-channel ends the real 16*C columns, not the stored 64.
 static double conv_flops(const ConvOp& op) {
   double f = 0;
-  for (int c = 0; c < op.ncls; ++c) f += 2.0 * op.N * op.Hm * op.Wm * (double)op.Nc * op.cls[c].ntaps * op.Kc;
+  const double n_real = op.real_n > 0 ? op.real_n : op.Nr;
+  for (int c = 0; c < op.ncls; ++c) {
+    const double k_real = op.real_k > 0 ? op.real_k : (double)op.cls[c].ntaps * op.Kr;
+    f += 2.0 * op.N * op.Hm * op.Wm * n_real * k_real;
+  }
   return f;
 }
 
@@ -370,6 +377,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     View cols = make_view(nullptr, B, in.H, in.W, 64);
     ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p);
     cop.out_rows_f32 = s.cols.as<float>();
+    cop.real_n = 16 * ly.Cout;
     run_conv_fwd(ctx, cop);
     launch_col2im_tanh(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
     return;
@@ -381,6 +389,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     View cols = make_view(nullptr, B, in.H, in.W, 64);
     ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p);
     cop.out_rows_f32 = s.cols.as<float>();
+    cop.real_n = 16 * ly.Cout;
     run_conv_fwd(ctx, cop);
     launch_dhead_gather(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, (float*)out.p);
     return;
@@ -402,7 +411,8 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   if (li == 0 && s.used_im2col) run_conv_fwd(ctx, make_op_im2col(ly, R_FWD, s, z));
   else run_conv_fwd(ctx, make_op(ly, R_FWD, in, z, ly.wp_fwd.p));
   DropKey dk = drop_key(ctx, ly, s);
-  ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 2 : 3));
+  // SURVEY 8d byte model: forward = read z + write activation = 2*s per element (statistics belong to the conv epilogue)
+  ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * 2);
   if (ly.norm == NORM_NONE) {
     launch_norm_apply(ctx->L(), ctx->dt, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, nullptr, ly.act, dk, out.p,
                       out.pitch, out.coff);
@@ -564,8 +574,10 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
       View G = make_view(s.gcols.p, B, H / 2, W / 2, 64);
       ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 64, nullptr);
       wg.dW = gr + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = C;
+      wg.real_n = 16 * C;
       run_conv_wgrad(ctx, wg);
       ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p);
+      dg.real_k = 16 * C;
       run_conv_fwd(ctx, dg);
     } else {
       layer_backward(g, s, 15, GradSrc{s.dlogit.p, Cp, 0}, GradSrc{nullptr, 0, 0}, din, true);
@@ -661,9 +673,12 @@ static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool w
       if (want_wgrad) {
         ConvOp wg = make_op_1tap(in, lh.Cin, G, 64, 64, nullptr);
         wg.dW = d->grads.as<float>() + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = 1;
+        wg.real_n = 16;
         run_conv_wgrad(ctx, wg);
       }
-      run_conv_fwd(ctx, make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p));
+      ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p);
+      dg.real_k = 16;
+      run_conv_fwd(ctx, dg);
       continue;
     }
     layer_backward(d, s, li, src, GradSrc{nullptr, 0, 0}, din, want_wgrad);
@@ -811,6 +826,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   const size_t img_bytes = (size_t)B * H * W * C * 4;
   const float* x = stage_in(ctx, 0, x_in, img_bytes);
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
+  ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(d); }
@@ -867,6 +883,7 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   const size_t img_bytes = (size_t)B * H * W * C * 4;
   const float* x = stage_in(ctx, 0, x_in, img_bytes);
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
+  ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy); }
@@ -948,6 +965,7 @@ static void run_step_graphed(gan_ctx* ctx, const std::string& key, const float* 
     CUDA_CHECK(cudaMemcpyAsync(ctx->stage[i].p, src, img_bytes, cudaMemcpyDefault, ctx->stream));
     if (pre) CUDA_CHECK(cudaEventRecord(ctx->prefetch_consumed, ctx->stream));   // prefetch buffer free again
   }
+  ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
   const float* xs = ctx->stage[0].as<float>(); const float* ys = ctx->stage[1].as<float>();
   gan_ctx::GraphEntry& ge = ctx->graph_cache[key];
   if (ge.exec != nullptr && ge.alloc_epoch != g_alloc_epoch) {
@@ -1069,7 +1087,21 @@ int gan_ctx_sync(gan_ctx* ctx) {
   CUDA_CHECK(cudaGetLastError());
   API_END
 }
-int gan_ctx_set_dropout(gan_ctx* ctx, int enabled) { ctx->dropout_enabled = enabled ? 1 : 0; return GAN_OK; }
+// State that a captured step graph bakes in (kernel template choice, kernel arguments): changing it
+// synchronises the stream and drops the captured graphs, so the next step re-captures with the new value.
+static void invalidate_graphs(gan_ctx* ctx) {
+  if (ctx->graph_cache.empty()) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  drop_graphs(ctx);
+}
+int gan_ctx_set_dropout(gan_ctx* ctx, int enabled) {
+  API_BEGIN
+  const int v = enabled ? 1 : 0;
+  if (v != ctx->dropout_enabled) invalidate_graphs(ctx);
+  ctx->dropout_enabled = v;
+  API_END
+}
 int gan_ctx_set_rng(gan_ctx* ctx, uint64_t seed, uint32_t call_counter) {
   API_BEGIN
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1079,7 +1111,12 @@ int gan_ctx_set_rng(gan_ctx* ctx, uint64_t seed, uint32_t call_counter) {
   API_END
 }
 int gan_ctx_get_call_counter(gan_ctx* ctx, uint32_t* out) { *out = ctx->call_counter; return GAN_OK; }
-int gan_ctx_set_engine(gan_ctx* ctx, int engine) { ctx->engine = engine; return GAN_OK; }
+int gan_ctx_set_engine(gan_ctx* ctx, int engine) {
+  API_BEGIN
+  if (engine != ctx->engine) invalidate_graphs(ctx);
+  ctx->engine = engine;
+  API_END
+}
 int gan_ctx_set_graphs(gan_ctx* ctx, int enabled) { ctx->graphs = enabled; return GAN_OK; }
 int gan_ctx_launch_count(gan_ctx* ctx, uint64_t* out) { *out = ctx->launches; return GAN_OK; }
 int gan_ctx_stream(gan_ctx* ctx, void** out) { *out = (void*)ctx->stream; return GAN_OK; }
@@ -1104,7 +1141,12 @@ int gan_ctx_profile_read(gan_ctx* ctx, double ms[8], double work[8], int64_t cou
   ctx->prof.clear();
   API_END
 }
-int gan_ctx_set_sample_offset(gan_ctx* ctx, int64_t sample0) { ctx->sample0 = sample0; ctx->sample0_set = true; return GAN_OK; }
+int gan_ctx_set_sample_offset(gan_ctx* ctx, int64_t sample0) {
+  API_BEGIN
+  if (!ctx->sample0_set || sample0 != ctx->sample0) invalidate_graphs(ctx);    // sample0 is a kernel argument
+  ctx->sample0 = sample0; ctx->sample0_set = true;
+  API_END
+}
 
 int gan_comm_unique_id(void* out128) {
   API_BEGIN
@@ -1340,6 +1382,17 @@ int gan_adam_set_step(gan_adam* opt, int64_t t) {
   CUDA_CHECK(cudaMemcpy(opt->t_dev.p, &tv, 8, cudaMemcpyHostToDevice));
   API_END
 }
+int gan_adam_set_hyper(gan_adam* opt, double lr, double beta1, double beta2, double eps) {
+  API_BEGIN
+  GAN_REQUIRE(opt != nullptr, "null optimizer");
+  GAN_REQUIRE(lr >= 0.0 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "bad Adam hyper-parameters");
+  gan_ctx* ctx = opt->net->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  drop_graphs(ctx);                       // lr / betas are kernel arguments of the captured Adam launches
+  opt->lr = lr; opt->b1 = beta1; opt->b2 = beta2; opt->eps = eps;
+  API_END
+}
 int gan_adam_get_state(gan_adam* opt, int which, float* host_dst) {
   API_BEGIN
   CUDA_CHECK(cudaStreamSynchronize(opt->net->ctx->stream));
@@ -1471,7 +1524,8 @@ int gan_preprocess_images(gan_ctx* ctx, const uint8_t* images, int64_t image_str
   const size_t out_bytes = (size_t)batch * out_size * out_size * channels * 4;
   float* dst = out;
   if (!is_device_ptr(out)) { ctx->stage[2].ensure(out_bytes); dst = ctx->stage[2].as<float>(); }
-  preprocess_on(ctx, ctx->stream, 0, images, image_stride, xf, batch, channels, out_size, dst, nullptr, nullptr, nullptr);
+  // slot 2: the synchronous path never shares its uint8 staging / transform table with a prefetch in flight
+  preprocess_on(ctx, ctx->stream, 2, images, image_stride, xf, batch, channels, out_size, dst, nullptr, nullptr, nullptr);
   // device `out`: asynchronous on the context stream (the pageable transform array has been staged by the
   // runtime when cudaMemcpyAsync returns); host `out`: copied back and synchronised
   if (dst != out) {

@@ -62,7 +62,7 @@ struct gan_ctx {
   int im2col_next = 0;
   // input prefetch (tf.data-style): H2D of the NEXT step's images on a copy stream while this step computes
   DevBuf prefetch_buf[2];
-  DevBuf u8_stage[2], xf_dev[2];   // input pipeline: uint8 images and per-image transforms on the device
+  DevBuf u8_stage[3], xf_dev[3];   // input pipeline: uint8 images and per-image transforms on the device
   const void* prefetch_src[2] = {nullptr, nullptr};
   size_t prefetch_bytes = 0;
   cudaStream_t copy_stream = nullptr;

@@ -125,6 +125,9 @@ GAN_API int gan_adam_get_step(gan_adam* opt, int64_t* t);
 GAN_API int gan_adam_set_step(gan_adam* opt, int64_t t);
 GAN_API int gan_adam_get_state(gan_adam* opt, int which /*0=m,1=v*/, float* host_dst);   /* flat, param order */
 GAN_API int gan_adam_set_state(gan_adam* opt, int which, const float* host_src);
+/* Replace lr / beta_1 / beta_2 / epsilon (tf.train.Checkpoint.restore brings the saved optimizer
+ * hyper-parameters back with the slots, pix2pix.py:400-411).  Captured step graphs are dropped. */
+GAN_API int gan_adam_set_hyper(gan_adam* opt, double lr, double beta1, double beta2, double eps);
 
 /* ---- train steps ---------------------------------------------------------------------------
  * gan_pix2pix_train_step  replaces Pix2Pix.train_step(input_image, target, training)
