@@ -2,13 +2,20 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <stdexcept>
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
-enum { DT_F32 = 0, DT_BF16 = 1 };
+// Storage types.  The 16-bit (tcgen05) mode keeps two of them: ACTIVATIONS (layer inputs, raw conv outputs z,
+// the forward weight packs) are fp16 — 10 mantissa bits, every forward value of these normalised networks is
+// O(1..100), and tcgen05 kind::f16 runs f16 operands at the bf16 rate — while GRADIENTS (dy, dz, the
+// data-gradient weight packs) are bf16, whose fp32 exponent range needs no loss scaling.  Weight-gradient GEMMs
+// therefore multiply an f16 operand by a bf16 operand (instruction-descriptor formats are per operand).
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 enum { K_CONV_S2 = 0, K_CONV_S1P = 1, K_CONVT_S2 = 2 };
 enum { NORM_NONE = 0, NORM_BATCH = 1, NORM_INSTANCE = 2 };
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3 };
@@ -63,6 +70,9 @@ struct ConvOp {
   // algorithmic (unpadded) GEMM K per class / N for the roofline accounting when the stored operand carries
   // zero slots (im2col / cols rows hold 16 taps x 4 channel slots); 0 = ntaps*Kr / Nr
   int real_k, real_n;
+  // storage dtypes (DT_*) of the `in` view (and of the packed weights B, which always match it) and of the `out`
+  // view (forward / dgrad: what the epilogue writes; wgrad: the dtype of the output gradient it reads)
+  int dt_in, dt_out;
 };
 
 // ---- error handling (host) -----------------------------------------------------------------
@@ -100,6 +110,34 @@ template <> struct VecIO<float> {
   }
 };
 
+// fp32 -> fp16 with saturation to +-65504 (an overflowing activation must not become inf and poison the
+// batch statistics; NaN stays NaN)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ f16 f16_sat(float x) {
+  uint32_t r = pack_f16x2_sat(x, 0.f);
+  __half_raw h; h.x = (unsigned short)(r & 0xffffu);
+  return f16(h);
+}
+template <> struct VecIO<f16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const f16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ static __forceinline__ void store(f16* p, const float (&v)[8]) {
+    uint4 t;
+    t.x = pack_f16x2_sat(v[0], v[1]); t.y = pack_f16x2_sat(v[2], v[3]);
+    t.z = pack_f16x2_sat(v[4], v[5]); t.w = pack_f16x2_sat(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 template <> struct VecIO<bf16> {
   static constexpr int N = 8;
   __device__ static __forceinline__ void load(const bf16* p, float (&v)[8]) {
@@ -131,6 +169,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void unpack16(const uint4& t, float (&v)[4], const float*) {
   v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
 }
+__device__ __forceinline__ void unpack16(const uint4& t, float (&v)[8], const f16*) {
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
 __device__ __forceinline__ void unpack16(const uint4& t, float (&v)[8], const bf16*) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
@@ -143,6 +186,19 @@ template <typename T> struct Vec4IO;
 template <> struct Vec4IO<float> {
   __device__ static __forceinline__ void load(const float* p, float (&v)[4]) { VecIO<float>::load(p, v); }
   __device__ static __forceinline__ void store(float* p, const float (&v)[4]) { VecIO<float>::store(p, v); }
+};
+template <> struct Vec4IO<f16> {
+  __device__ static __forceinline__ void load(const f16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+    float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  __device__ static __forceinline__ void store(f16* p, const float (&v)[4]) {
+    uint2 t;
+    t.x = pack_f16x2_sat(v[0], v[1]); t.y = pack_f16x2_sat(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
 };
 template <> struct Vec4IO<bf16> {
   __device__ static __forceinline__ void load(const bf16* p, float (&v)[4]) {
@@ -161,9 +217,19 @@ template <> struct Vec4IO<bf16> {
 
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f(f16 x) { return __half2float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);
 template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ f16 from_f<f16>(float x) { return f16_sat(x); }
+
+// two fp32 -> one packed 16-bit pair (low half = first value)
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float lo, float hi) { return pack_f16x2_sat(lo, hi); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -28,6 +28,7 @@ template <typename T> __device__ __forceinline__ void load4(const T* p, float (&
 template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
   float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
+template <> __device__ __forceinline__ void load4<f16>(const f16* p, float (&v)[4]) { Vec4IO<f16>::load(p, v); }
 template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v)[4]) {
   uint2 t = *reinterpret_cast<const uint2*>(p);
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd_skinny(ConvOp op) {
 // Weight gradient: dW[t][kc][nc] += sum_m in(m,t,kc) * dy(m,nc).  64(k) x 64(nc) tile, the pixel
 // reduction split over blockIdx.z with fp32 atomics into the (pre-zeroed) gradient buffer.
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+template <typename T, typename TD, bool VEC>
 __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
   const int ci = blockIdx.z % op.ncls, split = blockIdx.z / op.ncls;
   const ClassGeom& cg = op.cls[ci];
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
   const int64_t per = ((M + splits - 1) / splits + 15) / 16 * 16;
   const int64_t mbeg = split * per, mend = (mbeg + per < M) ? mbeg + per : M;
   const T* __restrict__ in = (const T*)op.in;
-  const T* __restrict__ dy = (const T*)op.out;
+  const TD* __restrict__ dy = (const TD*)op.out;
 
   const int lm = tid >> 4, lq = (tid & 15) * 4;   // chunk row, 4-wide column group
   // A columns are fixed for the whole loop: precompute tap / channel
@@ -247,9 +248,9 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
       }
       int oh = mh * op.so + cg.oa, ow = mw * op.so + cg.ob;
       if (oh < op.Hout && ow < op.Wout) {
-        const T* dp = dy + (((int64_t)n_img * op.Hout + oh) * op.Wout + ow) * op.out_pitch + op.out_coff;
+        const TD* dp = dy + (((int64_t)n_img * op.Hout + oh) * op.Wout + ow) * op.out_pitch + op.out_coff;
         int n = n0 + lq;
-        if (VEC) { if (n < op.Nc) load4<T>(dp + n, dv); }
+        if (VEC) { if (n < op.Nc) load4<TD>(dp + n, dv); }
         else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) if (n + e < op.Nc) dv[e] = to_f(dp[n + e]);
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvOp op, int splits) {
 
 // Skinny-N weight gradient (Nc <= 4 heads): one thread per input channel, all taps of the class
 // kept in registers, pixel range split over blockIdx.y.
-template <typename T, int NT, int NC>
+template <typename T, typename TD, int NT, int NC>
 __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits) {
   const int ci = blockIdx.z;
   const ClassGeom& cg = op.cls[ci];
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits
   const int64_t per = (M + splits - 1) / splits;
   const int64_t mbeg = blockIdx.y * per, mend = (mbeg + per < M) ? mbeg + per : M;
   const T* __restrict__ in = (const T*)op.in;
-  const T* __restrict__ dy = (const T*)op.out;
+  const TD* __restrict__ dy = (const TD*)op.out;
   typedef typename Acc<T>::type acc_t;
   acc_t acc[NT][NC];
 #pragma unroll
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(128) k_conv_wgrad_skinny(ConvOp op, int splits
     int mw = (int)(m % op.Wm); int64_t r = m / op.Wm; int mh = (int)(r % op.Hm); int n_img = (int)(r / op.Hm);
     int oh = mh * op.so + cg.oa, ow = mw * op.so + cg.ob;
     if (oh >= op.Hout || ow >= op.Wout) continue;
-    const T* dp = dy + (((int64_t)n_img * op.Hout + oh) * op.Wout + ow) * op.out_pitch + op.out_coff;
+    const TD* dp = dy + (((int64_t)n_img * op.Hout + oh) * op.Wout + ow) * op.out_pitch + op.out_coff;
     float d[NC];
 #pragma unroll
     for (int n = 0; n < NC; ++n) d[n] = to_f(dp[n]);
@@ -352,21 +353,23 @@ void launch_conv_fwd_ffma(Launch L, int dt, const ConvOp& op) {
       else k_conv_fwd<T, false><<<grid, 256, 0, L.s>>>(op);
     }
   };
-  if (dt == DT_F32) run((float*)nullptr); else run((bf16*)nullptr);
+  if (dt == DT_F32) run((float*)nullptr); else if (dt == DT_F16) run((f16*)nullptr); else run((bf16*)nullptr);
   KLAUNCH(L);
 }
 
-void launch_conv_wgrad_ffma(Launch L, int dt, const ConvOp& op) {
+// dt_in: dtype of the layer input x; dt_dy: dtype of the output gradient (16-bit mode: f16 x bf16)
+void launch_conv_wgrad_ffma(Launch L, int dt_in, int dt_dy, const ConvOp& op) {
   const int64_t M = (int64_t)op.N * op.Hm * op.Wm;
-  auto run = [&](auto* tag) {
+  auto run = [&](auto* tag, auto* dtag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
+    using TD = typename std::remove_pointer<decltype(dtag)>::type;
     const int nt = op.cls[0].ntaps;
     if (op.Nc <= 4 && (nt == 4 || nt == 16) && (op.Nc == 1 || op.Nc == 3 || nt == 4)) {
       int cblocks = (op.Kc + 127) / 128;
       int64_t want = (148 * 8) / (cblocks * op.ncls);
       int splits = (int)(want < 1 ? 1 : (want > M / 64 + 1 ? M / 64 + 1 : want));
       dim3 grid(cblocks, splits, op.ncls);
-#define SKINNY(NT_, NC_) k_conv_wgrad_skinny<T, NT_, NC_><<<grid, 128, 0, L.s>>>(op, splits)
+#define SKINNY(NT_, NC_) k_conv_wgrad_skinny<T, TD, NT_, NC_><<<grid, 128, 0, L.s>>>(op, splits)
       if (nt == 16 && op.Nc == 1) SKINNY(16, 1);
       else if (nt == 16 && op.Nc == 3) SKINNY(16, 3);
       else if (nt == 4 && op.Nc == 1) SKINNY(4, 1);
@@ -384,9 +387,12 @@ void launch_conv_wgrad_ffma(Launch L, int dt, const ConvOp& op) {
     int splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
     if (splits < 1) splits = 1;
     dim3 grid(kt, ntile, op.ncls * splits);
-    if (vec_ok<T>(op, true)) k_conv_wgrad<T, true><<<grid, 256, 0, L.s>>>(op, splits);
-    else k_conv_wgrad<T, false><<<grid, 256, 0, L.s>>>(op, splits);
+    if (vec_ok<T>(op, true)) k_conv_wgrad<T, TD, true><<<grid, 256, 0, L.s>>>(op, splits);
+    else k_conv_wgrad<T, TD, false><<<grid, 256, 0, L.s>>>(op, splits);
   };
-  if (dt == DT_F32) run((float*)nullptr); else run((bf16*)nullptr);
+  if (dt_in == DT_F32) run((float*)nullptr, (float*)nullptr);
+  else if (dt_in == DT_F16) run((f16*)nullptr, (bf16*)nullptr);
+  else run((bf16*)nullptr, (bf16*)nullptr);
+  (void)dt_dy;
   KLAUNCH(L);
 }

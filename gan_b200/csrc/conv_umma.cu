@@ -165,10 +165,16 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_by
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((8 * SW) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16 (InstrDescriptor bit layout).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor, kind::f16 (InstrDescriptor bit layout): D format [4,6) = 1 (f32), A format [7,10) and
+// B format [10,13) = 0 (f16) | 1 (bf16) — chosen per operand, so an f16 activation tile can meet a bf16 gradient
+// tile in one MMA —, A/B major bits 15/16, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int a_bf16 = 1, int b_bf16 = 1) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// two fp32 accumulators -> one packed 16-bit pair of the output dtype
+__device__ __forceinline__ uint32_t cvt_pair(float lo, float hi, int out_f16) {
+  return out_f16 ? pack2<f16>(lo, hi) : pack2<bf16>(lo, hi);
 }
 
 // =============================================================================================
@@ -183,11 +189,13 @@ struct alignas(64) UmmaFwdParams {
   int ntaps[4], oa[4], ob[4];
   int kchunks;                 // Kc / 64 (KC == 64)
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;
-  bf16* out; int out_pitch, out_coff, Hout, Wout, so;
+  bf16* out; int out_pitch, out_coff, Hout, Wout, so;   // 16-bit elements (f16 or bf16 bit patterns, see out_f16)
   int N, Hm, Wm, Nc;
   const float* bias; float* out_f32; int epi, Nr;
   int num_tiles, ncls;
   int f32out;                        // write fp32 rows to ws (slab 0) instead of bf16 (cols of the generator head)
+  int ab_bf16;                       // operand format of A and B (both: the weights are packed in the input's dtype)
+  int out_f16;                       // 16-bit output format: 1 = f16 (activations), 0 = bf16 (gradients)
   float* ws; int ksplit; long long slab;   // split-K: split ks stores fp32 into ws[ks][pix][Nc] (no atomics)
 };
 
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    const uint32_t idesc = make_idesc(128, BN, 0, 0, p.ab_bf16, p.ab_bf16);
     uint32_t it = 0, li = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
       const int cls = ((tile / p.ksplit) % inner) / ntn;
@@ -351,12 +359,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
           } else if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+              uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
-              *reinterpret_cast<uint4*>(dst + c + j * 8) = o;
+                o[e] = cvt_pair(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]), p.out_f16);
+              *reinterpret_cast<uint4*>(dst + c + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
@@ -371,12 +378,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
           if (p.out != nullptr) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              uint4 o;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+              uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                h[e] = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
-              *reinterpret_cast<uint4*>(dst + j * 8) = o;
+                o[e] = cvt_pair(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]), p.out_f16);
+              *reinterpret_cast<uint4*>(dst + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
@@ -459,6 +465,7 @@ static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile, int
   P.out = (bf16*)op.out; P.out_pitch = op.out_pitch; P.out_coff = op.out_coff; P.Hout = op.Hout; P.Wout = op.Wout; P.so = op.so;
   P.N = op.N; P.Hm = op.Hm; P.Wm = op.Wm; P.Nc = op.Nc;
   P.bias = op.bias; P.out_f32 = op.out_f32; P.epi = op.epi; P.Nr = op.Nr; P.ncls = op.ncls;
+  P.ab_bf16 = op.dt_in == DT_F16 ? 0 : 1; P.out_f16 = op.dt_out == DT_F16 ? 1 : 0;
 }
 
 void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
@@ -500,7 +507,7 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   }
   KLAUNCH(L);
   if (P.ksplit > 1)   // deterministic reduction of the k-split slabs + conversion to bf16
-    launch_sum_slabs(L, DT_BF16, op.splitk_ws, P.ksplit, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
+    launch_sum_slabs(L, op.dt_out, op.splitk_ws, P.ksplit, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
 }
 
 // =============================================================================================
@@ -520,6 +527,7 @@ struct alignas(64) UmmaWgradParams {
   int Nc, Kr, Nr;
   int im2col_c;            // >0: rows are im2col K-blocks (t = source, kc = tap16*4 + channel slot)
   int n_slot4_c;           // >0: columns are (tap16*4 + channel slot) of a cols matrix
+  int a_bf16, b_bf16;      // operand formats: A = layer input (activation dtype), B = output gradient (bf16)
 };
 
 constexpr int WG_STAGES = 3;
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         }
       }
     } else if (warp == 1) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      const uint32_t idesc = make_idesc(128, BN, 1, 1, p.a_bf16, p.b_bf16);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % WG_STAGES;
         const uint32_t ph = (kb / WG_STAGES) & 1;
@@ -712,6 +720,7 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   P.dW = op.dW; P.s_tap = op.s_tap; P.s_k = op.s_k; P.s_n = op.s_n; P.Nc = op.Nc; P.Kr = op.Kr; P.Nr = op.Nr;
   P.im2col_c = op.in_tap[0] != nullptr ? op.im2col_c : 0;
   P.n_slot4_c = op.n_slot4_c;
+  P.a_bf16 = op.dt_in == DT_F16 ? 0 : 1; P.b_bf16 = op.dt_out == DT_F16 ? 0 : 1;
   const int ntaps = op.cls[0].ntaps;
   const int mblocks = (ntaps * op.Kc + 127) / 128;
   const int ntiles = op.Nc / BN;

@@ -13,7 +13,15 @@
 #define NSM 148
 
 template <typename F> static void dispatch_dt(int dt, F&& f) {
-  if (dt == DT_F32) f((float*)nullptr); else f((bf16*)nullptr);
+  if (dt == DT_F32) f((float*)nullptr); else if (dt == DT_F16) f((f16*)nullptr); else f((bf16*)nullptr);
+}
+// (activation dtype, gradient dtype) pairs: fp32/fp32, f16/bf16 (default 16-bit mode), bf16/bf16
+template <typename F> static void dispatch_dt2(int dtz, int dtg, F&& f) {
+  if (dtz == DT_F32) { GAN_REQUIRE(dtg == DT_F32, "fp32 activations need fp32 gradients"); f((float*)nullptr, (float*)nullptr); }
+  else {
+    GAN_REQUIRE(dtg == DT_BF16, "16-bit gradients are bf16");
+    if (dtz == DT_F16) f((f16*)nullptr, (bf16*)nullptr); else f((bf16*)nullptr, (bf16*)nullptr);
+  }
 }
 #define KLAUNCH(L) (++*(L).count)
 
@@ -318,8 +326,8 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
 //   dbeta = sum g, dgamma = sum g*xhat,  dz = gamma*inv * (g - mean(g) - xhat*mean(g*xhat))
 // ---------------------------------------------------------------------------------------------
 // Issue the cp.async copies of one iteration (z row vector + one or two gradient sources).
-template <typename T>
-__device__ __forceinline__ void ring_issue3(uint4* ring, uint32_t it, bool ok, const T* z, size_t zoff, const GradSrc& d1,
+template <typename TZ, typename T>
+__device__ __forceinline__ void ring_issue3(uint4* ring, uint32_t it, bool ok, const TZ* z, size_t zoff, const GradSrc& d1,
                                             const GradSrc& d2, size_t p, int c0) {
   const int narr = d2.p != nullptr ? 3 : 2;
   uint4* slot = ring + ((it % RING_STAGES) * narr) * 256 + threadIdx.x;
@@ -328,11 +336,11 @@ __device__ __forceinline__ void ring_issue3(uint4* ring, uint32_t it, bool ok, c
   if (narr == 3) cp_async16(slot + 512, (const T*)d2.p + (ok ? p * d2.pitch + d2.coff + c0 : 0), ok);
   cp_async_commit();
 }
-template <typename T, int V>
+template <typename TZ, typename T, int V>
 __device__ __forceinline__ void ring_read3(const uint4* ring, uint32_t it, bool has_d2, float (&v)[V], float (&g)[V]) {
   const int narr = has_d2 ? 3 : 2;
   const uint4* slot = ring + ((it % RING_STAGES) * narr) * 256 + threadIdx.x;
-  unpack16(slot[0], v, (const T*)nullptr);
+  unpack16(slot[0], v, (const TZ*)nullptr);
   unpack16(slot[256], g, (const T*)nullptr);
   if (has_d2) {
     float h[V];
@@ -342,8 +350,8 @@ __device__ __forceinline__ void ring_read3(const uint4* ring, uint32_t it, bool 
   }
 }
 
-template <typename T, bool DROP>
-__global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t Pg, uint32_t HW,
+template <typename TZ, typename T, bool DROP>
+__global__ void __launch_bounds__(256) k_bwd_reduce(const TZ* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t Pg, uint32_t HW,
                                                     int C, int lcv, int nchunk, const float* __restrict__ mean,
                                                     const float* __restrict__ inv, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int act, DropKey dk,
@@ -369,14 +377,14 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const T* __restrict__ z, Gra
   auto issue = [&](uint32_t it) {
     const bool ok = it < nit;
     const size_t p = (size_t)g * Pg + first + (size_t)it * rows_par;
-    ring_issue3<T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
+    ring_issue3<TZ, T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
   };
   for (uint32_t it = 0; it < RING_STAGES - 1; ++it) issue(it);
   for (uint32_t it = 0; it < nit; ++it) {
     issue(it + RING_STAGES - 1);
     cp_async_wait<RING_STAGES - 1>();
     float v[V], gr[V];
-    ring_read3<T, V>(ring, it, has_d2, v, gr);
+    ring_read3<TZ, T, V>(ring, it, has_d2, v, gr);
     const uint32_t pg = g * Pg + first + it * rows_par;
     uint32_t smp = 0, e0 = 0;
     if (DROP) { smp = pg / HW; e0 = (pg - smp * HW) * C + c0; }
@@ -410,8 +418,8 @@ __global__ void __launch_bounds__(32 * FIN_LANES) k_bwd_finalize(const float* __
   atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
 }
 
-template <typename T, bool DROP>
-__global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t P, uint32_t Pg,
+template <typename TZ, typename T, bool DROP>
+__global__ void __launch_bounds__(256) k_bwd_apply(const TZ* __restrict__ z, GradSrc d1, GradSrc d2, uint32_t P, uint32_t Pg,
                                                    int G, uint32_t HW, int C, int lcv, int norm,
                                                    const float* __restrict__ mean, const float* __restrict__ inv,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
   auto issue = [&](uint32_t it) {
     const bool ok = it < nit;
     const size_t p = (size_t)prow + (size_t)it * pstride;
-    ring_issue3<T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
+    ring_issue3<TZ, T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
   };
   for (uint32_t it = 0; it < RING_STAGES - 1; ++it) issue(it);
   for (uint32_t it = 0; it < nit; ++it) {
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const T* __restrict__ z, Grad
     cp_async_wait<RING_STAGES - 1>();
     const uint32_t pp = prow + it * pstride;
     float v[V], gr[V], o[V];
-    ring_read3<T, V>(ring, it, has_d2, v, gr);
+    ring_read3<TZ, T, V>(ring, it, has_d2, v, gr);
     if (norm == NORM_NONE) {
 #pragma unroll
       for (int k = 0; k < V; ++k) o[k] = gr[k] * act_bwd(v[k], act);
@@ -563,9 +571,9 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_fwd(
   }
 }
 
-template <typename T, bool DROP>
+template <typename TZ, typename T, bool DROP>
 __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
-    const T* __restrict__ z_all, GradSrc d1, GradSrc d2, uint32_t P, uint32_t HW, int C, const float* __restrict__ mean,
+    const TZ* __restrict__ z_all, GradSrc d1, GradSrc d2, uint32_t P, uint32_t HW, int C, const float* __restrict__ mean,
     const float* __restrict__ inv, const float* __restrict__ scale, const float* __restrict__ shift, int act, DropKey dk,
     float* __restrict__ c1, float* __restrict__ c2, float* dgamma, float* dbeta, T* __restrict__ dz_all) {
   constexpr int V = VecIO<T>::N;
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
   const uint32_t g = blockIdx.y;                        // normalisation group (see k_bn_small_fwd)
   const size_t gi = (size_t)g * C;
   const size_t p_base = (size_t)g * P;
-  const T* z = z_all + p_base * C;
+  const TZ* z = z_all + p_base * C;
   T* dz = dz_all + p_base * C;
   const bool has_d2 = d2.p != nullptr;
   for (uint32_t p = threadIdx.x; p < P; p += BNS_THREADS) {
@@ -596,7 +604,7 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
   // g = (d1 + d2) * act'(u) * dropout'
   auto grad_at = [&](uint32_t p, float (&xc)[V], float (&gg)[V]) {
     float v[V], gr[V];
-    unpack16(slab[p], v, (const T*)nullptr);
+    unpack16(slab[p], v, (const TZ*)nullptr);
     unpack16(slab[P + p], gr, (const T*)nullptr);
     if (has_d2) {
       float h[V];
@@ -675,40 +683,42 @@ bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int 
   return true;
 }
 
-void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
+void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz) {
   int nchunk = stats_chunks(G, Pg);
-  dispatch_dt(dt, [&](auto* tag) {
+  dispatch_dt2(dtz, dt, [&](auto* ztag, auto* tag) {
+    using TZ = typename std::remove_pointer<decltype(ztag)>::type;
     using T = typename std::remove_pointer<decltype(tag)>::type;
+    static_assert(sizeof(TZ) == sizeof(T), "activation and gradient vectors must have the same width");
     const int cv = C / VecIO<T>::N;
     GAN_REQUIRE((cv & (cv - 1)) == 0 && cv <= 256 && cv >= 1, "channel count must be a power of two");
     const int lcv = ilog2(cv);
     const int narr = d2.p != nullptr ? 3 : 2;
     const size_t smem = (size_t)RING_STAGES * narr * 256 * 16;
     const size_t smem_max = (size_t)RING_STAGES * 3 * 256 * 16;
-    static bool once = (set_smem(k_bwd_reduce<T, true>, smem_max), set_smem(k_bwd_reduce<T, false>, smem_max),
-                        set_smem(k_bwd_apply<T, true>, smem_max), set_smem(k_bwd_apply<T, false>, smem_max), true);
+    static bool once = (set_smem(k_bwd_reduce<TZ, T, true>, smem_max), set_smem(k_bwd_reduce<TZ, T, false>, smem_max),
+                        set_smem(k_bwd_apply<TZ, T, true>, smem_max), set_smem(k_bwd_apply<TZ, T, false>, smem_max), true);
     (void)once;
     if (norm != NORM_NONE && bn_small_fits(G, P, narr)) {
-      static bool once2 = (set_smem(k_bn_small_bwd<T, true>, BNS_MAX_SMEM), set_smem(k_bn_small_bwd<T, false>, BNS_MAX_SMEM), true);
+      static bool once2 = (set_smem(k_bn_small_bwd<TZ, T, true>, BNS_MAX_SMEM), set_smem(k_bn_small_bwd<TZ, T, false>, BNS_MAX_SMEM), true);
       (void)once2;
-      auto kern = dk.enabled ? k_bn_small_bwd<T, true> : k_bn_small_bwd<T, false>;
-      kern<<<dim3(C / VecIO<T>::N, G), BNS_THREADS, (size_t)Pg * narr * 16, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, mean,
+      auto kern = dk.enabled ? k_bn_small_bwd<TZ, T, true> : k_bn_small_bwd<TZ, T, false>;
+      kern<<<dim3(C / VecIO<T>::N, G), BNS_THREADS, (size_t)Pg * narr * 16, L.s>>>((const TZ*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, mean,
                                                                          inv, scale, shift, act, dk, c1, c2, dgamma, dbeta, (T*)dz);
       KLAUNCH(L);
       return;
     }
     if (norm != NORM_NONE) {
-      auto kred = dk.enabled ? k_bwd_reduce<T, true> : k_bwd_reduce<T, false>;
-      kred<<<dim3(nchunk, G), 256, smem, L.s>>>((const T*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean, inv,
+      auto kred = dk.enabled ? k_bwd_reduce<TZ, T, true> : k_bwd_reduce<TZ, T, false>;
+      kred<<<dim3(nchunk, G), 256, smem, L.s>>>((const TZ*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean, inv,
                                                 scale, shift, act, dk, ws);
       KLAUNCH(L);
       k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
       KLAUNCH(L);
     }
-    auto kapp = dk.enabled ? k_bwd_apply<T, true> : k_bwd_apply<T, false>;
-    kapp<<<norm_grid(P, cv, narr == 3 ? 2 : 3), 256, smem, L.s>>>((const T*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW,
+    auto kapp = dk.enabled ? k_bwd_apply<TZ, T, true> : k_bwd_apply<TZ, T, false>;
+    kapp<<<norm_grid(P, cv, narr == 3 ? 2 : 3), 256, smem, L.s>>>((const TZ*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW,
                                                                  C, lcv, norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz);
     KLAUNCH(L);
   });
@@ -933,6 +943,13 @@ void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp&
   KLAUNCH(L);
 }
 
+// 16-bit destinations carry their own format per entry (forward packs: activation dtype, data-gradient packs: bf16)
+template <typename T> __device__ __forceinline__ T pack_cvt(float v, int dt16);
+template <> __device__ __forceinline__ float pack_cvt<float>(float v, int) { return v; }
+template <> __device__ __forceinline__ bf16 pack_cvt<bf16>(float v, int dt16) {
+  if (dt16 == DT_F16) { f16 h = f16_sat(v); return *reinterpret_cast<bf16*>(&h); }    // bit pattern of the fp16 value
+  return __float2bfloat16_rn(v);
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict__ tab, int nent) {
   __shared__ float tile[32][33];
@@ -967,7 +984,7 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
       int n = n0 + r, kc = k0 + tx;
-      if (n < op.Nc && kc < op.Kc) dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(tile[tx][r]);
+      if (n < op.Nc && kc < op.Kc) dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = pack_cvt<T>(tile[tx][r], E.dt16);
     }
   } else {
     // master contiguous along kc (s_k == 1): straight tile copy
@@ -976,16 +993,15 @@ __global__ void __launch_bounds__(256) k_pack_multi(const PackEntry* __restrict_
       int n = n0 + r, kc = k0 + tx;
       if (n < op.Nc && kc < op.Kc) {
         float v = (kc < op.Kr && n < op.Nr) ? src[(int64_t)kc * op.s_k + (int64_t)n * op.s_n] : 0.f;
-        dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = from_f<T>(v);
+        dst[(int64_t)n * Ktot + (int64_t)t * op.Kc + kc] = pack_cvt<T>(v, E.dt16);
       }
     }
   }
 }
 void launch_pack_multi(Launch L, int dt, const PackEntry* tab_dev, int nent, int total_tiles) {
-  dispatch_dt(dt, [&](auto* tag) {
-    using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_pack_multi<T><<<total_tiles, 256, 0, L.s>>>(tab_dev, nent);
-  });
+  // dt: DT_F32 or "16-bit" (the format of each destination is PackEntry::dt16)
+  if (dt == DT_F32) k_pack_multi<float><<<total_tiles, 256, 0, L.s>>>(tab_dev, nent);
+  else k_pack_multi<bf16><<<total_tiles, 256, 0, L.s>>>(tab_dev, nent);
   KLAUNCH(L);
 }
 
@@ -1008,7 +1024,7 @@ __device__ __forceinline__ float adam_update(const AdamArgs& a, long long i, flo
 // 64x64 tiles of the master [16][A][B] kernel tensors, 256 threads: thread = (column b, 4 row groups);
 // the 4 x 8 rows of a half-tile are loaded first (32 independent loads per thread), then updated.
 #define APT 64
-template <typename T>
+template <typename TF, typename TD>
 __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEntry* __restrict__ tab, int nent) {
   __shared__ float tile[APT][APT + 1];
   __shared__ int s_e;
@@ -1028,8 +1044,8 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
   const int a0 = ta * APT, b0 = tb * APT;
   const int tx = threadIdx.x & (APT - 1), ty = threadIdx.x >> 6;          // 64 x 4
   const int cF = E.invF[widx] >> 4, tF = E.invF[widx] & 15, cD = E.invD[widx] >> 4, tD = E.invD[widx] & 15;
-  T* __restrict__ dF = (T*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
-  T* __restrict__ dD = (T*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
+  TF* __restrict__ dF = (TF*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
+  TD* __restrict__ dD = (TD*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
   const long long base = E.w_off + (long long)widx * E.A * E.B;
   const int bi = b0 + tx;
 #pragma unroll
@@ -1055,8 +1071,8 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
         pn = P[i] - lr_t * mm / (sqrtf(vv) + a.eps);
         a.m[idx] = mm; a.v[idx] = vv; a.p[idx] = pn;
         // destination that is contiguous along the master's fast index b
-        if (E.conv2d) dD[(long long)ai * E.KtotD + bi] = from_f<T>(pn);        // ci = a, co = b
-        else dF[(long long)ai * E.KtotF + bi] = from_f<T>(pn);                 // co = a, ci = b
+        if (E.conv2d) dD[(long long)ai * E.KtotD + bi] = from_f<TD>(pn);       // ci = a, co = b
+        else dF[(long long)ai * E.KtotF + bi] = from_f<TF>(pn);                // co = a, ci = b
       }
       tile[r][tx] = pn;
     }
@@ -1067,15 +1083,16 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
     const int r = ty + 4 * i;                 // row of the transposed tile = b index
     const int bj = b0 + r, ai = a0 + tx;
     if (ai < E.A && bj < E.B) {
-      if (E.conv2d) dF[(long long)bj * E.KtotF + ai] = from_f<T>(tile[tx][r]);   // co = b, ci = a
-      else dD[(long long)bj * E.KtotD + ai] = from_f<T>(tile[tx][r]);            // ci = b, co = a
+      if (E.conv2d) dF[(long long)bj * E.KtotF + ai] = from_f<TF>(tile[tx][r]);  // co = b, ci = a
+      else dD[(long long)bj * E.KtotD + ai] = from_f<TD>(tile[tx][r]);           // ci = b, co = a
     }
   }
 }
-void launch_adam_pack(Launch L, int dt, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles) {
-  dispatch_dt(dt, [&](auto* tag) {
-    using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_adam_pack<T><<<total_tiles, 256, 0, L.s>>>(a, tab_dev, nent);
+void launch_adam_pack(Launch L, int dt_fwd, int dt_dgrad, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles) {
+  dispatch_dt2(dt_fwd, dt_dgrad, [&](auto* ftag, auto* dtag) {
+    using TF = typename std::remove_pointer<decltype(ftag)>::type;
+    using TD = typename std::remove_pointer<decltype(dtag)>::type;
+    k_adam_pack<TF, TD><<<total_tiles, 256, 0, L.s>>>(a, tab_dev, nent);
   });
   KLAUNCH(L);
 }
@@ -1138,9 +1155,9 @@ void launch_gather_pack(Launch L, int dt, const float* master, const int* idx_de
 // unfold of the generator-head gradient): one thread per output-grid point writes one 128-byte row
 // [16 taps x 4 channel slots] (slots >= C are zero), entirely from registers.
 // ---------------------------------------------------------------------------------------------
-template <typename TS, int C>
+template <typename TS, int C, typename TO>
 __global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int pitch, int B, int H, int W,
-                                                bf16* __restrict__ dst) {
+                                                TO* __restrict__ dst) {
   // 8 threads per output-grid point, each builds one 16-byte chunk (2 taps x 4 channel slots): a warp
   // stores 4 consecutive 128-byte rows, fully coalesced.
   const int Ho = H / 2, Wo = W / 2;
@@ -1160,8 +1177,7 @@ __global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int 
 #pragma unroll
         for (int c = 0; c < C; ++c) v[c] = to_f(sp[c]);
       }
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-      w[2 * e] = *reinterpret_cast<uint32_t*>(&lo); w[2 * e + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      w[2 * e] = pack2<TO>(v[0], v[1]); w[2 * e + 1] = pack2<TO>(v[2], v[3]);
     }
     *reinterpret_cast<uint4*>(dst + m * 64 + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -1236,20 +1252,21 @@ void launch_ghead_bwd_cols(Launch L, const float* out_f32, const float* ref_f32,
   KLAUNCH(L);
 }
 
-template <typename TS>
+template <typename TS, typename TO>
 static void im2col_dispatch(Launch L, const TS* src, int pitch, int B, int H, int W, int C, void* dst) {
   GAN_REQUIRE(C >= 1 && C <= 4, "im2col supports 1..4 channels per source");
   const int64_t M = (int64_t)B * (H / 2) * (W / 2);
   const int grid = grid_for(M * 8, 256, 16);
-  bf16* d = (bf16*)dst;
-  if (C == 1) k_im2col<TS, 1><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
-  else if (C == 2) k_im2col<TS, 2><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
-  else if (C == 3) k_im2col<TS, 3><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
-  else k_im2col<TS, 4><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  TO* d = (TO*)dst;
+  if (C == 1) k_im2col<TS, 1, TO><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  else if (C == 2) k_im2col<TS, 2, TO><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  else if (C == 3) k_im2col<TS, 3, TO><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
+  else k_im2col<TS, 4, TO><<<grid, 256, 0, L.s>>>(src, pitch, B, H, W, d);
   KLAUNCH(L);
 }
-void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16) {
-  im2col_dispatch<float>(L, src, C, B, H, W, C, dst_bf16);
+void launch_im2col(Launch L, int dt_rows, const float* src, int B, int H, int W, int C, void* dst_rows) {
+  if (dt_rows == DT_F16) im2col_dispatch<float, f16>(L, src, C, B, H, W, C, dst_rows);
+  else im2col_dispatch<float, bf16>(L, src, C, B, H, W, C, dst_rows);
 }
 
 // col2im of the transposed-conv head: one thread per output pixel gathers its 4 contributing taps

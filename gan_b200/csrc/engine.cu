@@ -88,8 +88,11 @@ static void weight_strides(const Layer& ly, int role, int& Kc, int& Nc, int& Kr,
 }
 
 // x: layer-input-side view (N,Hin,Win,Cin); y: layer-output-side view (N,Hout,Wout,Cout).
-static ConvOp make_op(const Layer& ly, int role, View x, View y, const void* wpack) {
+static ConvOp make_op(const gan_ctx* ctx, const Layer& ly, int role, View x, View y, const void* wpack) {
   ConvOp op; memset(&op, 0, sizeof(op));
+  // forward: activations in, activations out; dgrad: gradients in, gradients out; wgrad: activations x gradients
+  op.dt_in = role == R_DGRAD ? ctx->dtG : ctx->dtA;
+  op.dt_out = role == R_FWD ? ctx->dtA : ctx->dtG;
   op.ncls = fill_geometry(ly.kind, role, op.cls);
   weight_strides(ly, role, op.Kc, op.Nc, op.Kr, op.Nr, op.s_tap, op.s_k, op.s_n);
   View src = (role == R_DGRAD) ? y : x, dst = (role == R_DGRAD) ? x : y;
@@ -115,8 +118,9 @@ static bool im2col_on(const gan_ctx* ctx, const Layer& ly) {
   return ly.first && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.src_c <= 4 && ly.Cout_p % 64 == 0;
 }
 // role: R_FWD (y = z written) or R_WGRAD (y = dz read).  M-space = output grid of the layer.
-static ConvOp make_op_im2col(const Layer& ly, int role, const Slot& s, View y) {
+static ConvOp make_op_im2col(const gan_ctx* ctx, const Layer& ly, int role, const Slot& s, View y) {
   ConvOp op; memset(&op, 0, sizeof(op));
+  op.dt_in = ctx->dtA; op.dt_out = role == R_FWD ? ctx->dtA : ctx->dtG;
   op.ncls = 1;
   op.cls[0].ntaps = ly.nsrc;
   for (int t = 0; t < ly.nsrc; ++t) { op.cls[0].widx[t] = (int8_t)t; op.in_tap[t] = s.im2col[t]; }
@@ -144,8 +148,9 @@ static bool dcols_on(const gan_ctx* ctx, const gan_net* n, const Layer& ly) {
   return !n->is_gen && ly.head && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && ly.Cout == 1 &&
          ly.Cin % 64 == 0 && ly.wp_cols.p != nullptr;
 }
-static ConvOp make_op_1tap(View in, int Kc, View out, int Nc, int Nr, const void* B) {
+static ConvOp make_op_1tap(View in, int Kc, View out, int Nc, int Nr, const void* B, int dt_in, int dt_out) {
   ConvOp op; memset(&op, 0, sizeof(op));
+  op.dt_in = dt_in; op.dt_out = dt_out;
   op.ncls = 1; op.cls[0].ntaps = 1;
   op.in = in.p; op.in_pitch = in.pitch; op.in_coff = in.coff; op.Hin = in.H; op.Win = in.W;
   op.out = out.p; op.out_pitch = out.pitch; op.out_coff = out.coff; op.Hout = out.H; op.Wout = out.W;
@@ -161,7 +166,7 @@ static const void* cached_im2col(gan_ctx* ctx, const float* src, int B, int H, i
   gan_ctx::Im2colEntry& e = ctx->im2col_cache[ctx->im2col_next];
   ctx->im2col_next = (ctx->im2col_next + 1) % 6;
   e.buf.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
-  launch_im2col(ctx->L(), src, B, H, W, C, e.buf.p);
+  launch_im2col(ctx->L(), ctx->dtA, src, B, H, W, C, e.buf.p);
   e.src = src; e.B = B; e.H = H; e.W = W; e.C = C; e.epoch = ctx->step_epoch;
   return e.buf.p;
 }
@@ -206,7 +211,7 @@ static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
   ProfScope ps(ctx, um ? FAM_UMMA_FWD : FAM_FFMA_FWD, conv_flops(op));
   if (um) launch_conv_fwd_umma(ctx->L(), op);
-  else launch_conv_fwd_ffma(ctx->L(), ctx->dt, op);
+  else launch_conv_fwd_ffma(ctx->L(), op.dt_in, op);
 }
 static void run_conv_wgrad(gan_ctx* ctx, const ConvOp& op) {
   bool can = ctx->dt == DT_BF16 && umma_wgrad_supported(op);
@@ -214,7 +219,7 @@ static void run_conv_wgrad(gan_ctx* ctx, const ConvOp& op) {
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
   ProfScope ps(ctx, um ? FAM_UMMA_WGRAD : FAM_FFMA_WGRAD, conv_flops(op));
   if (um) launch_conv_wgrad_umma(ctx->L(), op);
-  else launch_conv_wgrad_ffma(ctx->L(), ctx->dt, op);
+  else launch_conv_wgrad_ffma(ctx->L(), op.dt_in, op.dt_out, op);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,6 +296,7 @@ static void pack_weights(gan_net* n) {
         DevBuf& dst = role == R_FWD ? ly.wp_fwd : ly.wp_dgrad;
         dst.ensure((size_t)16 * ly.Cin_p * ly.Cout_p * ctx->esize());
         e.master = n->params.as<float>() + ly.w_off; e.dst = dst.p;
+        e.dt16 = role == R_FWD ? ctx->dtA : ctx->dtG;
         e.tiles_k = (po.Kc + 31) / 32; e.tiles_n = (po.Nc + 31) / 32;
         e.tile_begin = tiles;
         tiles += e.tiles_k * e.tiles_n * po.cls[0].ntaps * po.ncls;
@@ -303,9 +309,10 @@ static void pack_weights(gan_net* n) {
     // extra packed copies (bf16 mode) through index tables: the first layer in im2col K order
     // (k = source*64 + tap*4 + channel slot); the generator head as the two single-tap GEMM operands
     // of its cols formulation (n = tap*4 + channel slot)
-    auto add_gather = [&](const std::vector<int>& idx, DevBuf& dstbuf) {
+    auto add_gather = [&](const std::vector<int>& idx, DevBuf& dstbuf, int dt) {
       n->gathers.emplace_back();
       gan_net::GatherTab& gt = n->gathers.back();
+      gt.dt = dt;
       dstbuf.ensure(idx.size() * ctx->esize());
       gt.idx.ensure(idx.size() * sizeof(int));
       CUDA_CHECK(cudaMemcpy(gt.idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -320,7 +327,7 @@ static void pack_weights(gan_net* n) {
           for (int t = 0; t < 16; ++t)
             for (int c = 0; c < C; ++c)
               idx[(size_t)nn * Kt + sidx * 64 + t * 4 + c] = (int)(l0.w_off + ((int64_t)t * l0.Cin + sidx * C + c) * l0.Cout + nn);
-      add_gather(idx, l0.wp_im2col);
+      add_gather(idx, l0.wp_im2col, ctx->dtA);
     }
     Layer& lh = n->layers.back();
     if (n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout <= 4 && lh.Cin % 64 == 0) {
@@ -333,8 +340,8 @@ static void pack_weights(gan_net* n) {
             fc[(size_t)(t * 4 + co) * Ci + ci] = m;      // forward  B[n = tap*4+co][ci]
             dc[(size_t)ci * 64 + t * 4 + co] = m;        // dgrad    B[n = ci][k = tap*4+co]
           }
-      add_gather(fc, lh.wp_cols);
-      add_gather(dc, lh.wp_dcols);
+      add_gather(fc, lh.wp_cols, ctx->dtA);      // forward operand: multiplies activations
+      add_gather(dc, lh.wp_dcols, ctx->dtG);     // data-gradient operand: multiplies gradients
     }
     if (!n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout == 1 && lh.Cin % 64 == 0) {
       const int Ci = lh.Cin;                        // master (kh,kw,ci,1): element tap*Ci + ci
@@ -345,12 +352,12 @@ static void pack_weights(gan_net* n) {
           fc[(size_t)(t * 4) * Ci + ci] = m;        // forward  B[n = tap*4][ci]
           dc[(size_t)ci * 64 + t * 4] = m;          // dgrad    B[n = ci][k = tap*4]
         }
-      add_gather(fc, lh.wp_cols);
-      add_gather(dc, lh.wp_dcols);
+      add_gather(fc, lh.wp_cols, ctx->dtA);      // forward operand: multiplies activations
+      add_gather(dc, lh.wp_dcols, ctx->dtG);     // data-gradient operand: multiplies gradients
     }
   }
   launch_pack_multi(ctx->L(), ctx->dt, (const PackEntry*)n->pack_tab.p, n->pack_nent, n->pack_tiles);
-  for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), ctx->dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
+  for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), gt.dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
   n->packed_dirty = false;
 }
 
@@ -375,7 +382,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     s.used_cols = true;
     s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);            // fp32 rows: the 4-term col2im sum is not pre-rounded
     View cols = make_view(nullptr, B, in.H, in.W, 64);
-    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p);
+    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p, ctx->dtA, ctx->dtA);
     cop.out_rows_f32 = s.cols.as<float>();
     cop.real_n = 16 * ly.Cout;
     run_conv_fwd(ctx, cop);
@@ -387,7 +394,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     s.used_cols = true;
     s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);
     View cols = make_view(nullptr, B, in.H, in.W, 64);
-    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p);
+    ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p, ctx->dtA, ctx->dtA);
     cop.out_rows_f32 = s.cols.as<float>();
     cop.real_n = 16 * ly.Cout;
     run_conv_fwd(ctx, cop);
@@ -398,7 +405,7 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     s.used_cols = false;
     // generator head: bias + tanh -> fp32 image; discriminator head: bias -> fp32 logits
     View y = make_view(nullptr, B, Ho, Wo, ly.Cout_p);
-    ConvOp op = make_op(ly, R_FWD, in, y, ly.wp_fwd.p);
+    ConvOp op = make_op(ctx, ly, R_FWD, in, y, ly.wp_fwd.p);
     op.bias = n->params.as<float>() + ly.bias_off;
     op.epi = ly.act == ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS;
     op.out_f32 = (float*)out.p;
@@ -408,13 +415,13 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   int64_t P = (int64_t)B * Ho * Wo;
   s.z[li].ensure((size_t)P * ly.Cout * ctx->esize());
   View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
-  if (li == 0 && s.used_im2col) run_conv_fwd(ctx, make_op_im2col(ly, R_FWD, s, z));
-  else run_conv_fwd(ctx, make_op(ly, R_FWD, in, z, ly.wp_fwd.p));
+  if (li == 0 && s.used_im2col) run_conv_fwd(ctx, make_op_im2col(ctx, ly, R_FWD, s, z));
+  else run_conv_fwd(ctx, make_op(ctx, ly, R_FWD, in, z, ly.wp_fwd.p));
   DropKey dk = drop_key(ctx, ly, s);
   // SURVEY 8d byte model: forward = read z + write activation = 2*s per element (statistics belong to the conv epilogue)
   ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * 2);
   if (ly.norm == NORM_NONE) {
-    launch_norm_apply(ctx->L(), ctx->dt, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, nullptr, ly.act, dk, out.p,
+    launch_norm_apply(ctx->L(), ctx->dtA, z.p, P, P, 1, Ho * Wo, ly.Cout, nullptr, nullptr, nullptr, ly.act, dk, out.p,
                       out.pitch, out.coff);
     return;
   }
@@ -426,15 +433,15 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
   float* pr = n->params.as<float>();
   float* mm = (ly.mov_off >= 0) ? n->mov.as<float>() + ly.mov_off : nullptr;
-  if (launch_bn_small_fwd(ctx->L(), ctx->dt, z.p, P, G, Ho * Wo, ly.Cout, ly.norm == NORM_BATCH ? BN_EPS : IN_EPS,
+  if (launch_bn_small_fwd(ctx->L(), ctx->dtA, z.p, P, G, Ho * Wo, ly.Cout, ly.norm == NORM_BATCH ? BN_EPS : IN_EPS,
                           pr + ly.g_off, pr + ly.b_off, st, st + gc,
                           st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM, ly.act, dk, out.p,
                           out.pitch, out.coff))
     return;
-  launch_norm_stats(ctx->L(), ctx->dt, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(),
+  launch_norm_stats(ctx->L(), ctx->dtA, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(),
                     ly.norm == NORM_BATCH ? BN_EPS : IN_EPS, pr + ly.g_off, pr + ly.b_off, st, st + gc, st + 2 * gc,
                     st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
-  launch_norm_apply(ctx->L(), ctx->dt, z.p, P, Pg, G, Ho * Wo, ly.Cout, st, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
+  launch_norm_apply(ctx->L(), ctx->dtA, z.p, P, Pg, G, Ho * Wo, ly.Cout, st, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
                     out.pitch, out.coff);
 }
 
@@ -463,18 +470,18 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
     float* dbeta = (gr && ly.norm != NORM_NONE) ? gr + ly.b_off : ctx->junk.as<float>() + 1024;
     if (ly.norm != NORM_NONE) ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
     ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 3 : 5));
-    launch_norm_bwd(ctx->L(), ctx->dt, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
+    launch_norm_bwd(ctx->L(), ctx->dtA, ctx->dtG, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
                     st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
                     ctx->stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
   }
   if (want_wgrad) {
-    ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ly, R_WGRAD, s, dz) : make_op(ly, R_WGRAD, in, dz, nullptr);
+    ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_WGRAD, s, dz) : make_op(ctx, ly, R_WGRAD, in, dz, nullptr);
     op.dW = n->grads.as<float>() + ly.w_off;
     run_conv_wgrad(ctx, op);
   }
   if (din.p != nullptr) {
     GAN_REQUIRE(ly.need_dgrad, "dgrad weights not packed");
-    run_conv_fwd(ctx, make_op(ly, R_DGRAD, din, dz, ly.wp_dgrad.p));
+    run_conv_fwd(ctx, make_op(ctx, ly, R_DGRAD, din, dz, ly.wp_dgrad.p));
   }
 }
 
@@ -509,7 +516,7 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   if (s.used_im2col) {
     s.im2col[0] = cached_im2col(ctx, x_f32, B, H, W, C);
   } else {
-    launch_convert(ctx->L(), ctx->dt, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
+    launch_convert(ctx->L(), ctx->dtA, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
   }
   // concat buffers: cat[k-1] = [up_k output (UP_F[k-1]) | down_{8-k} output (DOWN_F[7-k])] at H/2^(8-k)
   for (int k = 1; k <= 7; ++k) {
@@ -557,7 +564,7 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
                           gr + g->layers[15].bias_off);
   } else {
     s.dlogit.ensure((size_t)B * H * W * Cp * es);
-    launch_ghead_bwd(ctx->L(), ctx->dt, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
+    launch_ghead_bwd(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
                      gr + g->layers[15].bias_off);
   }
   for (int k = 1; k <= 7; ++k) {
@@ -572,11 +579,11 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
       // G = im2col(dz): [B*(H/2)*(W/2)][tap*C+co]; dW (kh,kw,co,ci) = G^T x; dx = G f
       View x = s.in_views[15];
       View G = make_view(s.gcols.p, B, H / 2, W / 2, 64);
-      ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 64, nullptr);
+      ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 64, nullptr, ctx->dtA, ctx->dtG);
       wg.dW = gr + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = C;
       wg.real_n = 16 * C;
       run_conv_wgrad(ctx, wg);
-      ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p);
+      ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p, ctx->dtG, ctx->dtG);
       dg.real_k = 16 * C;
       run_conv_fwd(ctx, dg);
     } else {
@@ -636,8 +643,8 @@ static void discriminator_forward(gan_net* d, int slot, const float* inp, const 
     s.im2col[0] = cached_im2col(ctx, inp, B, H, W, C);
     if (tar) s.im2col[1] = cached_im2col(ctx, tar, B, H, W, C);
   } else {
-    launch_convert(ctx->L(), ctx->dt, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
-    if (tar) launch_convert(ctx->L(), ctx->dt, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
+    launch_convert(ctx->L(), ctx->dtA, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
+    if (tar) launch_convert(ctx->L(), ctx->dtA, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
   }
   View in = make_view(s.in0.p, B, H, W, C0);
   int h = H, w = W;
@@ -671,12 +678,12 @@ static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool w
       launch_dhead_unfold(ctx->L(), s.dlogit.p, lh.Cout_p, B, in.H, in.W, s.gcols.p);
       View G = make_view(s.gcols.p, B, in.H, in.W, 64);
       if (want_wgrad) {
-        ConvOp wg = make_op_1tap(in, lh.Cin, G, 64, 64, nullptr);
+        ConvOp wg = make_op_1tap(in, lh.Cin, G, 64, 64, nullptr, ctx->dtA, ctx->dtG);
         wg.dW = d->grads.as<float>() + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = 1;
         wg.real_n = 16;
         run_conv_wgrad(ctx, wg);
       }
-      ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p);
+      ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p, ctx->dtG, ctx->dtG);
       dg.real_k = 16;
       run_conv_fwd(ctx, dg);
       continue;
@@ -694,7 +701,7 @@ static void disc_bce(gan_net* d, int slot, float label, float coef, bool make_dz
   int64_t n = logits_count(s);
   const int dzp = d->layers[4].Cout_p;
   if (make_dz) s.dlogit.ensure((size_t)n * dzp * ctx->esize());
-  launch_bce(ctx->L(), ctx->dt, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr, dzp,
+  launch_bce(ctx->L(), ctx->dtG, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr, dzp,
              (make_dz && bias_grad) ? d->grads.as<float>() + d->layers[4].bias_off : nullptr, ctx->loss_ws.as<float>(),
              loss_slot);
 }
@@ -781,10 +788,10 @@ static void adam_apply(gan_adam* o, bool reduced = false) {
              o->lr, o->b1, o->b2, (float)o->eps, 1.f / (float)ctx->world};
   // fused update + repack: 28 B/param of optimizer traffic + 4 B/param for the two packed bf16 copies
   ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
-  launch_adam_pack(ctx->L(), ctx->dt, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
+  launch_adam_pack(ctx->L(), ctx->dtA, ctx->dtG, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
   launch_adam_ranges(ctx->L(), a, (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
   // the few small special layouts (first-layer im2col order, head cols operands)
-  for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), ctx->dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
+  for (auto& gt : n->gathers) launch_gather_pack(ctx->L(), gt.dt, n->params.as<float>(), gt.idx.as<int>(), gt.n, gt.dst);
   n->packed_dirty = false;
 }
 static void finish_losses(gan_ctx* ctx, const LossMix& mix, float* losses_host) {
@@ -1050,6 +1057,14 @@ int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
                                                               std::to_string(prop.minor) + ", this library is sm_100a only");
   gan_ctx* c = new gan_ctx();
   c->device = device; c->dt = precision == GAN_FP32 ? DT_F32 : DT_BF16; c->seed = seed;
+  if (c->dt == DT_F32) { c->dtA = DT_F32; c->dtG = DT_F32; }
+  else {
+    // 16-bit mode: fp16 activations / forward weights, bf16 gradients (common.cuh).  GAN_B200_ACT=bf16 stores the
+    // activations as bf16 too (round 1's numerics: 8x the forward rounding error; kept for A/B measurements).
+    const char* e = getenv("GAN_B200_ACT");
+    c->dtA = (e && strcmp(e, "bf16") == 0) ? DT_BF16 : DT_F16;
+    c->dtG = DT_BF16;
+  }
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost((void**)&c->loss_host, 16 * 4));
   c->call_dev.ensure(16);
@@ -1292,9 +1307,10 @@ int gan_net_debug_tensor(gan_net* net, int slot, const char* name, float* host_d
   GAN_REQUIRE(s.B > 0, "slot has no forward call yet");
   std::string nm(name);
   const void* src = nullptr; int pitch = 0, coff = 0, C = 0; int64_t P = 0; bool is_f32 = false;
+  int src_dt = ctx->dtA;
   if (nm == "out" && net->is_gen) { src = s.out_f32.p; C = net->C; P = (int64_t)s.B * s.H * s.W; pitch = C; is_f32 = true; }
   else if (nm == "logits" && !net->is_gen) { src = s.logits.p; C = 1; P = logits_count(s); pitch = 1; is_f32 = true; }
-  else if (nm == "din0" && !net->is_gen) { src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = net->Cin0_p; }
+  else if (nm == "din0" && !net->is_gen) { src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = net->Cin0_p; src_dt = ctx->dtG; }
   else {
     size_t dot = nm.rfind('.');
     GAN_REQUIRE(dot != std::string::npos, "debug tensor name must be <layer>.z or <layer>.a");
@@ -1315,7 +1331,7 @@ int gan_net_debug_tensor(gan_net* net, int slot, const char* name, float* host_d
     CUDA_CHECK(cudaMemcpy(host_dst, src, P * C * 4, cudaMemcpyDeviceToHost));
   } else {
     DevBuf tmp; tmp.ensure((size_t)P * C * 4);
-    launch_export(ctx->L(), ctx->dt, src, pitch, coff, P, C, tmp.as<float>());
+    launch_export(ctx->L(), src_dt, src, pitch, coff, P, C, tmp.as<float>());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     CUDA_CHECK(cudaMemcpy(host_dst, tmp.p, P * C * 4, cudaMemcpyDeviceToHost));
   }
@@ -1600,31 +1616,31 @@ int gan_op_conv(gan_ctx* ctx, int kind, int role, int engine, const float* a, co
       weight_strides(ly, role, po.Kc, po.Nc, po.Kr, po.Nr, po.s_tap, po.s_k, po.s_n);
       for (int c = 0; c < po.ncls; ++c) po.cls[c].b_off = (int64_t)c * po.Nc * po.cls[c].ntaps * po.Kc;
       wp.ensure((size_t)16 * cin_p * cout_p * es);
-      launch_pack(L, ctx->dt, fb.as<float>(), wp.p, po);
+      launch_pack(L, role == R_FWD ? ctx->dtA : ctx->dtG, fb.as<float>(), wp.p, po);
       if (role == R_FWD) {
         up(fa, a, nx);
-        launch_convert(L, ctx->dt, fa.as<float>(), px, cin, x.p, cin_p, 0);
-        run_conv_fwd(ctx, make_op(ly, R_FWD, x, y, wp.p));
+        launch_convert(L, ctx->dtA, fa.as<float>(), px, cin, x.p, cin_p, 0);
+        run_conv_fwd(ctx, make_op(ctx, ly, R_FWD, x, y, wp.p));
         fo.ensure((size_t)ny * 4);
-        launch_export(L, ctx->dt, y.p, cout_p, 0, py, cout, fo.as<float>());
+        launch_export(L, ctx->dtA, y.p, cout_p, 0, py, cout, fo.as<float>());
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         CUDA_CHECK(cudaMemcpy(out, fo.p, ny * 4, cudaMemcpyDeviceToHost));
       } else {
         up(fa, a, ny);
-        launch_convert(L, ctx->dt, fa.as<float>(), py, cout, y.p, cout_p, 0);
-        run_conv_fwd(ctx, make_op(ly, R_DGRAD, x, y, wp.p));
+        launch_convert(L, ctx->dtG, fa.as<float>(), py, cout, y.p, cout_p, 0);
+        run_conv_fwd(ctx, make_op(ctx, ly, R_DGRAD, x, y, wp.p));
         fo.ensure((size_t)nx * 4);
-        launch_export(L, ctx->dt, x.p, cin_p, 0, px, cin, fo.as<float>());
+        launch_export(L, ctx->dtG, x.p, cin_p, 0, px, cin, fo.as<float>());
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         CUDA_CHECK(cudaMemcpy(out, fo.p, nx * 4, cudaMemcpyDeviceToHost));
       }
     } else {
       up(fa, a, nx); up(fb, b, ny);
-      launch_convert(L, ctx->dt, fa.as<float>(), px, cin, x.p, cin_p, 0);
-      launch_convert(L, ctx->dt, fb.as<float>(), py, cout, y.p, cout_p, 0);
+      launch_convert(L, ctx->dtA, fa.as<float>(), px, cin, x.p, cin_p, 0);
+      launch_convert(L, ctx->dtG, fb.as<float>(), py, cout, y.p, cout_p, 0);
       fo.ensure((size_t)nw * 4);
       CUDA_CHECK(cudaMemsetAsync(fo.p, 0, nw * 4, ctx->stream));
-      ConvOp op = make_op(ly, R_WGRAD, x, y, nullptr);
+      ConvOp op = make_op(ctx, ly, R_WGRAD, x, y, nullptr);
       op.dW = fo.as<float>();
       run_conv_wgrad(ctx, op);
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

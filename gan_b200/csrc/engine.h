@@ -40,7 +40,9 @@ struct ProfEntry { cudaEvent_t a, b; int fam; double work; };
 
 struct gan_ctx {
   int device = 0;
-  int dt = DT_F32;
+  int dt = DT_F32;            // mode: DT_F32 (FFMA parity mode) or DT_BF16 (= the 16-bit tcgen05 mode)
+  int dtA = DT_F32;           // storage dtype of activations / forward weight packs (16-bit mode: DT_F16, see common.cuh)
+  int dtG = DT_F32;           // storage dtype of gradients / data-gradient weight packs (16-bit mode: DT_BF16)
   cudaStream_t stream = nullptr;
   uint64_t seed = 0;
   uint32_t call_counter = 0;
@@ -153,7 +155,7 @@ struct gan_net {
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
   int pack_nent = 0, pack_tiles = 0;
   // extra packed copies through index tables: first layer in im2col K order, head as cols GEMM operands
-  struct GatherTab { DevBuf idx; void* dst = nullptr; int n = 0; };
+  struct GatherTab { DevBuf idx; void* dst = nullptr; int n = 0; int dt = DT_F32; };
   std::vector<GatherTab> gathers;
   DevBuf adam_tab, adam_ranges;   // fused Adam+pack tables (AdamPackEntry / AdamRange)
   int adam_nent = 0, adam_tiles = 0, adam_nranges = 0;

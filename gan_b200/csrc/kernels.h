@@ -16,7 +16,7 @@ void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* 
 // dst[i] = master[idx[i]] (idx < 0 -> 0): small special weight layouts via a device index table
 void launch_gather_pack(Launch L, int dt, const float* master, const int* idx_dev, int n, void* dst);
 // fp32 NHWC image -> bf16 im2col rows of the 4x4 stride-2 'same' window: dst[m][t*4 + c], 64 per row (slots >= C zero)
-void launch_im2col(Launch L, const float* src, int B, int H, int W, int C, void* dst_bf16);
+void launch_im2col(Launch L, int dt_rows, const float* src, int B, int H, int W, int C, void* dst_rows);
 // Same rows from a bf16 image with pixel pitch `pitch` (generator-head gradient dz): G[m][t*4 + c]
 // Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*4 + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
@@ -50,7 +50,7 @@ void launch_norm_apply(Launch L, int dt, const void* z, int64_t P, int64_t Pg, i
                        int out_pitch, int out_coff);
 struct GradSrc { const void* p; int pitch, coff; };
 // Backward of (norm -> dropout -> activation): dz, plus dgamma/dbeta accumulated into the grad buffer.
-void launch_norm_bwd(Launch L, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
+void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz);
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
@@ -73,7 +73,7 @@ struct PackOp { int ncls; ClassGeom cls[4]; int Kc, Nc, Kr, Nr; int64_t s_tap, s
 void launch_pack(Launch L, int dt, const float* master, void* dst, const PackOp& op);
 // All layers / roles of a net in ONE launch: 32x32 tiles, transposed through shared memory when the
 // master layout is contiguous along the packed N index.  `tab` is a device array of PackEntry.
-struct PackEntry { PackOp op; const float* master; void* dst; int tiles_k, tiles_n, tile_begin, pad; };
+struct PackEntry { PackOp op; const float* master; void* dst; int tiles_k, tiles_n, tile_begin, dt16; };   // dt16: DT_F16 | DT_BF16 of a 16-bit destination
 void launch_pack_multi(Launch L, int dt, const PackEntry* tab_dev, int nent, int total_tiles);
 void launch_scale(Launch L, float* p, int64_t n, float s);
 // Fused Keras-Adam + weight packing: one pass over every convolution kernel of a net (32x32 tiles of
@@ -91,12 +91,12 @@ struct AdamPackEntry {
 };
 struct AdamRange { long long off; int n, pad; };
 struct AdamArgs { float* p; const float* g; float* m; float* v; const long long* t_dev; double lr, b1, b2; float eps, gscale; };
-void launch_adam_pack(Launch L, int dt, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles);
+void launch_adam_pack(Launch L, int dt_fwd, int dt_dgrad, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles);
 void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, int nranges);
 
 // ---- conv_ffma.cu ---------------------------------------------------------------------------
 void launch_conv_fwd_ffma(Launch L, int dt, const ConvOp& op);
-void launch_conv_wgrad_ffma(Launch L, int dt, const ConvOp& op);
+void launch_conv_wgrad_ffma(Launch L, int dt_in, int dt_dy, const ConvOp& op);
 
 // ---- conv_umma.cu ---------------------------------------------------------------------------
 struct UmmaPlan;   // opaque: tensor maps + tiling for one (op, batch) pair

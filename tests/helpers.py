@@ -46,6 +46,16 @@ def bf16_round(a):
     return torch.tensor(np.asarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
 
 
+def f16_round(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32)).to(torch.float16).to(torch.float32).numpy()
+
+
+def act_round(a, act="f16"):
+    """Rounding the device applies to ACTIVATION-side operands (layer inputs, forward weights) in the 16-bit mode:
+    fp16 by default, bf16 under GAN_B200_ACT=bf16.  Gradient-side operands are always bf16 (common.cuh)."""
+    return f16_round(a) if act == "f16" else bf16_round(a)
+
+
 def make_pix2pix(seed_w, channels, dtype):
     """Oracle-side Pix2Pix parameters (numpy lists) from default_rng(seed_w) in Keras variable order."""
     rng = np.random.default_rng(seed_w)

@@ -1,10 +1,18 @@
 """GPU parity of every convolution kernel family against the CPU oracle, through the C-ABI
 (gan_op_conv): Conv2D 4x4 s2 'same', ZeroPad+Conv2D 4x4 s1, Conv2DTranspose 4x4 s2 'same', each in
-forward / data-gradient / weight-gradient form, on the FFMA (fp32, bf16) and tcgen05 engines."""
+forward / data-gradient / weight-gradient form, on the FFMA (fp32, 16-bit) and tcgen05 engines.
+
+16-bit mode operand formats (common.cuh): forward = f16 activations x f16 weights -> f16; data gradient =
+bf16 gradients x bf16 weights -> bf16; weight gradient = f16 activations x bf16 gradients -> fp32 (one
+tcgen05.mma with different A and B formats).  The oracle is fed operands rounded the same way, so what is
+left is accumulation order and the rounding of the stored result.  Both activation formats are run
+(GAN_B200_ACT=bf16 is round 1's all-bf16 storage)."""
+import os
+
 import numpy as np
 import pytest
 
-from helpers import oracle_conv, oracle_conv_grads, rel_err, bf16_round
+from helpers import oracle_conv, oracle_conv_grads, rel_err, bf16_round, act_round
 
 pytestmark = pytest.mark.gpu
 
@@ -20,12 +28,32 @@ def ctx32():
     c.close()
 
 
-@pytest.fixture(scope="module")
-def ctx16():
+@pytest.fixture(scope="module", params=["f16", "bf16"])
+def ctx16(request):
     from gan_b200 import Context
+    old = os.environ.get("GAN_B200_ACT")
+    os.environ["GAN_B200_ACT"] = request.param          # read when the context is created
     c = Context(0, "bf16", 1)
+    c.act = request.param
+    if old is None:
+        del os.environ["GAN_B200_ACT"]
+    else:
+        os.environ["GAN_B200_ACT"] = old
     yield c
     c.close()
+
+
+def _refs(ctx, kind, x, wt, dy):
+    """Oracle results on operands rounded the way the device stores them."""
+    a = ctx.act
+    y_ref = oracle_conv(kind, act_round(x, a), act_round(wt, a)).numpy()
+    dx_ref, _ = oracle_conv_grads(kind, bf16_round(x), bf16_round(wt), bf16_round(dy))
+    _, dw_ref = oracle_conv_grads(kind, act_round(x, a), bf16_round(wt), bf16_round(dy))
+    return y_ref, dx_ref, dw_ref
+
+
+def _out_tol(ctx):
+    return 6e-3 if ctx.act == "bf16" else 1e-3          # rounding of the stored forward result (2^-9 vs 2^-12 relative)
 
 
 def _case(kind, b, h, w, cin, cout, seed=0):
@@ -61,9 +89,7 @@ def test_ffma_fp32_forward_dgrad_wgrad(ctx32, kind, b, h, w, cin, cout):
 @pytest.mark.parametrize("kind,b,h,w,cin,cout", SMALL[:3] + SMALL[5:6] + SMALL[8:10])
 def test_ffma_bf16_forward_dgrad_wgrad(ctx16, kind, b, h, w, cin, cout):
     x, wt, dy = _case(kind, b, h, w, cin, cout)
-    xq, wq, dyq = bf16_round(x), bf16_round(wt), bf16_round(dy)   # device sees bf16-rounded operands
-    y_ref = oracle_conv(kind, xq, wq).numpy()
-    dx_ref, dw_ref = oracle_conv_grads(kind, xq, wq, dyq)
+    y_ref, dx_ref, dw_ref = _refs(ctx16, kind, x, wt, dy)          # device sees rounded operands
     y = ctx16.op_conv(kind, 0, x, wt, b, h, w, cin, cout, engine=0)
     dx = ctx16.op_conv(kind, 1, dy, wt, b, h, w, cin, cout, engine=0)
     dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=0)
@@ -83,26 +109,23 @@ UMMA_CASES = [  # shapes where Kc and Nc are multiples of 64 (the tcgen05 tile c
 @pytest.mark.parametrize("kind,b,h,w,cin,cout", UMMA_CASES)
 def test_umma_forward_dgrad_match_oracle(ctx16, kind, b, h, w, cin, cout):
     x, wt, dy = _case(kind, b, h, w, cin, cout, seed=3)
-    xq, wq, dyq = bf16_round(x), bf16_round(wt), bf16_round(dy)
-    y_ref = oracle_conv(kind, xq, wq).numpy()
-    dx_ref, _ = oracle_conv_grads(kind, xq, wq, dyq)
+    y_ref, dx_ref, _ = _refs(ctx16, kind, x, wt, dy)
     y = ctx16.op_conv(kind, 0, x, wt, b, h, w, cin, cout, engine=1)
     dx = ctx16.op_conv(kind, 1, dy, wt, b, h, w, cin, cout, engine=1)
-    # bf16 output rounding is the only error source besides fp32 accumulation order
-    assert rel_err(y, y_ref) < 6e-3
+    # rounding of the stored output is the only error source besides fp32 accumulation order
+    assert rel_err(y, y_ref) < _out_tol(ctx16)
     assert rel_err(dx, dx_ref) < 6e-3
     # and the two engines agree to output rounding
     y_f = ctx16.op_conv(kind, 0, x, wt, b, h, w, cin, cout, engine=0)
-    assert rel_err(y, y_f) < 6e-3
+    assert rel_err(y, y_f) < _out_tol(ctx16)
 
 
 @pytest.mark.parametrize("kind,b,h,w,cin,cout", UMMA_CASES)
 def test_umma_wgrad_matches_oracle(ctx16, kind, b, h, w, cin, cout):
     x, wt, dy = _case(kind, b, h, w, cin, cout, seed=4)
-    xq, wq, dyq = bf16_round(x), bf16_round(wt), bf16_round(dy)
-    _, dw_ref = oracle_conv_grads(kind, xq, wq, dyq)
+    _, _, dw_ref = _refs(ctx16, kind, x, wt, dy)
     dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=1)
-    assert rel_err(dw, dw_ref) < 1e-4
+    assert rel_err(dw, dw_ref) < 1e-4        # f16 x bf16 operands, fp32 accumulate: exact products
 
 
 SMALLC = [  # first layers (Cin in {1,3,6}) and heads (Cout in {1,3}): channel-padded tcgen05 paths
@@ -115,12 +138,10 @@ SMALLC = [  # first layers (Cin in {1,3,6}) and heads (Cout in {1,3}): channel-p
 @pytest.mark.parametrize("kind,b,h,w,cin,cout", SMALLC)
 def test_umma_small_channel_layers(ctx16, kind, b, h, w, cin, cout):
     x, wt, dy = _case(kind, b, h, w, cin, cout, seed=6)
-    xq, wq, dyq = bf16_round(x), bf16_round(wt), bf16_round(dy)
-    y_ref = oracle_conv(kind, xq, wq).numpy()
-    dx_ref, dw_ref = oracle_conv_grads(kind, xq, wq, dyq)
+    y_ref, dx_ref, dw_ref = _refs(ctx16, kind, x, wt, dy)
     y = ctx16.op_conv(kind, 0, x, wt, b, h, w, cin, cout, engine=1)
     dx = ctx16.op_conv(kind, 1, dy, wt, b, h, w, cin, cout, engine=1)
     dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=1)
-    assert rel_err(y, y_ref) < 6e-3
+    assert rel_err(y, y_ref) < _out_tol(ctx16)
     assert rel_err(dx, dx_ref) < 6e-3
     assert rel_err(dw, dw_ref) < 1e-4

@@ -197,9 +197,10 @@ def _cos(a, b):
 
 
 def test_bf16_step_tracks_oracle():
-    """bf16/tcgen05 path (BASELINE.json: <=1e-2 relative on generator output and losses after N steps).
-    Batch 8, N=3 train steps from identical weights, inputs and dropout masks:
-      * step 0 (identical weights): generator output ||dev-ref||_2/||ref||_2 <= 1e-2, losses <= 1e-2,
+    """16-bit tcgen05 path (BASELINE.json: <=1e-2 relative on generator output and losses after N steps).
+    Batch 8, N=3 train steps from identical weights, inputs and dropout masks (the benchmarked batch 64 and
+    N=10 are in test_gpu_parity_configs.py):
+      * step 0 (identical weights): generator output max-rel <= 1e-2 and L2 <= 5e-3, losses <= 1e-2,
         gradients point the same way (cosine >= 0.95 for every conv kernel; measured 0.969..1.000);
       * after every one of the N=3 steps the four losses stay within 1e-2 of the free-running float64
         oracle;
@@ -220,7 +221,7 @@ def test_bf16_step_tracks_oracle():
     ref = O.generator_forward(gp, xt, "batchnorm", masks).detach().numpy()
     l2 = float(np.linalg.norm(out - ref) / np.linalg.norm(ref))
     print(f"bf16 step 0: gen_out l2_rel={l2:.3e} max_rel={rel_err(out, ref):.3e}")
-    assert l2 < 1e-2 and rel_err(out, ref) < 3e-2
+    assert l2 < 5e-3 and rel_err(out, ref) < 1e-2       # SURVEY 8c metric (max-rel) and L2; fp16 activations: measured ~1e-3
     for step in range(3):
         masks = O.generator_keep_masks(SEED, m.ctx.call_counter(), 0, B, 256)
         losses = m.train_step(x, y, True)
@@ -240,9 +241,8 @@ def test_bf16_step_tracks_oracle():
     l2_free = float(np.linalg.norm(out - ref_free) / np.linalg.norm(ref_free))
     l2_sync = float(np.linalg.norm(out - ref_sync) / np.linalg.norm(ref_sync))
     print(f"bf16 after 3 steps: gen_out l2_rel vs oracle at device weights={l2_sync:.3e}, vs free-running oracle={l2_free:.3e}")
-    # measured 9.95e-3 (deterministic up to fp32 atomic order in the weight gradients); 16 stacked bf16 layers sit
-    # right at the 1e-2 target, so the bound leaves 10% head-room instead of flaking on the last digit
-    assert l2_sync < 1.1e-2
+    # the forward arithmetic at the device's own weights holds the stated tolerance with margin (fp16 activations)
+    assert l2_sync < 5e-3 and rel_err(out, ref_sync) < 1e-2
     m.ctx.close()
 
 
