@@ -64,6 +64,7 @@ SIGNATURES = {
     "gan_adam_set_state": (C.c_int, [_vp, C.c_int, _vp]),
     "gan_adam_set_hyper": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "gan_pix2pix_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]),
+    "gan_pix2pix_train_step_ex": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp]),
     "gan_cyclegan_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float,
                                           C.c_int, _vp]),
     "gan_ctx_last_losses": (C.c_int, [_vp, _vp, C.c_int]),

@@ -823,8 +823,11 @@ static void loss_ws_reset(gan_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------
 // Pix2Pix.train_step (pix2pix.py:190-218)
 // ---------------------------------------------------------------------------------------------
+// gan_scale: factor on the adversarial term of the GENERATOR gradient only (1 for the default 'l1' loss; the
+// reference's 'ssim' branch makes the total loss a per-image vector, whose tape.gradient is the gradient of the SUM
+// over the batch = B x d(gan_loss), pix2pix.py:182-186,210).
 static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, const float* x_in, const float* y_in, int B,
-                         float lambda, int training, float* losses) {
+                         float lambda, float gan_scale, int training, float* losses) {
   gan_ctx* ctx = g->ctx;
   GAN_REQUIRE(d->ctx == ctx, "nets belong to different contexts");
   GAN_REQUIRE(g->is_gen && !d->is_gen && d->target, "pix2pix needs a generator and a target=True discriminator");
@@ -853,7 +856,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
     discriminator_backward(d, 1, true, false);
     comm_allreduce_async(ctx, d->grads.as<float>(), d->nparams);          // D gradients final: reduce under G's backward
   }
-  disc_bce(d, 1, 1.f, 1.0f, training, false, 0);
+  disc_bce(d, 1, 1.f, gan_scale, training, false, 0);
   if (training) {
     discriminator_backward(d, 1, false, true);                           // dL_G/d(gen_output) through D (:210)
     GradSrc dgan{d->slots[1].din0.p, d->Cin0_p, C};
@@ -1422,24 +1425,32 @@ int gan_adam_set_state(gan_adam* opt, int which, const float* host_src) {
   API_END
 }
 
-int gan_pix2pix_train_step(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_opt, const float* input_image,
-                           const float* target, int batch, float lambda, int training, float losses[4]) {
+int gan_pix2pix_train_step_ex(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_opt, const float* input_image,
+                              const float* target, int batch, float l1_weight, float gan_grad_scale, int training,
+                              float losses[4]) {
   API_BEGIN
   GAN_REQUIRE(g && d && input_image && target, "null argument");
   GAN_REQUIRE(!training || (g_opt && d_opt && g_opt->net == g && d_opt->net == d), "optimizers do not match the nets");
   gan_ctx* ctx = g->ctx;
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (!ctx->graphs || ctx->profile) {
-    pix2pix_step(g, d, g_opt, d_opt, input_image, target, batch, lambda, training, losses);
+    pix2pix_step(g, d, g_opt, d_opt, input_image, target, batch, l1_weight, gan_grad_scale, training, losses);
   } else {
-    char key[160];
-    snprintf(key, sizeof(key), "p2p:%p:%p:%p:%p:%d:%d:%g", (void*)g, (void*)d, (void*)g_opt, (void*)d_opt, batch, training, (double)lambda);
+    char key[200];
+    snprintf(key, sizeof(key), "p2p:%p:%p:%p:%p:%d:%d:%g:%g", (void*)g, (void*)d, (void*)g_opt, (void*)d_opt, batch, training,
+             (double)l1_weight, (double)gan_grad_scale);
     const size_t img_bytes = (size_t)batch * g->H * g->W * g->C * 4;
     run_step_graphed(ctx, key, input_image, target, img_bytes, losses, 4, std::vector<gan_net*>{g, d},
                      training ? std::vector<gan_adam*>{g_opt, d_opt} : std::vector<gan_adam*>{},
-                     [&](const float* xs, const float* ys) { pix2pix_step(g, d, g_opt, d_opt, xs, ys, batch, lambda, training, nullptr); });
+                     [&](const float* xs, const float* ys) {
+                       pix2pix_step(g, d, g_opt, d_opt, xs, ys, batch, l1_weight, gan_grad_scale, training, nullptr);
+                     });
   }
   API_END
+}
+int gan_pix2pix_train_step(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_opt, const float* input_image,
+                           const float* target, int batch, float lambda, int training, float losses[4]) {
+  return gan_pix2pix_train_step_ex(g, d, g_opt, d_opt, input_image, target, batch, lambda, 1.0f, training, losses);
 }
 
 int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_adam* g_opt, gan_adam* f_opt,

@@ -2,13 +2,14 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
 
 from . import _ffi, input_pipeline
 from .base_gan import GAN, LossValue, _as_f32
-from .utils import cyclegan_losses
+from .utils import cyclegan_losses, save_panel
 
 
 class CycleGAN(GAN):
@@ -85,15 +86,64 @@ class CycleGAN(GAN):
         return input_pipeline.prefetch(self.ctx, packed_x[0], packed_x[1], self._xforms(images_x, train, rng),
                                        packed_y[0], packed_y[1], self._xforms(images_y, train, rng), c, s)
 
+    def image_pipeline(self, predict: bool = False):
+        """Reference cycle_gan.py:87-152: list the two unpaired directories, the seeded test/val/train split
+        (``random.seed(seed)``; test from X only; val sizes ceil(n*validation_size)), per-iteration shuffling of the
+        train and val sets (tf.data ``shuffle(buffer_size, reshuffle_each_iteration=True)``: the order itself is not
+        reproducible across frameworks), batching without drop_remainder.  Decoding is PIL on the host, every pixel
+        operation runs on the device.  Returns (train_X, train_Y, val_X, val_Y, test)."""
+        import random
+        cfg = self.config
+        contents_X = input_pipeline.list_images(cfg['input_images'])
+        assert contents_X, "No images found in input image directory!"
+        full = lambda d, names: [os.path.join(d, i) for i in names]   # noqa: E731
+        if predict:
+            return self._batches(full(cfg['input_images'], contents_X), 1, False, False, squeeze=True), None, None, None, None
+        contents_Y = input_pipeline.list_images(cfg['target_images'])
+        assert contents_Y, "No images found in target image directory!"
+        random.seed(cfg['seed'])
+        test = random.sample(contents_X, cfg['test_img'])
+        val_obs_X = np.ceil((len(contents_X) - cfg['test_img']) * cfg['validation_size'])
+        val_obs_Y = np.ceil(len(contents_Y) * cfg['validation_size'])
+        val_X = random.sample([i for i in contents_X if i not in test], int(val_obs_X))
+        val_Y = random.sample([i for i in contents_Y], int(val_obs_Y))
+        train_X = [i for i in contents_X if i not in test and i not in val_X]
+        train_Y = [i for i in contents_Y if i not in val_Y]
+        bs, dx, dy = cfg['batch_size'], cfg['input_images'], cfg['target_images']
+        return (self._batches(full(dx, train_X), bs, True, True), self._batches(full(dy, train_Y), bs, True, True),
+                self._batches(full(dx, val_X), bs, False, True), self._batches(full(dy, val_Y), bs, False, True),
+                self._batches(full(dx, test), bs, False, False))
+
+    def _batches(self, files, batch_size, train, shuffle, squeeze=False):
+        rng = np.random.default_rng(int(self.config.get('seed', 123)) + 2)
+        c = int(self.config['channels'])
+
+        class _DS:
+            def __iter__(ds):
+                order = list(rng.permutation(len(files))) if shuffle else list(range(len(files)))
+                for i in range(0, len(order), batch_size):
+                    ims = [input_pipeline.load(files[j], c) for j in order[i:i + batch_size]]
+                    a = self.process_images(ims, train, rng)
+                    yield a[0] if squeeze else a
+
+            def __len__(ds):
+                return (len(files) + batch_size - 1) // batch_size
+        return _DS()
+
     def generate_images(self, model, test_input, path_filename: str = None):
-        """Forward call of reference cycle_gan.py:179-186."""
+        """Reference cycle_gan.py:179-204: ``model(test_input, training=True)`` and the two-panel figure (input,
+        prediction) written as a PNG panel through PIL (or .npy for another suffix)."""
         prediction = model(test_input, training=True)
         if path_filename:
-            np.save(path_filename, prediction)
+            if path_filename.lower().endswith(".png"):
+                save_panel(path_filename, [np.asarray(test_input)[0], prediction[0]], int(self.config['channels']))
+            else:
+                np.save(path_filename, prediction)
         return prediction
 
     def fit(self, train_X, train_Y, val_X, val_Y, test=None, output_path: str = None, checkpoint_manager=None):
         """Reference cycle_gan.py:278-358 (zip of the X and Y batch iterables)."""
+        example = next(iter(test), None) if (test is not None and output_path) else None     # cycle_gan.py:283
         start = time.time()
         train_cost_functions, val_cost_functions = cyclegan_losses(), cyclegan_losses()
         keys = list(train_cost_functions.keys())
@@ -113,6 +163,9 @@ class CycleGAN(GAN):
             last = (epoch + 1) == self.config['epochs']
             if checkpoint_manager is not None and (((epoch + 1) % 5 == 0) or last):
                 checkpoint_manager.save()
+            if example is not None and (epoch + 1) % 5 == 0 and not last and self.ctx.rank == 0:
+                self.generate_images(self.generator_g, np.asarray(example)[:1],
+                                     path_filename=os.path.join(output_path, 'test_images', f"epoch_{epoch + 1}.png"))
             print(f'\nCumulative training duration at end of epoch {epoch + 1}: {(time.time() - start) / 60:.2f} min')
         return train_cost_functions, val_cost_functions
 

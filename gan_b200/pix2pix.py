@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _ffi, input_pipeline
 from .base_gan import GAN, LossValue, _as_f32
-from .utils import pix2pix_losses
+from .utils import pix2pix_losses, save_panel, ssim
 
 
 class Pix2Pix(GAN):
@@ -32,9 +32,12 @@ class Pix2Pix(GAN):
         """Reference pix2pix.py:167-188 on host arrays (default 'l1' branch).  ``train_step`` fuses
         the same arithmetic on the device; this method exists for API parity."""
         gan_loss = self.loss_obj(np.ones_like(disc_generated_output), disc_generated_output)
-        if self.config.get('generator_loss', 'l1') != 'l1':
-            raise NotImplementedError("only the default generator_loss='l1' is on the accelerated path")
-        gan_loss2 = float(np.mean(np.abs(np.asarray(target, np.float64) - np.asarray(gen_output, np.float64))))
+        if self.config.get('generator_loss', 'l1') == 'l1':
+            gan_loss2 = float(np.mean(np.abs(np.asarray(target, np.float64) - np.asarray(gen_output, np.float64))))
+        else:
+            # 'ssim' exactly as the reference wrote it (pix2pix.py:182-184): SSIM of the INPUT against the target with
+            # max_val=255 on [-1,1] data — a per-image VECTOR that does not depend on the generator
+            gan_loss2 = ssim(input_image, target, max_val=255, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03)
         return gan_loss + self.config.get('lambda', 100) * gan_loss2, gan_loss, gan_loss2
 
     def train_step(self, input_image, target, training: bool = True, sync: bool = True):
@@ -45,8 +48,6 @@ class Pix2Pix(GAN):
         CUDA).  Returns (gen_total_loss, gen_gan_loss, gen_gan_loss2, disc_loss) as LossValue
         (``.numpy()`` works like on tf scalars).  ``sync=False`` only enqueues the step and returns
         None; read the losses later with ``self.ctx.last_losses(4)``."""
-        if self.config.get('generator_loss', 'l1') != 'l1':
-            raise NotImplementedError("only the default generator_loss='l1' is on the accelerated path")
         x, y = _as_f32(input_image), _as_f32(target)
         if tuple(x.shape) != tuple(y.shape):
             raise ValueError("input_image and target must have the same shape")
@@ -54,11 +55,22 @@ class Pix2Pix(GAN):
         g_opt = self.generator_optimizer.bind(self.generator)
         d_opt = self.discriminator_optimizer.bind(self.discriminator)
         losses = np.zeros(4, dtype=np.float32) if sync else None
-        _ffi.check(_ffi.lib().gan_pix2pix_train_step(
+        lam = float(self.config.get('lambda', 100))
+        use_ssim = self.config.get('generator_loss', 'l1') != 'l1'
+        # 'ssim' (pix2pix.py:182-186): gan_loss2 = SSIM(input, target) is a constant per-image vector, so the generator
+        # gradient is that of sum_b(gan_loss + lambda*ssim_b) = batch * d(gan_loss): no L1 term, adversarial term x batch
+        l1_weight, gan_scale = (0.0, float(b)) if use_ssim else (lam, 1.0)
+        _ffi.check(_ffi.lib().gan_pix2pix_train_step_ex(
             self.generator.handle, self.discriminator.handle, g_opt, d_opt, _ffi.ptr_of(x), _ffi.ptr_of(y), b,
-            C.c_float(float(self.config.get('lambda', 100))), int(bool(training)), _ffi.ptr_of(losses)))
+            C.c_float(l1_weight), C.c_float(gan_scale), int(bool(training)), _ffi.ptr_of(losses)))
         if not sync:
             return None
+        if use_ssim:
+            if hasattr(x, "cpu"):
+                x, y = x.cpu().numpy(), y.cpu().numpy()
+            s = ssim(x, y, max_val=255, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03).astype(np.float32)
+            # the reference returns VECTORS for the total and the secondary loss in this branch
+            return (float(losses[1]) + np.float32(lam) * s, LossValue(losses[1]), s, LossValue(losses[3]))
         return tuple(LossValue(v) for v in losses)
 
     # -- input pipeline on the device (reference pix2pix.py:34-112) ---------------------------------
@@ -142,17 +154,25 @@ class Pix2Pix(GAN):
         return _DS()
 
     def generate_images(self, model, test_input, tar=None, path_filename: str = None):
-        """Forward call of reference pix2pix.py:220-228 (``model(test_input, training=True)``);
-        the matplotlib rendering is out of scope — the prediction is returned (and saved as .npy
-        when a filename is given)."""
+        """Reference pix2pix.py:220-246: ``model(test_input, training=True)`` and the three-panel figure
+        (input, ground truth, prediction; values x*0.5+0.5) written to ``path_filename`` — as a PNG panel through PIL
+        (matplotlib is not a dependency), or the raw prediction as .npy for any other suffix.  The prediction is
+        also returned."""
         prediction = model(test_input, training=True)
         if path_filename:
-            np.save(path_filename, prediction)
+            if path_filename.lower().endswith(".png"):
+                panels = [np.asarray(test_input)[0]] + ([np.asarray(tar)[0]] if tar is not None else []) + [prediction[0]]
+                save_panel(path_filename, panels, int(self.config['channels']))
+            else:
+                np.save(path_filename, prediction)
         return prediction
 
     def fit(self, train_ds, val_ds, test_ds=None, output_path: str = None, checkpoint_manager=None):
         """Reference pix2pix.py:248-323: per-epoch mean of each loss over mini-batches, validation
         through ``train_step(..., False)``.  Datasets are iterables of (input, target) batches."""
+        example = None
+        if test_ds is not None and output_path:
+            example = next(iter(test_ds), None)            # example_input, example_target (pix2pix.py:260)
         start = time.time()
         train_cost_functions, val_cost_functions = pix2pix_losses(), pix2pix_losses()
         keys = list(train_cost_functions.keys())
@@ -172,12 +192,19 @@ class Pix2Pix(GAN):
             last = (epoch + 1) == self.config['epochs']
             if checkpoint_manager is not None and (((epoch + 1) % 5 == 0) or last):
                 checkpoint_manager.save()
+            # every 5 epochs (not the last): predicted image of the first test example (pix2pix.py:307-313)
+            if example is not None and (epoch + 1) % 5 == 0 and not last and self.ctx.rank == 0:
+                self.generate_images(self.generator, np.asarray(example[0])[:1], np.asarray(example[1])[:1],
+                                     path_filename=os.path.join(output_path, 'test_images', f"epoch_{epoch + 1}.png"))
             print(f'\nCumulative training duration at end of epoch {epoch + 1}: {(time.time() - start) / 60:.2f} min')
         return train_cost_functions, val_cost_functions
 
     def predict(self, predict_ds, output_path: str = None):
-        """Reference pix2pix.py:325-339: batch-1 generator forward per (input, target) pair."""
+        """Reference pix2pix.py:325-339: batch-1 generator forward per (input, target) pair; with ``output_path``
+        the panels are written to ``<output_path>/prediction_images/img<k>.png`` as the reference does."""
         outs = []
-        for i in predict_ds:
-            outs.append(self.generate_images(self.generator, np.expand_dims(np.asarray(i[0]), axis=0)))
+        for k, i in enumerate(predict_ds):
+            fn = os.path.join(output_path, 'prediction_images', f"img{k}.png") if output_path else None
+            outs.append(self.generate_images(self.generator, np.expand_dims(np.asarray(i[0]), axis=0),
+                                             np.expand_dims(np.asarray(i[1]), axis=0), fn))
         return outs

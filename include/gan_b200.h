@@ -143,6 +143,14 @@ GAN_API int gan_adam_set_hyper(gan_adam* opt, double lr, double beta1, double be
 GAN_API int gan_pix2pix_train_step(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_opt,
                            const float* input_image, const float* target, int batch,
                            float lambda, int training, float losses[4]);
+/* Same step with the two weights of the generator objective spelled out: l1_weight multiplies mean|target-G(x)| in
+ * both the reported total and the gradient (lambda for the default generator_loss='l1'); gan_grad_scale multiplies
+ * the adversarial term of the GENERATOR gradient only.  The reference's generator_loss='ssim' branch
+ * (pix2pix.py:182-186) is l1_weight = 0, gan_grad_scale = batch: its total loss is a per-image vector built from
+ * SSIM(input, target), a constant of the step, so tape.gradient differentiates the sum over the batch. */
+GAN_API int gan_pix2pix_train_step_ex(gan_net* g, gan_net* d, gan_adam* g_opt, gan_adam* d_opt,
+                              const float* input_image, const float* target, int batch,
+                              float l1_weight, float gan_grad_scale, int training, float losses[4]);
 GAN_API int gan_cyclegan_train_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy,
                             gan_adam* g_opt, gan_adam* f_opt, gan_adam* dx_opt, gan_adam* dy_opt,
                             const float* real_x, const float* real_y, int batch,

@@ -86,3 +86,40 @@ def test_manager_rotation_partial_restore_and_errors(tmp_path):
     with pytest.raises(TypeError):
         Checkpoint(thing=np.zeros(3))
     m.ctx.close(); g1.ctx.close()
+
+
+def test_reference_predict_flow_restores_into_unbound_optimizers(tmp_path):
+    """The reference's predict path (pix2pix.py:400-411): build a fresh model, wrap models AND optimizers in a
+    Checkpoint, restore(latest).expect_partial() BEFORE any train_step — the optimizers have no slots yet.  The
+    slots must be deferred (TF's deferred restoration), not an error, and applied when training resumes."""
+    from gan_b200 import CheckpointManager
+    rng = np.random.default_rng(8)
+    x, y = O.synthetic_images(rng, 2, 256, 256, 3), O.synthetic_images(rng, 2, 256, 256, 3)
+    a = _build("fp32")
+    a.ctx.set_graphs(False)
+    for _ in range(2):
+        a.train_step(x, y, True)
+    mgr = CheckpointManager(_ckpt(a), str(tmp_path), max_to_keep=1)
+    mgr.save()
+    # a crashed writer's leftover must not break the manager (glob vs regex)
+    open(os.path.join(str(tmp_path), "ckpt-9.npz.tmp.npz"), "wb").close()
+    assert [os.path.basename(p) for p in mgr.checkpoints] == ["ckpt-1.npz"]
+    b = _build("fp32", seed_shift=9)
+    b.generator_optimizer.learning_rate = 1e-3                           # differs from the file: the file wins, as in TF
+    status = _ckpt(b).restore(mgr.latest_checkpoint)
+    status.expect_partial()
+    status.assert_consumed()                                             # deferred slots count as consumed
+    assert b.generator_optimizer.iterations == 2 and b.generator_optimizer.learning_rate == 2e-4
+    out_a, out_b = a.generator(x), None
+    b.ctx.set_rng(SEED, a.ctx.call_counter() - 1)
+    out_b = b.generator(x)
+    assert np.array_equal(out_a, out_b)                                  # predict: weights came from the file
+    # training resumes with the restored slots: one more step on both gives identical weights
+    b.ctx.set_graphs(False)
+    a.ctx.set_rng(SEED, 100); b.ctx.set_rng(SEED, 100)
+    a.train_step(x, y, True); b.train_step(x, y, True)
+    assert b.generator_optimizer.iterations == 3
+    for which in ("m", "v"):
+        assert np.allclose(a.generator_optimizer.get_state(which), b.generator_optimizer.get_state(which), rtol=0, atol=1e-7)
+    assert np.abs(a.generator.get_flat_params() - b.generator.get_flat_params()).max() <= 2 * 2e-4 * 1.01
+    a.ctx.close(); b.ctx.close()

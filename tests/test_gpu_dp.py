@@ -76,3 +76,99 @@ def test_two_gpu_data_parallel_step_matches_oracle():
     for a, r in zip(r0["losses"], r0["ref_losses"]):
         assert abs(a - r) <= 1e-4 * max(1.0, abs(r)), (r0["losses"], r0["ref_losses"])
     assert r0["grad_err"] < 3e-3, r0["grad_err"]            # batch-2 shards: fp32 conditioning level
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same data-parallel DEFINITION on ONE GPU (so that a single-GPU box still checks it): the two shards of a global
+# batch run one after the other in two contexts with identical weights, each with its global sample offset
+# (gan_ctx_set_sample_offset keys the dropout masks on the GLOBAL sample index); gradients and losses are averaged on
+# the host as the all-reduce + 1/world scaling would.
+# ---------------------------------------------------------------------------------------------------------------
+def _shard_models(cls, cfg, loaders, world):
+    ms = []
+    for r in range(world):
+        m = cls(dict(cfg))
+        loaders(m)
+        ms.append(m)
+    return ms
+
+
+def test_one_gpu_sharded_pix2pix_equals_data_parallel_oracle():
+    """Pix2Pix: per-replica BatchNorm statistics, global-sample-keyed dropout."""
+    from gan_b200 import Pix2Pix, shard_bounds
+    from helpers import make_pix2pix, load_model
+    from oracle import gan_oracle as O
+    world, GB = 2, 4
+    cfg = dict(img_size=256, channels='3', learning_rate=2e-4, beta_1=0.5, beta_2=0.999, generator_loss='l1',
+               seed=SEED, precision='fp32', device=0)
+    cfg['lambda'] = 100
+    g_np, d_np = make_pix2pix(SEED + 1, 3, None)
+    ms = _shard_models(Pix2Pix, cfg, lambda m: (load_model(m.generator, g_np), load_model(m.discriminator, d_np)), world)
+    rng = np.random.default_rng(SEED)
+    x = O.synthetic_images(rng, GB, 256, 256, 3); y = O.synthetic_images(rng, GB, 256, 256, 3)
+    losses, gg, dg = [], [], []
+    for r, m in enumerate(ms):
+        lo, hi = shard_bounds(GB, r, world)
+        m.ctx.set_sample_offset(lo)
+        assert m.ctx.call_counter() == 0
+        losses.append([float(v) for v in m.train_step(x[lo:hi], y[lo:hi], True)])
+        gg.append(m.generator.get_flat_grads().astype(np.float64)); dg.append(m.discriminator.get_flat_grads().astype(np.float64))
+    dev_losses = np.mean(np.array(losses), axis=0)
+    dev_gg, dev_dg = sum(gg) / world, sum(dg) / world
+    gp, dp = O.to_torch(g_np, torch.float64), O.to_torch(d_np, torch.float64)
+    go, do = O.KerasAdam(gp), O.KerasAdam(dp)
+    masks = O.generator_keep_masks(SEED, 0, 0, GB, 256)
+    ref_losses, ref_gg, ref_dg = O.pix2pix_train_step(gp, dp, go, do, torch.tensor(x, dtype=torch.float64),
+                                                      torch.tensor(y, dtype=torch.float64), 100.0, True, masks, world=world)
+    for a, r in zip(dev_losses, ref_losses):
+        assert abs(a - r) <= 1e-4 * max(1.0, abs(r)), (dev_losses, ref_losses)
+    for dev, ref in ((dev_gg, ref_gg), (dev_dg, ref_dg)):
+        ref_flat = np.concatenate([g.numpy().ravel() for g in ref])
+        assert np.abs(dev - ref_flat).max() / np.abs(ref_flat).max() < 3e-3     # batch-2 shards: fp32 conditioning level (DESIGN §5)
+    # and the UNSHARDED batch-4 step is a different function (BatchNorm couples the batch): the test would notice
+    # a kernel that silently normalised over the wrong set
+    ref1, _, _ = O.pix2pix_train_step(O.to_torch(g_np, torch.float64), O.to_torch(d_np, torch.float64), O.KerasAdam(gp), O.KerasAdam(dp),
+                                      torch.tensor(x, dtype=torch.float64), torch.tensor(y, dtype=torch.float64), 100.0, False, masks, world=1)
+    assert max(abs(a - b) for a, b in zip(ref1, ref_losses)) > 1e-3
+    for m in ms:
+        m.ctx.close()
+
+
+def test_one_gpu_sharded_cyclegan_equals_unsharded_oracle():
+    """CycleGAN: InstanceNorm is per sample, so the sharded step equals the UNSHARDED oracle batch (bf16-free fp32 mode)."""
+    from gan_b200 import CycleGAN, shard_bounds
+    from helpers import load_model
+    from oracle import gan_oracle as O
+    world, GB = 2, 2
+    cfg = dict(img_size=256, channels='3', learning_rate=2e-4, beta_1=0.5, beta_2=0.999, seed=SEED, precision='fp32', device=0)
+    cfg['lambda'] = 10
+    rng = np.random.default_rng(SEED + 1)
+    specs = [O.generator_spec(3), O.generator_spec(3), O.discriminator_spec(3, False), O.discriminator_spec(3, False)]
+    nets_np = [O.init_params(s, rng, "instancenorm") for s in specs]
+
+    def load(m):
+        for mod, arrs in zip([m.generator_g, m.generator_f, m.discriminator_x, m.discriminator_y], nets_np):
+            load_model(mod, arrs)
+    ms = _shard_models(CycleGAN, cfg, load, world)
+    irng = np.random.default_rng(SEED)
+    x = O.synthetic_images(irng, GB, 256, 256, 3); y = O.synthetic_images(irng, GB, 256, 256, 3)
+    losses, grads = [], []
+    for r, m in enumerate(ms):
+        lo, hi = shard_bounds(GB, r, world)
+        m.ctx.set_sample_offset(lo)
+        losses.append([float(v) for v in m.train_step(x[lo:hi], y[lo:hi], True)])
+        grads.append([mod.get_flat_grads().astype(np.float64) for mod in (m.generator_g, m.generator_f, m.discriminator_x, m.discriminator_y)])
+    dev_losses = np.mean(np.array(losses), axis=0)
+    calls = ['fake_y', 'cycled_x', 'fake_x', 'cycled_y', 'same_x', 'same_y']
+    masks = {n: O.generator_keep_masks(SEED, i, 0, GB, 256) for i, n in enumerate(calls)}
+    nets = [O.to_torch(a, torch.float64) for a in nets_np]
+    ref_losses, g1, g2, g3, g4, _ = O.cyclegan_losses_and_grads(nets[0], nets[1], nets[2], nets[3], torch.tensor(x, dtype=torch.float64),
+                                                                 torch.tensor(y, dtype=torch.float64), 10.0, masks)
+    for a, r in zip(dev_losses, ref_losses):
+        assert abs(a - float(r)) <= 1e-4 * max(1.0, abs(float(r))), (dev_losses, [float(v) for v in ref_losses])
+    for k, ref in enumerate((g1, g2, g3, g4)):
+        dev = sum(g[k] for g in grads) / world
+        ref_flat = np.concatenate([g.numpy().ravel() for g in ref])
+        assert np.abs(dev - ref_flat).max() / np.abs(ref_flat).max() < 3e-3, k
+    for m in ms:
+        m.ctx.close()

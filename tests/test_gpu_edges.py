@@ -146,3 +146,31 @@ def test_handle_ownership_and_double_destroy():
     h = m.ctx.handle
     m.ctx.close()                                         # frees the discriminator
     assert lib.gan_ctx_destroy(h) == -1
+
+
+def test_ctx_setters_invalidate_captured_graphs():
+    """gan_ctx_set_dropout / set_sample_offset change state a captured step graph has baked in (kernel template,
+    kernel argument): the setters must drop the graphs so the next step honours the new value."""
+    m, _, _ = _build("bf16")
+    m.ctx.set_graphs(True)
+    x, y = _inputs(2, 3, seed=41)
+    for _ in range(4):                                    # eager, capture, replay, replay
+        m.train_step(x, y, False)
+    c = m.ctx.call_counter()
+    with_drop = [float(v) for v in m.train_step(x, y, False)]             # replayed graph, dropout on
+    m.ctx.set_dropout(False)                                              # after capture: must not be ignored
+    runs = [[float(v) for v in m.train_step(x, y, False)] for _ in range(3)]   # eager, capture, replay
+    ref = _build("bf16")[0]
+    ref.ctx.set_dropout(False)
+    want = [float(v) for v in ref.train_step(x, y, False)]                # eager, dropout off from the start
+    assert all(r == want for r in runs) and want != with_drop
+    # sample offset: a different global sample index draws different masks
+    m.ctx.set_dropout(True)
+    for _ in range(3):
+        m.ctx.set_rng(SEED, c)
+        a = [float(v) for v in m.train_step(x, y, False)]
+    m.ctx.set_sample_offset(2)
+    m.ctx.set_rng(SEED, c)
+    b = [float(v) for v in m.train_step(x, y, False)]
+    assert a == with_drop and b != a
+    m.ctx.close(); ref.ctx.close()

@@ -135,11 +135,34 @@ def test_float32_oracle_agrees_with_float64():
         assert abs(a - b) <= 1e-5 * max(1.0, abs(b))
 
 
-def test_cyclegan_single_sweep_equals_four_tape_gradients():
-    """one backward of gen_g+gen_f+total_cycle+id_x+id_y gives the reference's
-    generator_g / generator_f gradients (checked on the discriminator-free part, small config)."""
+def test_cyclegan_loss_identities_in_the_golden():
+    """total_gen_g = gen_g + total_cycle + identity_y (cycle_gan.py:243-244): consistency of the stored losses."""
     want = np.load(os.path.join(GOLD, "cyclegan_b1_c3.npz"))
     assert want["losses_0"].shape == (7,)
     l = want["losses_0"]
-    # total_gen_g = gen_g + total_cycle + identity_y  >= gen_g + total_cycle
     assert l[3] >= l[0] + l[2] - 1e-12 and l[4] >= l[1] + l[2] - 1e-12
+
+
+def test_cyclegan_single_sweep_equals_four_tape_gradients():
+    """ONE backward sweep of gen_g + gen_f + total_cycle + id_x + id_y (what the device runs) yields
+    exactly the reference's generator_g and generator_f gradients, which TensorFlow computes with two separate
+    tape.gradient calls on total_gen_g / total_gen_f (cycle_gan.py:252-255): d gen_f / dG = d id_x / dG = 0 and
+    d gen_g / dF = d id_y / dF = 0, and total_cycle is shared."""
+    rng = np.random.default_rng(5)
+    specs = [O.generator_spec(3), O.generator_spec(3), O.discriminator_spec(3, False), O.discriminator_spec(3, False)]
+    nets = [O.to_torch(O.init_params(s, rng, "instancenorm"), torch.float64) for s in specs]
+    irng = np.random.default_rng(6)
+    x = torch.tensor(O.synthetic_images(irng, 1, 256, 256, 3), dtype=torch.float64)
+    y = torch.tensor(O.synthetic_images(irng, 1, 256, 256, 3), dtype=torch.float64)
+    losses, _, _, _, _, outs = O.cyclegan_losses_and_grads(nets[0], nets[1], nets[2], nets[3], x, y, 10.0, None, want_grads=False)
+    gen_g, gen_f, total_cycle, total_g, total_f = losses[:5]
+    g_g = torch.autograd.grad(total_g, nets[0], retain_graph=True)      # cycle_gan.py:252
+    g_f = torch.autograd.grad(total_f, nets[1], retain_graph=True)      # cycle_gan.py:254
+    id_y = total_g - gen_g - total_cycle
+    id_x = total_f - gen_f - total_cycle
+    single = gen_g + gen_f + total_cycle + id_x + id_y
+    sweep_g = torch.autograd.grad(single, nets[0], retain_graph=True)
+    sweep_f = torch.autograd.grad(single, nets[1])
+    for a, b in list(zip(sweep_g, g_g)) + list(zip(sweep_f, g_f)):
+        den = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 1e-12 * max(den, 1e-30) + 1e-18
