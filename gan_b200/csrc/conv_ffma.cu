@@ -357,7 +357,7 @@ void launch_conv_fwd_ffma(Launch L, int dt, const ConvOp& op) {
   KLAUNCH(L);
 }
 
-// dt_in: dtype of the layer input x; dt_dy: dtype of the output gradient (16-bit mode: f16 x bf16)
+// dt_in: dtype of the layer input x; dt_dy: dtype of the output gradient (always equal: see common.cuh)
 void launch_conv_wgrad_ffma(Launch L, int dt_in, int dt_dy, const ConvOp& op) {
   const int64_t M = (int64_t)op.N * op.Hm * op.Wm;
   auto run = [&](auto* tag, auto* dtag) {
@@ -391,7 +391,7 @@ void launch_conv_wgrad_ffma(Launch L, int dt_in, int dt_dy, const ConvOp& op) {
     else k_conv_wgrad<T, TD, false><<<grid, 256, 0, L.s>>>(op, splits);
   };
   if (dt_in == DT_F32) run((float*)nullptr, (float*)nullptr);
-  else if (dt_in == DT_F16) run((f16*)nullptr, (bf16*)nullptr);
+  else if (dt_in == DT_F16) run((f16*)nullptr, (f16*)nullptr);
   else run((bf16*)nullptr, (bf16*)nullptr);
   (void)dt_dy;
   KLAUNCH(L);

@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <mutex>
 #include <cstring>
+#include <cstdlib>
 #include "kernels.h"
 
 #define KLAUNCH(L) (++*(L).count)
@@ -140,6 +141,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// ---- cta_group::2 (CTA pair on one TPC) ------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are counted on the
+// mbarrier of the pair's leader CTA (`bar_cluster_addr`, a shared::cluster address)
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows of each CTA] * B[N/2 rows of each CTA]^T : one M=256 MMA over the pair
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once all prior MMAs of this thread are done
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -197,6 +241,7 @@ struct alignas(64) UmmaFwdParams {
   int ab_bf16;                       // operand format of A and B (both: the weights are packed in the input's dtype)
   int out_f16;                       // 16-bit output format: 1 = f16 (activations), 0 = bf16 (gradients)
   float* ws; int ksplit; long long slab;   // split-K: split ks stores fp32 into ws[ks][pix][Nc] (no atomics)
+  float* stats_ws;                   // CTA-pair kernel: per-(CTA, quadrant) column sums / sums of squares, or nullptr
 };
 
 constexpr int FWD_STAGES = 3;         // BN <= 128: 3 x 32 KB, two CTAs per SM
@@ -398,6 +443,208 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =============================================================================================
+// CTA-pair forward-type kernel (tcgen05.mma.cta_group::2): one 256 x BN output tile per CTA pair.
+//   * each CTA of the pair loads ITS 128 M-space rows of A and HALF of the B tile (BN/2 weight rows); the pair's
+//     leader issues M=256 MMAs that read both halves, so every weight byte is fetched from L2 once per 256 rows
+//     (half the L2->SMEM operand traffic per FLOP of the one-CTA tile, the measured limiter of the N<=256 layers)
+//     and each SM's shared-memory operand read per MMA drops from A+B to A+B/2;
+//   * 8 epilogue warps (two per TMEM lane quadrant, alternating 32-column chunks) drain a double-buffered
+//     accumulator; the deeper TMA ring (5-6 stages) is paid for by the smaller per-CTA stage;
+//   * BatchNorm statistics come from the fp32 accumulators: each epilogue warp transposes its 32x32 chunk through
+//     shared memory, lane c sums column c, and the per-(CTA, quadrant) sums live in shared memory until the end of
+//     the persistent loop (one deterministic partial per CTA and quadrant -> k_stats_finalize), which removes the
+//     separate statistics pass over z.
+// Restrictions (launch_conv_fwd_umma falls back to the one-CTA kernel otherwise): KC = 64, 16-bit output, no bias
+// epilogue, no split-K, no fp32 row output.
+// =============================================================================================
+constexpr int F2_THREADS = 320;      // warp0 TMA, warp1 MMA (leader CTA only), warps 2..9 epilogue
+constexpr int F2_EPI_WARPS = 8;
+constexpr int F2_STAT_NC = 512;      // statistics accumulators: up to 512 output channels
+__host__ __device__ constexpr int f2_stages(int BN) { return BN == 256 ? 5 : 6; }
+__host__ __device__ constexpr uint32_t f2_stage_bytes(int BN) { return 128u * 128u + (uint32_t)(BN / 2) * 128u; }
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F2_THREADS, 1) k_conv_fwd_umma2(const __grid_constant__ UmmaFwdParams p) {
+  constexpr uint32_t A_BYTES = 128 * 128;
+  constexpr uint32_t STAGE_BYTES = f2_stage_bytes(BN);
+  constexpr uint32_t ACC_COLS = BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;       // 128 | 256 | 512
+  constexpr int NSTAGE = f2_stages(BN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + NSTAGE * STAGE_BYTES);     // leader's are used
+  uint64_t* empty = full + NSTAGE;                               // own
+  uint64_t* tmem_full = empty + NSTAGE;                          // [2] own
+  uint64_t* tmem_empty = tmem_full + 2;                          // [2] leader's are used
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* scr = (float*)(tmem_slot + 4);                          // [8 warps][32 columns][33]
+  float2* sacc = (float2*)(scr + F2_EPI_WARPS * 32 * 33);        // [4 quadrants][F2_STAT_NC]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int ntn = p.Nc / BN;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.bmap);
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.amap[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 2 * F2_EPI_WARPS); }
+    ptx::fence_barrier_init();
+  }
+  if (p.stats_ws != nullptr)
+    for (int i = threadIdx.x; i < 4 * F2_STAT_NC; i += F2_THREADS) sacc[i] = make_float2(0.f, 0.f);
+  if (warp == 2) ptx::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();               // the peer's barriers are initialised before anything signals them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair tile -> (class, n-tile, pair of M tiles); (class, n-tile) fastest as in the one-CTA kernel
+  const int inner = ntn * p.ncls;
+  auto decode = [&](int tile, int& cls, int& n0, int& w0, int& h0, int& b0) {
+    int pm = tile / inner; int r = tile - pm * inner;
+    n0 = (r % ntn) * BN; cls = r / ntn;
+    int tm = 2 * pm + (int)rank;                     // this CTA's M tile (may lie beyond the last: all rows invalid)
+    w0 = (tm % p.tiles_w) * p.TW; tm /= p.tiles_w;
+    h0 = (tm % p.tiles_h) * p.TH; tm /= p.tiles_h;
+    b0 = tm * p.TN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t full_leader[NSTAGE];
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) full_leader[s] = ptx::mapa_u32(ptx::smem_u32(&full[s]), 0);
+      uint32_t it = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+        int cls, n0, w0, h0, b0;
+        decode(tile, cls, n0, w0, h0, b0);
+        const int nk = p.ntaps[cls] * p.kchunks;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
+          const int t = kb / p.kchunks, kc = kb - t * p.kchunks;
+          ptx::tma_load_4d_2sm(sa, &p.amap[p.tap_map[cls][t]], full_leader[s], kc * 64, w0 + p.tap_dw[cls][t], h0 + p.tap_dh[cls][t], b0);
+          ptx::tma_load_2d_2sm(sa + A_BYTES, &p.bmap, full_leader[s], kb * 64, cls * p.Nc + n0 + (int)rank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(256, BN, 0, 0, p.ab_bf16, p.ab_bf16);
+      uint32_t it = 0, li = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += npairs, ++li) {
+        const int cls = (tile % inner) / ntn;
+        const int nk = p.ntaps[cls] * p.kchunks;
+        const uint32_t buf = li & 1, use = li >> 1;
+        ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // all 16 epilogue warps of the pair have drained it
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * ACC_COLS;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t sa = ptx::smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_2sm(acc, desc_kmajor<128>(sa) + 2 * k, desc_kmajor<128>(sa + A_BYTES) + 2 * k, idesc, (kb > 0) || (k != 0));
+            ptx::umma_commit_2sm(&empty[s]);
+            if (kb == nk - 1) ptx::umma_commit_2sm(&tmem_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                       // the two warps of a quadrant alternate 32-column chunks
+    const int r = q * 32 + lane;
+    const int wl = r % p.TW, hl = (r / p.TW) % p.TH, nl = r / (p.TW * p.TH);
+    const uint32_t tmem_empty_leader[2] = {ptx::mapa_u32(ptx::smem_u32(&tmem_empty[0]), 0), ptx::mapa_u32(ptx::smem_u32(&tmem_empty[1]), 0)};
+    float* S = scr + ew * 32 * 33;
+    float2* A = sacc + q * F2_STAT_NC;
+    const bool stats = p.stats_ws != nullptr;
+    uint32_t li = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += npairs, ++li) {
+      int cls, n0, w0, h0, b0;
+      decode(tile, cls, n0, w0, h0, b0);
+      const uint32_t buf = li & 1, use = li >> 1;
+      const int mw = w0 + wl, mh = h0 + hl, nb = b0 + nl;
+      const int oh = mh * p.so + p.oa[cls], ow = mw * p.so + p.ob[cls];
+      const bool valid = nb < p.N && mh < p.Hm && mw < p.Wm && oh < p.Hout && ow < p.Wout;
+      const int64_t pix = ((int64_t)nb * p.Hout + oh) * p.Wout + ow;
+      bf16* dst = p.out + pix * p.out_pitch + p.out_coff + n0;
+      ptx::mbar_wait(&tmem_full[buf], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = half * 32; c < BN; c += 64) {
+        uint32_t v[32];
+        ptx::tmem_ld32(acc + c, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = cvt_pair(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]), p.out_f16);
+            *reinterpret_cast<uint4*>(dst + c + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (stats) {
+          // transpose the warp's 32 rows x 32 columns through shared memory: lane = row writes column-major,
+          // lane = column reads its 32 rows; both patterns are bank-conflict free with the 33-float pitch
+#pragma unroll
+          for (int j = 0; j < 32; ++j) S[j * 33 + lane] = valid ? __uint_as_float(v[j]) : 0.f;
+          __syncwarp();
+          float sm = 0.f, sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float x = S[lane * 33 + i]; sm += x; sq = fmaf(x, x, sq); }
+          __syncwarp();
+          float2 a = A[n0 + c + lane];
+          a.x += sm; a.y += sq;
+          A[n0 + c + lane] = a;
+        }
+      }
+      // accumulator buffer fully read into registers: hand it back to the leader's MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_leader[buf]);
+    }
+    if (stats) {
+      // one partial per (CTA, quadrant): ws[(cta*4 + q)][0][c] = sum, [1][c] = sum of squares
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < 4 * p.Nc; i += 256) {
+        const int qq = i / p.Nc, c = i - qq * p.Nc;
+        const float2 a = sacc[qq * F2_STAT_NC + c];
+        float* o = p.stats_ws + ((size_t)(blockIdx.x * 4 + qq) * 2) * p.Nc;
+        o[c] = a.x; o[p.Nc + c] = a.y;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();               // nobody leaves while the peer can still signal its barriers / read its smem
+  if (warp == 2) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+static size_t f2_smem_bytes(int BN) {
+  return (size_t)f2_stages(BN) * f2_stage_bytes(BN) + 1024 + 256 + (size_t)F2_EPI_WARPS * 32 * 33 * 4 + (size_t)4 * F2_STAT_NC * 8;
+}
+
 static size_t fwd_smem_bytes(int BN) { return (size_t)fwd_stages(BN) * (128 * 128 + BN * 128) + 1024 + 256; }
 
 static bool view_ok(int pitch, int coff, const void* p) {
@@ -468,7 +715,40 @@ static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile, int
   P.ab_bf16 = op.dt_in == DT_F16 ? 0 : 1; P.out_f16 = op.dt_out == DT_F16 ? 1 : 0;
 }
 
-void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
+// dev A/B switches (read once): GAN_B200_2CTA=0 keeps every layer on the one-CTA kernel, GAN_B200_EPI_STATS=0 keeps the
+// separate statistics pass
+static bool env_on(const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); }
+static const bool g_use_2cta = env_on("GAN_B200_2CTA");
+static const bool g_epi_stats = env_on("GAN_B200_EPI_STATS");
+
+// CTA-pair path: returns true when it launched (and *stat_parts = number of statistics partials written).
+static bool launch_conv_fwd_umma2(Launch L, const ConvOp& op, int* stat_parts) {
+  *stat_parts = 0;
+  if (!g_use_2cta) return false;
+  if (op.Kc % 64 != 0 || op.Nc % 64 != 0 || op.out == nullptr) return false;
+  if (op.epi != EPI_NONE || op.out_f32 != nullptr || op.out_rows_f32 != nullptr) return false;
+  const int BN = (op.Nc % 256 == 0) ? 256 : (op.Nc % 128 == 0 ? 128 : 64);
+  UmmaFwdParams P;
+  fill_fwd_params(P, op, BN / 2, 64);                 // each CTA of the pair loads half of the weight tile's rows
+  const int mtiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  if (mtiles < 148) return false;                     // small-M layers: split-K on the one-CTA kernel fills the chip better
+  P.num_tiles = ((mtiles + 1) / 2) * (op.Nc / BN) * op.ncls;     // pair tiles
+  P.ksplit = 1; P.ws = nullptr; P.f32out = 0;
+  P.stats_ws = (g_epi_stats && op.stats_ws != nullptr && op.Nc <= F2_STAT_NC) ? op.stats_ws : nullptr;
+  const int pairs = P.num_tiles < 74 ? P.num_tiles : 74;        // persistent: one CTA pair per TPC
+  dim3 grid(2 * pairs);
+  const size_t sm = f2_smem_bytes(BN);
+  if (BN == 256) k_conv_fwd_umma2<256><<<grid, F2_THREADS, sm, L.s>>>(P);
+  else if (BN == 128) k_conv_fwd_umma2<128><<<grid, F2_THREADS, sm, L.s>>>(P);
+  else k_conv_fwd_umma2<64><<<grid, F2_THREADS, sm, L.s>>>(P);
+  KLAUNCH(L);
+  if (P.stats_ws != nullptr) *stat_parts = (int)grid.x * 4;
+  return true;
+}
+
+int launch_conv_fwd_umma(Launch L, const ConvOp& op) {
+  int stat_parts = 0;
+  if (launch_conv_fwd_umma2(L, op, &stat_parts)) return stat_parts;
   int BN = (op.Nc % 128 == 0) ? 128 : (op.Nc % 64 == 0 ? 64 : 16);
   const int KC = op.Kc == 16 ? 16 : 64;
   UmmaFwdParams P;
@@ -508,6 +788,7 @@ void launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   KLAUNCH(L);
   if (P.ksplit > 1)   // deterministic reduction of the k-split slabs + conversion to bf16
     launch_sum_slabs(L, op.dt_out, op.splitk_ws, P.ksplit, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
+  return 0;
 }
 
 // =============================================================================================
@@ -754,6 +1035,9 @@ void umma_init() {
     if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (PFN_encodeTiled)fn;
     else cudaGetLastError();
 #define SET_SMEM(K, B) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B))
+    SET_SMEM((k_conv_fwd_umma2<256>), f2_smem_bytes(256));
+    SET_SMEM((k_conv_fwd_umma2<128>), f2_smem_bytes(128));
+    SET_SMEM((k_conv_fwd_umma2<64>), f2_smem_bytes(64));
     SET_SMEM((k_conv_fwd_umma<256, 64>), fwd_smem_bytes(256));
     SET_SMEM((k_conv_fwd_umma<128, 64>), fwd_smem_bytes(128));
     SET_SMEM((k_conv_fwd_umma<64, 64>), fwd_smem_bytes(64));

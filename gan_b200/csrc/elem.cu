@@ -15,13 +15,12 @@
 template <typename F> static void dispatch_dt(int dt, F&& f) {
   if (dt == DT_F32) f((float*)nullptr); else if (dt == DT_F16) f((f16*)nullptr); else f((bf16*)nullptr);
 }
-// (activation dtype, gradient dtype) pairs: fp32/fp32, f16/bf16 (default 16-bit mode), bf16/bf16
+// (activation dtype, gradient dtype) pairs: fp32/fp32, f16/f16 (default 16-bit mode), bf16/bf16
 template <typename F> static void dispatch_dt2(int dtz, int dtg, F&& f) {
-  if (dtz == DT_F32) { GAN_REQUIRE(dtg == DT_F32, "fp32 activations need fp32 gradients"); f((float*)nullptr, (float*)nullptr); }
-  else {
-    GAN_REQUIRE(dtg == DT_BF16, "16-bit gradients are bf16");
-    if (dtz == DT_F16) f((f16*)nullptr, (bf16*)nullptr); else f((bf16*)nullptr, (bf16*)nullptr);
-  }
+  GAN_REQUIRE(dtz == dtg, "activations and gradients share one storage format (tcgen05 kind::f16 needs equal A/B formats)");
+  if (dtz == DT_F32) f((float*)nullptr, (float*)nullptr);
+  else if (dtz == DT_F16) f((f16*)nullptr, (f16*)nullptr);
+  else f((bf16*)nullptr, (bf16*)nullptr);
 }
 #define KLAUNCH(L) (++*(L).count)
 
@@ -215,6 +214,16 @@ void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C
   KLAUNCH(L);
   k_stats_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, eps, gamma, beta, mean,
                                                                       inv, scale, shift, mov_mean, mov_var, momentum);
+  KLAUNCH(L);
+}
+
+// Stage 2 alone: the partials were produced elsewhere (the CTA-pair conv epilogue writes one [2][C] partial per
+// (CTA, TMEM quadrant) from its fp32 accumulators), layout ws[part][2][C].
+void launch_norm_stats_finalize(Launch L, const float* ws, int nparts, int64_t n, int C, float eps, const float* gamma,
+                                const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
+                                float* mov_var, float momentum) {
+  k_stats_finalize<<<dim3((C + 31) / 32, 1), 32 * FIN_LANES, 0, L.s>>>(ws, 1, nparts, C, (double)n, eps, gamma, beta, mean, inv,
+                                                                      scale, shift, mov_mean, mov_var, momentum);
   KLAUNCH(L);
 }
 
@@ -1186,10 +1195,10 @@ __global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int 
 // dz = (d1 + d2 + l1_coef*sign(out - ref)) * (1 - out^2) for the 2 taps of this thread's chunk straight from the
 // fp32 output / target images and writes the slot-4 row chunk; dz itself never exists in HBM.  Every
 // image pixel appears in 4 rows; the bias gradient counts it once, in the row where it is an inner tap.
-template <int C>
+template <int C, typename T>
 __global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict__ out, const float* __restrict__ ref,
                                                         GradSrc d1, GradSrc d2, float l1_coef, int B, int H, int W,
-                                                        bf16* __restrict__ dst, float* dbias) {
+                                                        T* __restrict__ dst, float* dbias) {
   __shared__ float sh[8];
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
   const int Ho = H / 2, Wo = W / 2;
@@ -1211,18 +1220,17 @@ __global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict_
         for (int c = 0; c < C; ++c) {
           const float o = out[p * C + c];
           float d = 0.f;
-          if (d1.p != nullptr) d += to_f(((const bf16*)d1.p)[p * d1.pitch + d1.coff + c]);
-          if (d2.p != nullptr) d += to_f(((const bf16*)d2.p)[p * d2.pitch + d2.coff + c]);
+          if (d1.p != nullptr) d += to_f(((const T*)d1.p)[p * d1.pitch + d1.coff + c]);
+          if (d2.p != nullptr) d += to_f(((const T*)d2.p)[p * d2.pitch + d2.coff + c]);
           if (ref != nullptr) {
             const float df = o - ref[p * C + c];
             d += l1_coef * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
           }
-          v[c] = to_f(from_f<bf16>(d * (1.f - o * o)));
+          v[c] = to_f(from_f<T>(d * (1.f - o * o)));
           if (owner) bsum[c] += v[c];
         }
       }
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-      w[2 * e] = *reinterpret_cast<uint32_t*>(&lo); w[2 * e + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      w[2 * e] = pack2<T>(v[0], v[1]); w[2 * e + 1] = pack2<T>(v[2], v[3]);
     }
     *reinterpret_cast<uint4*>(dst + m * 64 + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -1239,16 +1247,21 @@ __global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict_
     }
   }
 }
-void launch_ghead_bwd_cols(Launch L, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
-                           int H, int W, int C, void* gcols_bf16, float* dbias) {
+void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
+                           int H, int W, int C, void* gcols, float* dbias) {
   GAN_REQUIRE(C >= 1 && C <= 4, "generator head supports up to 4 output channels");
+  GAN_REQUIRE(dt == DT_F16 || dt == DT_BF16, "cols path is 16-bit only");
   const int64_t M = (int64_t)B * (H / 2) * (W / 2);
   const int grid = grid_for(M * 8, 256, 16);
-  bf16* d = (bf16*)gcols_bf16;
-  if (C == 1) k_ghead_bwd_cols<1><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
-  else if (C == 2) k_ghead_bwd_cols<2><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
-  else if (C == 3) k_ghead_bwd_cols<3><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
-  else k_ghead_bwd_cols<4><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+  auto run = [&](auto* tag) {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    T* d = (T*)gcols;
+    if (C == 1) k_ghead_bwd_cols<1, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+    else if (C == 2) k_ghead_bwd_cols<2, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+    else if (C == 3) k_ghead_bwd_cols<3, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+    else k_ghead_bwd_cols<4, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+  };
+  if (dt == DT_F16) run((f16*)nullptr); else run((bf16*)nullptr);
   KLAUNCH(L);
 }
 
@@ -1331,6 +1344,7 @@ void launch_dhead_gather(Launch L, const float* cols, const float* bias, int B, 
   KLAUNCH(L);
 }
 
+// (pure data movement of 16-bit elements: the same kernel serves f16 and bf16 gradients)
 __global__ void __launch_bounds__(256) k_dhead_unfold(const bf16* __restrict__ dl, int pitch, int B, int Hin, int Win,
                                                       bf16* __restrict__ dst) {
   const int Ho = Hin - 1, Wo = Win - 1;

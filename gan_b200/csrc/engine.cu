@@ -202,7 +202,8 @@ static double conv_flops(const ConvOp& op) {
 // ---------------------------------------------------------------------------------------------
 // conv dispatch: tcgen05 where the op fits (bf16 mode), FFMA otherwise
 // ---------------------------------------------------------------------------------------------
-static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
+// returns the number of BatchNorm-statistics partials the conv epilogue produced (0: none, run the statistics pass)
+static int run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
   ConvOp op = op_in;
   ctx->splitk_ws.ensure((size_t)32 << 20);
   op.splitk_ws = ctx->splitk_ws.as<float>(); op.splitk_ws_bytes = ctx->splitk_ws.bytes;
@@ -210,8 +211,9 @@ static void run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
   ProfScope ps(ctx, um ? FAM_UMMA_FWD : FAM_FFMA_FWD, conv_flops(op));
-  if (um) launch_conv_fwd_umma(ctx->L(), op);
-  else launch_conv_fwd_ffma(ctx->L(), op.dt_in, op);
+  if (um) return launch_conv_fwd_umma(ctx->L(), op);
+  launch_conv_fwd_ffma(ctx->L(), op.dt_in, op);
+  return 0;
 }
 static void run_conv_wgrad(gan_ctx* ctx, const ConvOp& op) {
   bool can = ctx->dt == DT_BF16 && umma_wgrad_supported(op);
@@ -415,8 +417,17 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   int64_t P = (int64_t)B * Ho * Wo;
   s.z[li].ensure((size_t)P * ly.Cout * ctx->esize());
   View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
-  if (li == 0 && s.used_im2col) run_conv_fwd(ctx, make_op_im2col(ctx, ly, R_FWD, s, z));
-  else run_conv_fwd(ctx, make_op(ctx, ly, R_FWD, in, z, ly.wp_fwd.p));
+  const int G = ly.norm == NORM_BATCH ? 1 : B;
+  const int64_t Pg = P / G;
+  const size_t gc = (size_t)G * ly.Cout;
+  if (ly.norm != NORM_NONE) {
+    size_t need = stats_ws_floats(G, Pg, ly.Cout), epi = (size_t)STATS_MAX_CHUNKS * 2 * ly.Cout;
+    ctx->stats_ws.ensure((need > epi ? need : epi) * 4);
+  }
+  ConvOp cop = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_FWD, s, z) : make_op(ctx, ly, R_FWD, in, z, ly.wp_fwd.p);
+  // BatchNorm statistics straight from the fp32 accumulators when the layer runs on the CTA-pair kernel
+  if (ly.norm == NORM_BATCH) cop.stats_ws = ctx->stats_ws.as<float>();
+  const int stat_parts = run_conv_fwd(ctx, cop);
   DropKey dk = drop_key(ctx, ly, s);
   // SURVEY 8d byte model: forward = read z + write activation = 2*s per element (statistics belong to the conv epilogue)
   ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * 2);
@@ -425,22 +436,22 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
                       out.pitch, out.coff);
     return;
   }
-  const int G = ly.norm == NORM_BATCH ? 1 : B;
-  const int64_t Pg = P / G;
-  const size_t gc = (size_t)G * ly.Cout;
   s.stats[li].ensure(gc * 6 * 4);
   float* st = s.stats[li].as<float>();
-  ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
   float* pr = n->params.as<float>();
   float* mm = (ly.mov_off >= 0) ? n->mov.as<float>() + ly.mov_off : nullptr;
-  if (launch_bn_small_fwd(ctx->L(), ctx->dtA, z.p, P, G, Ho * Wo, ly.Cout, ly.norm == NORM_BATCH ? BN_EPS : IN_EPS,
-                          pr + ly.g_off, pr + ly.b_off, st, st + gc,
-                          st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM, ly.act, dk, out.p,
-                          out.pitch, out.coff))
-    return;
-  launch_norm_stats(ctx->L(), ctx->dtA, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(),
-                    ly.norm == NORM_BATCH ? BN_EPS : IN_EPS, pr + ly.g_off, pr + ly.b_off, st, st + gc, st + 2 * gc,
-                    st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
+  const float eps = ly.norm == NORM_BATCH ? BN_EPS : IN_EPS;
+  if (stat_parts > 0) {
+    launch_norm_stats_finalize(ctx->L(), ctx->stats_ws.as<float>(), stat_parts, P, ly.Cout, eps, pr + ly.g_off, pr + ly.b_off,
+                               st, st + gc, st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
+  } else {
+    if (launch_bn_small_fwd(ctx->L(), ctx->dtA, z.p, P, G, Ho * Wo, ly.Cout, eps, pr + ly.g_off, pr + ly.b_off, st, st + gc,
+                            st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM, ly.act, dk, out.p,
+                            out.pitch, out.coff))
+      return;
+    launch_norm_stats(ctx->L(), ctx->dtA, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(), eps, pr + ly.g_off, pr + ly.b_off, st,
+                      st + gc, st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
+  }
   launch_norm_apply(ctx->L(), ctx->dtA, z.p, P, Pg, G, Ho * Wo, ly.Cout, st, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
                     out.pitch, out.coff);
 }
@@ -560,7 +571,7 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   const int Cp = g->Cp;
   if (s.used_cols) {
     s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
-    launch_ghead_bwd_cols(ctx->L(), s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, B, H, W, C, s.gcols.p,
+    launch_ghead_bwd_cols(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, B, H, W, C, s.gcols.p,
                           gr + g->layers[15].bias_off);
   } else {
     s.dlogit.ensure((size_t)B * H * W * Cp * es);
@@ -785,7 +796,7 @@ static void adam_apply(gan_adam* o, bool reduced = false) {
   o->t += 1;
   launch_bump(ctx->L(), o->t_dev.as<long long>(), nullptr, 1);
   AdamArgs a{n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), o->t_dev.as<long long>(),
-             o->lr, o->b1, o->b2, (float)o->eps, 1.f / (float)ctx->world};
+             o->lr, o->b1, o->b2, (float)o->eps, 1.f / ((float)ctx->world * n->grad_scale)};   // undo the DP sum and the loss scale
   // fused update + repack: 28 B/param of optimizer traffic + 4 B/param for the two packed bf16 copies
   ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
   launch_adam_pack(ctx->L(), ctx->dtA, ctx->dtG, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
@@ -823,6 +834,18 @@ static void loss_ws_reset(gan_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------
 // Pix2Pix.train_step (pix2pix.py:190-218)
 // ---------------------------------------------------------------------------------------------
+// Static loss scale for fp16 gradient storage: the largest gradient any loss head emits (`g_head`: weight / number of
+// elements of its mean) is brought to ~4 by a power of two.  Measured on this model (scripts/): |dL/dz| over
+// all layers spans 2e-9 .. 16x the head value, i.e. 3e-5 .. 64 after scaling — inside fp16's 6e-8 .. 65504 with three
+// orders of magnitude of head-room on top, and conversions saturate.  fp32 / bf16 storage: 1.
+static float pick_grad_scale(const gan_ctx* ctx, double g_head) {
+  if (ctx->dtG != DT_F16 || !(g_head > 0.0)) return 1.f;
+  int k = (int)floor(log2(4.0 / g_head));
+  if (k < 0) k = 0;
+  if (k > 24) k = 24;
+  return ldexpf(1.f, k);
+}
+
 // gan_scale: factor on the adversarial term of the GENERATOR gradient only (1 for the default 'l1' loss; the
 // reference's 'ssim' branch makes the total loss a per-image vector, whose tape.gradient is the gradient of the SUM
 // over the batch = B x d(gan_loss), pix2pix.py:182-186,210).
@@ -840,6 +863,9 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(d); }
+  const double n_img_d = (double)B * H * W * C, n_log_d = (double)B * (H / 8 - 2) * (W / 8 - 2);
+  const float S = pick_grad_scale(ctx, std::max((double)lambda / n_img_d, std::max((double)gan_scale, 0.5) / n_log_d));
+  ctx->grad_scale = S; g->grad_scale = S; d->grad_scale = S;
 
   generator_forward(g, 0, x, B, H, W);                                   // gen_output           (:200)
   const float* gen_out = g->slots[0].out_f32.as<float>();
@@ -849,18 +875,18 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   const int64_t n_img = (int64_t)B * H * W * C;
   launch_l1(ctx->L(), y, gen_out, n_img, ctx->loss_ws.as<float>(), 1);   // gan_loss2 = mean|target-gen_output| (:181)
   // raw slots: 0 BCE(1,fake)  1 L1  2 BCE(1,real)  3 BCE(0,fake)
-  disc_bce(d, 0, 1.f, 0.5f, training, true, 2);
+  disc_bce(d, 0, 1.f, 0.5f * S, training, true, 2);
   if (training) discriminator_backward(d, 0, true, false);
-  disc_bce(d, 1, 0.f, 0.5f, training, true, 3);
+  disc_bce(d, 1, 0.f, 0.5f * S, training, true, 3);
   if (training) {
     discriminator_backward(d, 1, true, false);
     comm_allreduce_async(ctx, d->grads.as<float>(), d->nparams);          // D gradients final: reduce under G's backward
   }
-  disc_bce(d, 1, 1.f, gan_scale, training, false, 0);
+  disc_bce(d, 1, 1.f, gan_scale * S, training, false, 0);
   if (training) {
     discriminator_backward(d, 1, false, true);                           // dL_G/d(gen_output) through D (:210)
     GradSrc dgan{d->slots[1].din0.p, d->Cin0_p, C};
-    generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, lambda / (float)n_img, false, true);
+    generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, S * lambda / (float)n_img, false, true);
     comm_join(ctx);
     adam_apply(go, true);                                                // (:213)
     adam_apply(dopt, true);                                              // (:215)
@@ -897,6 +923,8 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy); }
+  const float S = pick_grad_scale(ctx, std::max((double)lambda / ((double)B * H * W * C), 1.0 / ((double)B * (H / 8 - 2) * (W / 8 - 2))));
+  ctx->grad_scale = S; g->grad_scale = S; f->grad_scale = S; dx->grad_scale = S; dy->grad_scale = S;
 
   generator_forward(g, 0, x, B, H, W);  const float* fake_y = g->slots[0].out_f32.as<float>();     // (:220)
   generator_forward(f, 0, fake_y, B, H, W); const float* cycled_x = f->slots[0].out_f32.as<float>(); // (:221)
@@ -917,15 +945,15 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   launch_l1(ctx->L(), y, cycled_y, n_img, lw, 3);
   launch_l1(ctx->L(), y, same_y, n_img, lw, 4);
   launch_l1(ctx->L(), x, same_x, n_img, lw, 5);
-  disc_bce(dx, 0, 1.f, 0.5f, training, true, 6); if (training) discriminator_backward(dx, 0, true, false);
-  disc_bce(dx, 1, 0.f, 0.5f, training, true, 7); if (training) discriminator_backward(dx, 1, true, false);
-  disc_bce(dy, 0, 1.f, 0.5f, training, true, 8); if (training) discriminator_backward(dy, 0, true, false);
-  disc_bce(dy, 1, 0.f, 0.5f, training, true, 9); if (training) discriminator_backward(dy, 1, true, false);
-  disc_bce(dy, 1, 1.f, 1.0f, training, false, 0); if (training) discriminator_backward(dy, 1, false, true);
-  disc_bce(dx, 1, 1.f, 1.0f, training, false, 1); if (training) discriminator_backward(dx, 1, false, true);
+  disc_bce(dx, 0, 1.f, 0.5f * S, training, true, 6); if (training) discriminator_backward(dx, 0, true, false);
+  disc_bce(dx, 1, 0.f, 0.5f * S, training, true, 7); if (training) discriminator_backward(dx, 1, true, false);
+  disc_bce(dy, 0, 1.f, 0.5f * S, training, true, 8); if (training) discriminator_backward(dy, 0, true, false);
+  disc_bce(dy, 1, 0.f, 0.5f * S, training, true, 9); if (training) discriminator_backward(dy, 1, true, false);
+  disc_bce(dy, 1, 1.f, S, training, false, 0); if (training) discriminator_backward(dy, 1, false, true);
+  disc_bce(dx, 1, 1.f, S, training, false, 1); if (training) discriminator_backward(dx, 1, false, true);
   if (training) {
     const GradSrc none{nullptr, 0, 0};
-    const float lc = lambda / (float)n_img;
+    const float lc = S * lambda / (float)n_img;
     generator_backward(f, 0, none, none, x, lc, true);                                   // cycle x: through F into fake_y
     generator_backward(g, 1, none, none, y, lc, true);                                   // cycle y: through G into fake_x
     generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->Cin0_p, 0}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false);
@@ -1062,11 +1090,11 @@ int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
   c->device = device; c->dt = precision == GAN_FP32 ? DT_F32 : DT_BF16; c->seed = seed;
   if (c->dt == DT_F32) { c->dtA = DT_F32; c->dtG = DT_F32; }
   else {
-    // 16-bit mode: fp16 activations / forward weights, bf16 gradients (common.cuh).  GAN_B200_ACT=bf16 stores the
-    // activations as bf16 too (round 1's numerics: 8x the forward rounding error; kept for A/B measurements).
+    // 16-bit mode: fp16 storage with a static loss scale (common.cuh).  GAN_B200_ACT=bf16 selects all-bf16 storage
+    // (round 1's numerics: 8x the rounding error, no loss scale needed; kept for A/B measurements).
     const char* e = getenv("GAN_B200_ACT");
     c->dtA = (e && strcmp(e, "bf16") == 0) ? DT_BF16 : DT_F16;
-    c->dtG = DT_BF16;
+    c->dtG = c->dtA;
   }
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost((void**)&c->loss_host, 16 * 4));
@@ -1275,10 +1303,17 @@ int gan_net_set_tensor(gan_net* net, int idx, const float* host_src) {
   net->packed_dirty = true;
   API_END
 }
+// the gradient buffer holds grad_scale x the gradient (a power of two: the division is exact)
+static void unscale_host(float* p, int64_t n, float s) {
+  if (s == 1.f) return;
+  const float inv = 1.f / s;
+  for (int64_t i = 0; i < n; ++i) p[i] *= inv;
+}
 int gan_net_get_grad(gan_net* net, int idx, float* host_dst) {
   API_BEGIN
   CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
   CUDA_CHECK(cudaMemcpy(host_dst, tensor_dev(net, idx, &net->grads), net->tensors[idx].numel * 4, cudaMemcpyDeviceToHost));
+  unscale_host(host_dst, net->tensors[idx].numel, net->grad_scale);
   API_END
 }
 int gan_net_num_params(gan_net* net, int64_t* out) { *out = net->nparams; return GAN_OK; }
@@ -1299,6 +1334,7 @@ int gan_net_get_grads(gan_net* net, float* host_dst) {
   API_BEGIN
   CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
   CUDA_CHECK(cudaMemcpy(host_dst, net->grads.p, net->nparams * 4, cudaMemcpyDeviceToHost));
+  unscale_host(host_dst, net->nparams, net->grad_scale);
   API_END
 }
 

@@ -42,7 +42,8 @@ struct gan_ctx {
   int device = 0;
   int dt = DT_F32;            // mode: DT_F32 (FFMA parity mode) or DT_BF16 (= the 16-bit tcgen05 mode)
   int dtA = DT_F32;           // storage dtype of activations / forward weight packs (16-bit mode: DT_F16, see common.cuh)
-  int dtG = DT_F32;           // storage dtype of gradients / data-gradient weight packs (16-bit mode: DT_BF16)
+  int dtG = DT_F32;           // storage dtype of gradients / data-gradient weight packs (always == dtA, see common.cuh)
+  float grad_scale = 1.f;     // loss scale of the current step: every gradient buffer holds grad_scale x the true gradient
   cudaStream_t stream = nullptr;
   uint64_t seed = 0;
   uint32_t call_counter = 0;
@@ -150,6 +151,7 @@ struct gan_net {
   int ntrain = 0;
   int64_t nparams = 0, nmov = 0;
   DevBuf params, grads, mov;
+  float grad_scale = 1.f;     // loss scale the contents of `grads` carry (removed by Adam / by the gradient getters)
   std::vector<Slot> slots;
   bool packed_dirty = true;
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once

@@ -38,6 +38,9 @@ size_t stats_ws_floats(int G, int64_t Pg, int C);
 void launch_norm_stats(Launch L, int dt, const void* z, int G, int64_t Pg, int C, float* ws, float eps,
                        const float* gamma, const float* beta, float* mean, float* inv, float* scale,
                        float* shift, float* mov_mean, float* mov_var, float momentum);
+void launch_norm_stats_finalize(Launch L, const float* ws, int nparts, int64_t n, int C, float eps, const float* gamma,
+                                const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
+                                float* mov_var, float momentum);
 // out = act(dropout(z*scale+shift)); scale == nullptr => identity affine (no-norm layers).
 // One-kernel BatchNorm / InstanceNorm layer (G groups of P/G pixels) for small groups; returns false (nothing
 // launched) when a group's slab does not fit in shared memory.
@@ -55,8 +58,8 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz);
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
 // head backward written directly as slot-4 rows of the cols operand (bf16 path; dz is never materialised)
-void launch_ghead_bwd_cols(Launch L, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
-                           int H, int W, int C, void* gcols_bf16, float* dbias);
+void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
+                           int H, int W, int C, void* gcols, float* dbias);
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
                       float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias);
 // BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
@@ -102,7 +105,8 @@ void launch_conv_wgrad_ffma(Launch L, int dt_in, int dt_dy, const ConvOp& op);
 struct UmmaPlan;   // opaque: tensor maps + tiling for one (op, batch) pair
 bool umma_fwd_supported(const ConvOp& op);
 bool umma_wgrad_supported(const ConvOp& op);
-void launch_conv_fwd_umma(Launch L, const ConvOp& op);
+// returns the number of BatchNorm-statistics partials the epilogue wrote into op.stats_ws ([part][2][Nc]); 0 = none
+int launch_conv_fwd_umma(Launch L, const ConvOp& op);
 void launch_conv_wgrad_umma(Launch L, const ConvOp& op);
 void umma_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
 

@@ -51,8 +51,8 @@ def f16_round(a):
 
 
 def act_round(a, act="f16"):
-    """Rounding the device applies to ACTIVATION-side operands (layer inputs, forward weights) in the 16-bit mode:
-    fp16 by default, bf16 under GAN_B200_ACT=bf16.  Gradient-side operands are always bf16 (common.cuh)."""
+    """Rounding the device applies to the stored operands (activations, gradients, weight packs) in the 16-bit mode:
+    fp16 by default, bf16 under GAN_B200_ACT=bf16 (common.cuh)."""
     return f16_round(a) if act == "f16" else bf16_round(a)
 
 

@@ -2,17 +2,16 @@
 (gan_op_conv): Conv2D 4x4 s2 'same', ZeroPad+Conv2D 4x4 s1, Conv2DTranspose 4x4 s2 'same', each in
 forward / data-gradient / weight-gradient form, on the FFMA (fp32, 16-bit) and tcgen05 engines.
 
-16-bit mode operand formats (common.cuh): forward = f16 activations x f16 weights -> f16; data gradient =
-bf16 gradients x bf16 weights -> bf16; weight gradient = f16 activations x bf16 gradients -> fp32 (one
-tcgen05.mma with different A and B formats).  The oracle is fed operands rounded the same way, so what is
-left is accumulation order and the rounding of the stored result.  Both activation formats are run
-(GAN_B200_ACT=bf16 is round 1's all-bf16 storage)."""
+16-bit mode storage (common.cuh): fp16 for activations, gradients and both weight packs (tcgen05 kind::f16 needs
+A and B in the same format: an f16 x bf16 MMA faults as an illegal instruction on B200).  The oracle is fed
+operands rounded the same way, so what is left is accumulation order and the rounding of the stored result.
+Both storage formats are run (GAN_B200_ACT=bf16 is round 1's all-bf16 storage)."""
 import os
 
 import numpy as np
 import pytest
 
-from helpers import oracle_conv, oracle_conv_grads, rel_err, bf16_round, act_round
+from helpers import oracle_conv, oracle_conv_grads, rel_err, act_round
 
 pytestmark = pytest.mark.gpu
 
@@ -47,8 +46,7 @@ def _refs(ctx, kind, x, wt, dy):
     """Oracle results on operands rounded the way the device stores them."""
     a = ctx.act
     y_ref = oracle_conv(kind, act_round(x, a), act_round(wt, a)).numpy()
-    dx_ref, _ = oracle_conv_grads(kind, bf16_round(x), bf16_round(wt), bf16_round(dy))
-    _, dw_ref = oracle_conv_grads(kind, act_round(x, a), bf16_round(wt), bf16_round(dy))
+    dx_ref, dw_ref = oracle_conv_grads(kind, act_round(x, a), act_round(wt, a), act_round(dy, a))
     return y_ref, dx_ref, dw_ref
 
 
@@ -114,7 +112,7 @@ def test_umma_forward_dgrad_match_oracle(ctx16, kind, b, h, w, cin, cout):
     dx = ctx16.op_conv(kind, 1, dy, wt, b, h, w, cin, cout, engine=1)
     # rounding of the stored output is the only error source besides fp32 accumulation order
     assert rel_err(y, y_ref) < _out_tol(ctx16)
-    assert rel_err(dx, dx_ref) < 6e-3
+    assert rel_err(dx, dx_ref) < _out_tol(ctx16)
     # and the two engines agree to output rounding
     y_f = ctx16.op_conv(kind, 0, x, wt, b, h, w, cin, cout, engine=0)
     assert rel_err(y, y_f) < _out_tol(ctx16)
@@ -125,7 +123,7 @@ def test_umma_wgrad_matches_oracle(ctx16, kind, b, h, w, cin, cout):
     x, wt, dy = _case(kind, b, h, w, cin, cout, seed=4)
     _, _, dw_ref = _refs(ctx16, kind, x, wt, dy)
     dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=1)
-    assert rel_err(dw, dw_ref) < 1e-4        # f16 x bf16 operands, fp32 accumulate: exact products
+    assert rel_err(dw, dw_ref) < 1e-4        # 16-bit operands, fp32 accumulate: exact products
 
 
 SMALLC = [  # first layers (Cin in {1,3,6}) and heads (Cout in {1,3}): channel-padded tcgen05 paths
@@ -143,5 +141,5 @@ def test_umma_small_channel_layers(ctx16, kind, b, h, w, cin, cout):
     dx = ctx16.op_conv(kind, 1, dy, wt, b, h, w, cin, cout, engine=1)
     dw = ctx16.op_conv(kind, 2, x, dy, b, h, w, cin, cout, engine=1)
     assert rel_err(y, y_ref) < _out_tol(ctx16)
-    assert rel_err(dx, dx_ref) < 6e-3
+    assert rel_err(dx, dx_ref) < _out_tol(ctx16)
     assert rel_err(dw, dw_ref) < 1e-4
