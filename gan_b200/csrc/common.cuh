@@ -79,6 +79,11 @@ struct ConvOp {
   // optional: fp32 workspace [592][2][Nc] for per-channel sum / sum-of-squares partials produced by the conv epilogue
   // (BatchNorm layers on the CTA-pair tcgen05 kernel); the launcher reports how many partials it wrote
   float* stats_ws;
+  // wgrad: 0 = this launch is the first contribution to dW in the step (store), 1 = add to what is there; optional
+  // fp32 workspace for the split partial tiles of the deterministic two-stage reduction
+  int accumulate;
+  float* wgrad_ws; size_t wgrad_ws_bytes;
+  long long dW_elems;            // floats of the whole kernel tensor behind dW (the FFMA path zeroes it on a first contribution)
 };
 
 // ---- error handling (host) -----------------------------------------------------------------

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include "kernels.h"
 
 #define KLAUNCH(L) (++*(L).count)
@@ -720,6 +721,12 @@ static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile, int
 static bool env_on(const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); }
 static const bool g_use_2cta = env_on("GAN_B200_2CTA");
 static const bool g_epi_stats = env_on("GAN_B200_EPI_STATS");
+// CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters, filled by umma_init): a B200 has 148 of the die's
+// SMs enabled, and a TPC with one fused-off SM cannot host a pair, so this can be below 74.  The persistent grid must
+// not exceed it: a pair that waits for a free TPC would run its whole share of tiles after everybody else.
+static int g_f2_pairs[3] = {0, 0, 0};      // BN = 64, 128, 256
+static int f2_idx(int BN) { return BN == 64 ? 0 : (BN == 128 ? 1 : 2); }
+int umma2_max_pairs(int BN) { return g_f2_pairs[f2_idx(BN)]; }
 
 // CTA-pair path: returns true when it launched (and *stat_parts = number of statistics partials written).
 static bool launch_conv_fwd_umma2(Launch L, const ConvOp& op, int* stat_parts) {
@@ -735,7 +742,9 @@ static bool launch_conv_fwd_umma2(Launch L, const ConvOp& op, int* stat_parts) {
   P.num_tiles = ((mtiles + 1) / 2) * (op.Nc / BN) * op.ncls;     // pair tiles
   P.ksplit = 1; P.ws = nullptr; P.f32out = 0;
   P.stats_ws = (g_epi_stats && op.stats_ws != nullptr && op.Nc <= F2_STAT_NC) ? op.stats_ws : nullptr;
-  const int pairs = P.num_tiles < 74 ? P.num_tiles : 74;        // persistent: one CTA pair per TPC
+  const int max_pairs = g_f2_pairs[f2_idx(BN)];
+  if (max_pairs < 37) return false;                    // clusters not schedulable on (most of) this device
+  const int pairs = P.num_tiles < max_pairs ? P.num_tiles : max_pairs;        // persistent: one CTA pair per usable TPC
   dim3 grid(2 * pairs);
   const size_t sm = f2_smem_bytes(BN);
   if (BN == 256) k_conv_fwd_umma2<256><<<grid, F2_THREADS, sm, L.s>>>(P);
@@ -808,7 +817,12 @@ struct alignas(64) UmmaWgradParams {
   int Nc, Kr, Nr;
   int im2col_c;            // >0: rows are im2col K-blocks (t = source, kc = tap16*4 + channel slot)
   int n_slot4_c;           // >0: columns are (tap16*4 + channel slot) of a cols matrix
-  int a_bf16, b_bf16;      // operand formats: A = layer input (activation dtype), B = output gradient (bf16)
+  int a_bf16, b_bf16;      // operand formats (always equal: tcgen05 kind::f16 faults on mixed f16 / bf16 operands)
+  // Deterministic reduction.  splits > 1: every CTA stores its fp32 partial tile into slab[item][128][BN] (plain
+  // stores, item = ((cls*mblocks + mblock)*ntiles + ntile)*splits + split) and k_wgrad_reduce sums the `splits`
+  // tiles of an output tile in a fixed order.  splits == 1 (slab == nullptr): the CTA is the only writer of its
+  // tile and stores (accumulate == 0) or adds (accumulate == 1, non-atomic read-modify-write) straight into dW.
+  float* slab; int accumulate, mblocks, ntiles;
 };
 
 constexpr int WG_STAGES = 3;
@@ -915,27 +929,50 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         dst = p.dW + (long long)(kc >> 2) * p.s_tap + (long long)(t * ic + (kc & 3)) * p.s_k + (long long)n0 * p.s_n;
       }
       const bool vec_ok = p.s_n == 1 && p.n_slot4_c == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+      const bool acc_dst = p.accumulate != 0;
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
-      if (BN >= 32) {
+      if (p.slab != nullptr) {
+        // partial tile -> slab (plain 16-byte stores; every CTA owns its tile)
+        const long long item = (((long long)cls * p.mblocks + blockIdx.x) * p.ntiles + blockIdx.y) * p.splits + split;
+        float* sl = p.slab + (item * 128 + r) * (BN < 32 ? 16 : BN);
+        if (BN >= 32) {
+#pragma unroll
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(sl + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+          uint32_t v[16];
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(sl + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      } else if (BN >= 32) {
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
           if (row_ok && vec_ok && n0 + c + 32 <= p.Nr) {
-            // 16-byte vector reductions: a quarter of the L2 atomic transactions of the scalar form
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + j), "r"(v[j]), "r"(v[j + 1]),
-                           "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              float4* d4 = reinterpret_cast<float4*>(dst + c + j);
+              if (acc_dst) { const float4 a = *d4; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+              *d4 = o;
+            }
           } else if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int nn = n0 + c + j;
+              float* d1 = nullptr;
               if (p.n_slot4_c > 0) {      // cols column (tap*4 + slot) -> master row tap*C + slot
-                if ((nn & 3) < p.n_slot4_c)
-                  atomicAdd(p.dW + (long long)kc * p.s_k + (long long)((nn >> 2) * p.n_slot4_c + (nn & 3)) * p.s_n, __uint_as_float(v[j]));
-              } else if (nn < p.Nr) atomicAdd(dst + (long long)(c + j) * p.s_n, __uint_as_float(v[j]));
+                if ((nn & 3) < p.n_slot4_c) d1 = p.dW + (long long)kc * p.s_k + (long long)((nn >> 2) * p.n_slot4_c + (nn & 3)) * p.s_n;
+              } else if (nn < p.Nr) d1 = dst + (long long)(c + j) * p.s_n;
+              if (d1 != nullptr) *d1 = acc_dst ? *d1 + __uint_as_float(v[j]) : __uint_as_float(v[j]);
             }
           }
         }
@@ -945,14 +982,76 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (j < p.Nr) atomicAdd(dst + (long long)j * p.s_n, __uint_as_float(v[j]));
+            if (j < p.Nr) { float* d1 = dst + (long long)j * p.s_n; *d1 = acc_dst ? *d1 + __uint_as_float(v[j]) : __uint_as_float(v[j]); }
         }
       }
     }
+  } else if (p.slab != nullptr && warp >= 2) {
+    // empty pixel range (more splits than boxes cannot happen, kept for safety): the reduction still reads this tile
+    const int q = warp & 3, r = q * 32 + lane;
+    const long long item = (((long long)cls * p.mblocks + blockIdx.x) * p.ntiles + blockIdx.y) * p.splits + split;
+    float* sl = p.slab + (item * 128 + r) * (BN < 32 ? 16 : BN);
+    for (int j = 0; j < (BN < 32 ? 16 : BN); ++j) sl[j] = 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// Second stage of the deterministic weight-gradient reduction: one block per output tile sums the `splits` slab tiles
+// in a fixed order and scatters the result into the master (TF) weight layout, storing (first contribution of the
+// step) or adding (later contributions: the second discriminator call, CycleGAN's three generator calls).  The tile
+// goes through shared memory so that the global writes are coalesced along whichever index the master layout has
+// contiguous (output channel for Conv2D kernels, input channel for Conv2DTranspose kernels).
+struct WgradReduceParams {
+  const float* slab; float* dW;
+  int splits, bn, mblocks, ntiles, ncls, accumulate;
+  int Kc, Kr, Nr, im2col_c, n_slot4_c;
+  long long s_tap, s_k, s_n;
+  int ntaps[4]; int8_t widx[4][16];
+};
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p) {
+  extern __shared__ float tile[];                       // [128][bn + 1]
+  const int bn = p.bn, pitch = bn + 1;
+  int b = blockIdx.x;
+  const int ntile = b % p.ntiles; b /= p.ntiles;
+  const int mblock = b % p.mblocks; const int cls = b / p.mblocks;
+  const float* base = p.slab + ((long long)blockIdx.x * p.splits) * 128 * bn;
+  const int total = 128 * bn;
+  for (int i = threadIdx.x * 4; i < total; i += 256 * 4) {
+    float4 a = *reinterpret_cast<const float4*>(base + i);
+    for (int sp = 1; sp < p.splits; ++sp) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (long long)sp * total + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const int r = i / bn, c = i - r * bn;
+    float* t = tile + r * pitch + c;
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
+  }
+  __syncthreads();
+  const bool along_n = p.s_n == 1;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    int r, c;
+    if (along_n) { r = i / bn; c = i - r * bn; } else { c = i >> 7; r = i & 127; }
+    const int k = mblock * 128 + r;
+    const int t = k / p.Kc, kc = k - t * p.Kc;
+    if (t >= p.ntaps[cls]) continue;
+    const int nn = ntile * bn + c;
+    long long off;
+    if (p.im2col_c > 0) {
+      if ((kc & 3) >= p.im2col_c || nn >= p.Nr) continue;
+      off = (long long)(kc >> 2) * p.s_tap + (long long)(t * p.im2col_c + (kc & 3)) * p.s_k + (long long)nn * p.s_n;
+    } else if (p.n_slot4_c > 0) {
+      if (kc >= p.Kr || (nn & 3) >= p.n_slot4_c) continue;
+      off = (long long)kc * p.s_k + (long long)((nn >> 2) * p.n_slot4_c + (nn & 3)) * p.s_n;
+    } else {
+      if (kc >= p.Kr || nn >= p.Nr) continue;
+      off = (long long)p.widx[cls][t & 15] * p.s_tap + (long long)kc * p.s_k + (long long)nn * p.s_n;
+    }
+    const float v = tile[r * pitch + c];
+    p.dW[off] = p.accumulate ? p.dW[off] + v : v;
+  }
 }
 
 static size_t wg_smem_bytes(int BN) {
@@ -1012,7 +1111,12 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   int splits = (int)((148 * 2) / ctas);
   if (splits > total_boxes) splits = total_boxes;
   if (splits < 1) splits = 1;
+  const int bn_slab = BN < 32 ? 16 : BN;
+  if (splits > 1 && (op.wgrad_ws == nullptr || (size_t)ctas * splits * 128 * bn_slab * 4 > op.wgrad_ws_bytes)) splits = 1;
   P.splits = splits;
+  P.mblocks = mblocks; P.ntiles = ntiles;
+  P.slab = splits > 1 ? op.wgrad_ws : nullptr;
+  P.accumulate = op.accumulate;
   dim3 grid(mblocks, ntiles, op.ncls * splits);
   const size_t sm = wg_smem_bytes(BN);
   if (KCA == 64) {
@@ -1024,6 +1128,15 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
     else k_conv_wgrad_umma<64, 16><<<grid, FWD_THREADS, sm, L.s>>>(P);
   }
   KLAUNCH(L);
+  if (splits > 1) {
+    WgradReduceParams R; memset(&R, 0, sizeof(R));
+    R.slab = op.wgrad_ws; R.dW = op.dW; R.splits = splits; R.bn = bn_slab; R.mblocks = mblocks; R.ntiles = ntiles; R.ncls = op.ncls;
+    R.accumulate = op.accumulate; R.Kc = op.Kc; R.Kr = op.Kr; R.Nr = op.Nr; R.im2col_c = P.im2col_c; R.n_slot4_c = op.n_slot4_c;
+    R.s_tap = op.s_tap; R.s_k = op.s_k; R.s_n = op.s_n;
+    for (int c = 0; c < op.ncls; ++c) { R.ntaps[c] = op.cls[c].ntaps; for (int t = 0; t < op.cls[c].ntaps; ++t) R.widx[c][t] = op.cls[c].widx[t]; }
+    k_wgrad_reduce<<<(unsigned)ctas, 256, (size_t)128 * (bn_slab + 1) * 4, L.s>>>(R);
+    KLAUNCH(L);
+  }
 }
 
 void umma_init() {
@@ -1038,12 +1151,27 @@ void umma_init() {
     SET_SMEM((k_conv_fwd_umma2<256>), f2_smem_bytes(256));
     SET_SMEM((k_conv_fwd_umma2<128>), f2_smem_bytes(128));
     SET_SMEM((k_conv_fwd_umma2<64>), f2_smem_bytes(64));
+    auto query = [](const void* kern, int BN) {
+      cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(148); cfg.blockDim = dim3(F2_THREADS); cfg.dynamicSmemBytes = f2_smem_bytes(BN);
+      cudaLaunchAttribute at; memset(&at, 0, sizeof(at));
+      at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      g_f2_pairs[f2_idx(BN)] = n > 74 ? 74 : n;
+    };
+    query((const void*)k_conv_fwd_umma2<256>, 256);
+    query((const void*)k_conv_fwd_umma2<128>, 128);
+    query((const void*)k_conv_fwd_umma2<64>, 64);
+    if (getenv("GAN_B200_DEBUG")) fprintf(stderr, "[gan_b200] active CTA pairs: N=64 %d, N=128 %d, N=256 %d\n", g_f2_pairs[0], g_f2_pairs[1], g_f2_pairs[2]);
     SET_SMEM((k_conv_fwd_umma<256, 64>), fwd_smem_bytes(256));
     SET_SMEM((k_conv_fwd_umma<128, 64>), fwd_smem_bytes(128));
     SET_SMEM((k_conv_fwd_umma<64, 64>), fwd_smem_bytes(64));
     SET_SMEM((k_conv_fwd_umma<16, 64>), fwd_smem_bytes(16));
     SET_SMEM((k_conv_fwd_umma<128, 16>), fwd_smem_bytes(128));
     SET_SMEM((k_conv_fwd_umma<64, 16>), fwd_smem_bytes(64));
+    SET_SMEM(k_wgrad_reduce, 128 * 129 * 4);
     SET_SMEM((k_conv_wgrad_umma<128, 64>), wg_smem_bytes(128));
     SET_SMEM((k_conv_wgrad_umma<64, 64>), wg_smem_bytes(64));
     SET_SMEM((k_conv_wgrad_umma<16, 64>), wg_smem_bytes(16));

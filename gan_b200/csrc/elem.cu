@@ -423,8 +423,19 @@ __global__ void __launch_bounds__(32 * FIN_LANES) k_bwd_finalize(const float* __
   fin_reduce(ws, g, nchunk, C, c, lane, S, Q);
   if (lane != 0 || c >= C) return;
   c1[(size_t)g * C + c] = (float)(S / n); c2[(size_t)g * C + c] = (float)(Q / n);
-  // parameter gradients sum over the groups (InstanceNorm: over samples); one add per channel for BatchNorm
-  atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
+  // parameter gradients: BatchNorm has one group, so this is the only writer of the channel in this launch (launches of
+  // a step are ordered by the stream: deterministic).  InstanceNorm sums over its groups in k_group_param_grads.
+  if (G == 1) { dbeta[c] += (float)S; dgamma[c] += (float)Q; }
+}
+
+// InstanceNorm: dbeta[c] += sum_g n*c1[g][c], dgamma[c] += sum_g n*c2[g][c], groups in index order (deterministic)
+__global__ void __launch_bounds__(256) k_group_param_grads(const float* __restrict__ c1, const float* __restrict__ c2, int G, int C,
+                                                           float n, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float sb = 0.f, sg = 0.f;
+  for (int g = 0; g < G; ++g) { sb += c1[(size_t)g * C + c] * n; sg += c2[(size_t)g * C + c] * n; }
+  dbeta[c] += sb; dgamma[c] += sg;
 }
 
 template <typename TZ, typename T, bool DROP>
@@ -651,7 +662,7 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
     float a = (float)(S / n), b = (float)(Q / n);
     c1[gi + c] = a; c2[gi + c] = b;
     par[threadIdx.x] = a; par[V + threadIdx.x] = b;
-    atomicAdd(dbeta + c, (float)S); atomicAdd(dgamma + c, (float)Q);
+    if (gridDim.y == 1) { dbeta[c] += (float)S; dgamma[c] += (float)Q; }     // one group: only writer (see k_bwd_finalize)
   }
   __syncthreads();
   float k1[V], k2[V];
@@ -716,6 +727,7 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
       kern<<<dim3(C / VecIO<T>::N, G), BNS_THREADS, (size_t)Pg * narr * 16, L.s>>>((const TZ*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, mean,
                                                                          inv, scale, shift, act, dk, c1, c2, dgamma, dbeta, (T*)dz);
       KLAUNCH(L);
+      if (G > 1) { k_group_param_grads<<<(C + 255) / 256, 256, 0, L.s>>>(c1, c2, G, C, (float)Pg, dgamma, dbeta); KLAUNCH(L); }
       return;
     }
     if (norm != NORM_NONE) {
@@ -725,6 +737,7 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
       KLAUNCH(L);
       k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
       KLAUNCH(L);
+      if (G > 1) { k_group_param_grads<<<(C + 255) / 256, 256, 0, L.s>>>(c1, c2, G, C, (float)Pg, dgamma, dbeta); KLAUNCH(L); }
     }
     auto kapp = dk.enabled ? k_bwd_apply<TZ, T, true> : k_bwd_apply<TZ, T, false>;
     kapp<<<norm_grid(P, cv, narr == 3 ? 2 : 3), 256, smem, L.s>>>((const TZ*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW,
@@ -767,19 +780,31 @@ __global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-      atomicAdd(dbias + k, t);
+      dbias[(size_t)blockIdx.x * 4 + k] = t;             // per-block partial (summed in block order by k_sum_partials)
     }
   }
 }
+// dst[k] += sum over blocks (in index order) of part[block][k]: deterministic bias gradient of the generator head
+__global__ void k_sum_partials(const float* __restrict__ part, int nblocks, int C, float* dst) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (k >= C) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += (double)part[(size_t)b * 4 + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dst[k] += (float)s;
+}
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
-                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias) {
+                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part) {
   GAN_REQUIRE(C <= 4, "generator head supports up to 4 output channels");
   int64_t total = P * C;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_ghead_bwd<T><<<grid_for(total, 256, 4), 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dz_pitch, dbias);
+    const int grid = grid_for(total, 256, 4);
+    GAN_REQUIRE(grid <= HEAD_PART_BLOCKS, "bias partial workspace too small");
+    k_ghead_bwd<T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dz_pitch, part);
+    k_sum_partials<<<1, 128, 0, L.s>>>(part, grid, C, dbias);
   });
-  KLAUNCH(L);
+  KLAUNCH(L); KLAUNCH(L);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -814,6 +839,7 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
   }
   block_partial_store(acc, loss_slot + blockIdx.x);
   if (dz != nullptr && dbias != nullptr) {
+    // launched with ONE block in this case (launch_bce): a single, ordered read-modify-write of the bias gradient
     __syncthreads();
     __shared__ float shb[8];
     float v = warp_sum(bacc);
@@ -822,7 +848,7 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < 8; ++w) t += shb[w];
-      atomicAdd(dbias, t);
+      *dbias += t;
     }
   }
 }
@@ -830,6 +856,7 @@ void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, f
                 float* dbias, float* loss_ws, int slot) {
   int blocks = grid_for(n, 256, 1);
   if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+  if (dz != nullptr && dbias != nullptr) blocks = 1;     // deterministic bias gradient (n = B*900 .. B*3844 logits: microseconds)
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dz_pitch, dbias, loss_ws + slot * LOSS_BLOCKS);
@@ -1116,6 +1143,16 @@ void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, i
   KLAUNCH(L);
 }
 
+__global__ void __launch_bounds__(256) k_zero_ranges(float* __restrict__ g, const AdamRange* __restrict__ tab) {
+  const AdamRange r = tab[blockIdx.x];
+  for (int i = threadIdx.x; i < r.n; i += 256) g[r.off + i] = 0.f;
+}
+void launch_zero_ranges(Launch L, float* g, const AdamRange* tab_dev, int nranges) {
+  if (nranges <= 0) return;
+  k_zero_ranges<<<nranges, 256, 0, L.s>>>(g, tab_dev);
+  KLAUNCH(L);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_sum_slabs(const float* __restrict__ slabs, int nslab, int64_t total, int C,
                                                    T* __restrict__ dst, int pitch, int coff) {
@@ -1243,25 +1280,28 @@ __global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict_
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += sh[wi];
-      atomicAdd(dbias + k, t);
+      dbias[(size_t)blockIdx.x * 4 + k] = t;             // per-block partial (k_sum_partials)
     }
   }
 }
 void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
-                           int H, int W, int C, void* gcols, float* dbias) {
+                           int H, int W, int C, void* gcols, float* dbias, float* part) {
   GAN_REQUIRE(C >= 1 && C <= 4, "generator head supports up to 4 output channels");
   GAN_REQUIRE(dt == DT_F16 || dt == DT_BF16, "cols path is 16-bit only");
   const int64_t M = (int64_t)B * (H / 2) * (W / 2);
   const int grid = grid_for(M * 8, 256, 16);
+  GAN_REQUIRE(grid <= HEAD_PART_BLOCKS, "bias partial workspace too small");
   auto run = [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     T* d = (T*)gcols;
-    if (C == 1) k_ghead_bwd_cols<1, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
-    else if (C == 2) k_ghead_bwd_cols<2, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
-    else if (C == 3) k_ghead_bwd_cols<3, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
-    else k_ghead_bwd_cols<4, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias);
+    if (C == 1) k_ghead_bwd_cols<1, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
+    else if (C == 2) k_ghead_bwd_cols<2, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
+    else if (C == 3) k_ghead_bwd_cols<3, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
+    else k_ghead_bwd_cols<4, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
   };
   if (dt == DT_F16) run((f16*)nullptr); else run((bf16*)nullptr);
+  KLAUNCH(L);
+  k_sum_partials<<<1, 128, 0, L.s>>>(part, grid, C, dbias);
   KLAUNCH(L);
 }
 

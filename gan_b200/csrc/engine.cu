@@ -215,13 +215,23 @@ static int run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
   launch_conv_fwd_ffma(ctx->L(), op.dt_in, op);
   return 0;
 }
-static void run_conv_wgrad(gan_ctx* ctx, const ConvOp& op) {
+// ly: the layer whose kernel gradient is produced.  The first contribution of a step STORES (no zeroing pass over the
+// 57 M-float gradient buffer), later ones (second discriminator call, CycleGAN's repeated generator calls) add.
+static void run_conv_wgrad(gan_ctx* ctx, Layer& ly, const ConvOp& op_in) {
+  ConvOp op = op_in;
+  op.accumulate = ly.wgrad_epoch == ctx->step_epoch ? 1 : 0;
+  ly.wgrad_epoch = ctx->step_epoch;
+  op.dW_elems = 16LL * ly.Cin * ly.Cout;
+  ctx->wgrad_ws.ensure((size_t)24 << 20);              // <= 296 partial tiles of 128 x 128 fp32 per launch
+  op.wgrad_ws = ctx->wgrad_ws.as<float>(); op.wgrad_ws_bytes = ctx->wgrad_ws.bytes;
   bool can = ctx->dt == DT_BF16 && umma_wgrad_supported(op);
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
   ProfScope ps(ctx, um ? FAM_UMMA_WGRAD : FAM_FFMA_WGRAD, conv_flops(op));
-  if (um) launch_conv_wgrad_umma(ctx->L(), op);
-  else launch_conv_wgrad_ffma(ctx->L(), op.dt_in, op.dt_out, op);
+  if (um) { launch_conv_wgrad_umma(ctx->L(), op); return; }
+  // CUDA-core path (fp32 parity mode, odd shapes): split-M partial sums meet in fp32 atomics, so the tensor is zeroed first
+  if (!op.accumulate) CUDA_CHECK(cudaMemsetAsync(op.dW, 0, (size_t)op.dW_elems * 4, ctx->stream));
+  launch_conv_wgrad_ffma(ctx->L(), op.dt_in, op.dt_out, op);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -488,7 +498,7 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
   if (want_wgrad) {
     ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_WGRAD, s, dz) : make_op(ctx, ly, R_WGRAD, in, dz, nullptr);
     op.dW = n->grads.as<float>() + ly.w_off;
-    run_conv_wgrad(ctx, op);
+    run_conv_wgrad(ctx, ly, op);
   }
   if (din.p != nullptr) {
     GAN_REQUIRE(ly.need_dgrad, "dgrad weights not packed");
@@ -569,14 +579,15 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   float* gr = g->grads.as<float>();
   // head
   const int Cp = g->Cp;
+  ctx->head_part.ensure((size_t)HEAD_PART_BLOCKS * 4 * 4);
   if (s.used_cols) {
     s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
     launch_ghead_bwd_cols(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, B, H, W, C, s.gcols.p,
-                          gr + g->layers[15].bias_off);
+                          gr + g->layers[15].bias_off, ctx->head_part.as<float>());
   } else {
     s.dlogit.ensure((size_t)B * H * W * Cp * es);
     launch_ghead_bwd(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
-                     gr + g->layers[15].bias_off);
+                     gr + g->layers[15].bias_off, ctx->head_part.as<float>());
   }
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
@@ -593,7 +604,7 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
       ConvOp wg = make_op_1tap(x, lh.Cin, G, 64, 64, nullptr, ctx->dtA, ctx->dtG);
       wg.dW = gr + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = C;
       wg.real_n = 16 * C;
-      run_conv_wgrad(ctx, wg);
+      run_conv_wgrad(ctx, lh, wg);
       ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p, ctx->dtG, ctx->dtG);
       dg.real_k = 16 * C;
       run_conv_fwd(ctx, dg);
@@ -692,7 +703,7 @@ static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool w
         ConvOp wg = make_op_1tap(in, lh.Cin, G, 64, 64, nullptr, ctx->dtA, ctx->dtG);
         wg.dW = d->grads.as<float>() + lh.w_off; wg.s_tap = 0; wg.s_k = 1; wg.s_n = lh.Cin; wg.n_slot4_c = 1;
         wg.real_n = 16;
-        run_conv_wgrad(ctx, wg);
+        run_conv_wgrad(ctx, lh, wg);
       }
       ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p, ctx->dtG, ctx->dtG);
       dg.real_k = 16;
@@ -749,8 +760,13 @@ static void copy_out(gan_ctx* ctx, float* dst, const float* src_dev, size_t byte
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
 }
+static void build_adam_tables(gan_net* n);
+// Kernel gradients are stored (not accumulated) by the first weight-gradient launch of a step, so only the small
+// gamma / beta / bias ranges, which the norm and head kernels accumulate into, are zeroed (one launch per net instead of
+// a 229 MB memset per step).
 static void zero_grads(gan_net* n) {
-  CUDA_CHECK(cudaMemsetAsync(n->grads.p, 0, (size_t)n->nparams * 4, n->ctx->stream));
+  if (n->adam_nent == 0) build_adam_tables(n);
+  launch_zero_ranges(n->ctx->L(), n->grads.as<float>(), (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
 }
 static void build_adam_tables(gan_net* n) {
   pack_weights(n);                                   // makes sure the packed buffers exist
@@ -1689,7 +1705,8 @@ int gan_op_conv(gan_ctx* ctx, int kind, int role, int engine, const float* a, co
       CUDA_CHECK(cudaMemsetAsync(fo.p, 0, nw * 4, ctx->stream));
       ConvOp op = make_op(ctx, ly, R_WGRAD, x, y, nullptr);
       op.dW = fo.as<float>();
-      run_conv_wgrad(ctx, op);
+      ly.wgrad_epoch = 0;                      // first contribution: the kernel must define every element itself
+      run_conv_wgrad(ctx, ly, op);
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       CUDA_CHECK(cudaMemcpy(out, fo.p, nw * 4, cudaMemcpyDeviceToHost));
     }

@@ -53,7 +53,7 @@ struct gan_ctx {
   int64_t sample0 = 0;
   bool sample0_set = false;
   uint64_t launches = 0;
-  DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk, splitk_ws;
+  DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk, splitk_ws, wgrad_ws, head_part;
   DevBuf stage[4];
   // im2col rows of step inputs shared between nets (x feeds G.down1, D(real).down1 and D(fake).down1)
   struct Im2colEntry { const void* src = nullptr; int B = 0, H = 0, W = 0, C = 0; uint64_t epoch = 0; DevBuf buf; };
@@ -112,6 +112,7 @@ struct Layer {
   int Cin_p = 0, Cout_p = 0;     // channel counts as stored (zero-padded to 16 in bf16 mode when < 16)
   bool bias = false, dropout = false, need_dgrad = true, head = false;
   int tag = 0;
+  uint64_t wgrad_epoch = 0;      // step in which this layer's weight gradient was last written (first write stores, later ones add)
   int64_t w_off = -1, g_off = -1, b_off = -1, bias_off = -1, mov_off = -1;
   DevBuf wp_fwd, wp_dgrad;
   // first layers in bf16/tcgen05 mode: GEMM over im2col buffers (one 64-wide K-block per input source)

@@ -10,6 +10,7 @@ struct Launch {
 #define STATS_MAX_CHUNKS 592   // 4 x 148 SMs
 #define LOSS_SLOTS 16
 #define LOSS_BLOCKS 256
+#define HEAD_PART_BLOCKS 4096   // per-block bias-gradient partials of the generator-head backward (4 floats each)
 
 // ---- elem.cu --------------------------------------------------------------------------------
 void launch_convert(Launch L, int dt, const float* src, int64_t P, int C, void* dst, int pitch, int coff);
@@ -59,9 +60,9 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
 // head backward written directly as slot-4 rows of the cols operand (bf16 path; dz is never materialised)
 void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
-                           int H, int W, int C, void* gcols, float* dbias);
+                           int H, int W, int C, void* gcols, float* dbias, float* part_ws);
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
-                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias);
+                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part_ws);
 // BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
 void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
                 float* dbias, float* loss_ws, int slot);
@@ -96,6 +97,8 @@ struct AdamRange { long long off; int n, pad; };
 struct AdamArgs { float* p; const float* g; float* m; float* v; const long long* t_dev; double lr, b1, b2; float eps, gscale; };
 void launch_adam_pack(Launch L, int dt_fwd, int dt_dgrad, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles);
 void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, int nranges);
+// zero the gamma / beta / bias gradient ranges (the kernels that produce them accumulate)
+void launch_zero_ranges(Launch L, float* g, const AdamRange* tab_dev, int nranges);
 
 // ---- conv_ffma.cu ---------------------------------------------------------------------------
 void launch_conv_fwd_ffma(Launch L, int dt, const ConvOp& op);

@@ -120,6 +120,6 @@ def test_reference_predict_flow_restores_into_unbound_optimizers(tmp_path):
     a.train_step(x, y, True); b.train_step(x, y, True)
     assert b.generator_optimizer.iterations == 3
     for which in ("m", "v"):
-        assert np.allclose(a.generator_optimizer.get_state(which), b.generator_optimizer.get_state(which), rtol=0, atol=1e-7)
+        assert np.allclose(a.generator_optimizer.get_state(which), b.generator_optimizer.get_state(which), rtol=1e-5, atol=1e-7)
     assert np.abs(a.generator.get_flat_params() - b.generator.get_flat_params()).max() <= 2 * 2e-4 * 1.01
     a.ctx.close(); b.ctx.close()
