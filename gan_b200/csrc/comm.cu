@@ -14,6 +14,9 @@ typedef void* ncclComm_t_;
 typedef int (*fn_getuid)(ncclUniqueId_t*);
 typedef int (*fn_initrank)(ncclComm_t_*, int, ncclUniqueId_t, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+typedef int (*fn_reducescatter)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t);
+typedef int (*fn_group)(void);
 typedef int (*fn_destroy)(ncclComm_t_);
 typedef const char* (*fn_errstr)(int);
 
@@ -21,6 +24,7 @@ static struct {
   void* lib = nullptr;
   fn_getuid getuid = nullptr; fn_initrank initrank = nullptr; fn_allreduce allreduce = nullptr;
   fn_destroy destroy = nullptr; fn_errstr errstr = nullptr;
+  fn_reducescatter reducescatter = nullptr; fn_allgather allgather = nullptr; fn_group group_start = nullptr, group_end = nullptr;
 } g_nccl;
 
 static void nccl_load() {
@@ -33,7 +37,12 @@ static void nccl_load() {
   g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
-  if (!g_nccl.getuid || !g_nccl.initrank || !g_nccl.allreduce || !g_nccl.destroy)
+  g_nccl.reducescatter = (fn_reducescatter)dlsym(g_nccl.lib, "ncclReduceScatter");
+  g_nccl.allgather = (fn_allgather)dlsym(g_nccl.lib, "ncclAllGather");
+  g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
+  if (!g_nccl.getuid || !g_nccl.initrank || !g_nccl.allreduce || !g_nccl.destroy || !g_nccl.reducescatter || !g_nccl.allgather ||
+      !g_nccl.group_start || !g_nccl.group_end)
     throw GanError(-4, "libnccl is missing required symbols");
 }
 static void nccl_check(int r, const char* what) {
@@ -87,6 +96,33 @@ void comm_allreduce_async(gan_ctx* ctx, float* buf, int64_t n) {
   CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, e, 0));
   nccl_check(g_nccl.allreduce(buf, buf, (size_t)n, 7, 0, (ncclComm_t_)ctx->comm, ctx->comm_stream), "ncclAllReduce");
   ctx->comm_pending = true;
+}
+
+// Sharded form (ZeRO-1 style): the bucket [buf, buf+n) (n a multiple of world) is reduce-scattered in
+// place — rank r ends up with the sum of sub-range r, [buf + r*n/world, +n/world) — on the communication stream.
+void comm_reducescatter_async(gan_ctx* ctx, float* buf, int64_t n) {
+  if (ctx->world <= 1 || n <= 0) return;
+  GAN_REQUIRE(ctx->comm != nullptr, "communicator not initialised");
+  GAN_REQUIRE(n % ctx->world == 0, "reduce-scatter bucket must divide evenly over the ranks");
+  const int64_t cnt = n / ctx->world;
+  cudaEvent_t e = next_event(ctx);
+  CUDA_CHECK(cudaEventRecord(e, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, e, 0));
+  nccl_check(g_nccl.reducescatter(buf, buf + (int64_t)ctx->rank * cnt, (size_t)cnt, 7, 0, (ncclComm_t_)ctx->comm, ctx->comm_stream),
+             "ncclReduceScatter");
+  ctx->comm_pending = true;
+}
+// All-gather (in place) of the ranks' updated sub-ranges of several buckets as ONE grouped NCCL launch on the ctx stream.
+void comm_allgather_buckets(gan_ctx* ctx, float* base, const int64_t* off, const int64_t* len, int nb) {
+  if (ctx->world <= 1 || nb <= 0) return;
+  GAN_REQUIRE(ctx->comm != nullptr, "communicator not initialised");
+  nccl_check(g_nccl.group_start(), "ncclGroupStart");
+  for (int i = 0; i < nb; ++i) {
+    const int64_t cnt = len[i] / ctx->world;
+    nccl_check(g_nccl.allgather(base + off[i] + (int64_t)ctx->rank * cnt, base + off[i], (size_t)cnt, 7, (ncclComm_t_)ctx->comm, ctx->stream),
+               "ncclAllGather");
+  }
+  nccl_check(g_nccl.group_end(), "ncclGroupEnd");
 }
 
 void comm_join(gan_ctx* ctx) {

@@ -721,6 +721,9 @@ static void fill_fwd_params(UmmaFwdParams& P, const ConvOp& op, int bn_tile, int
 static bool env_on(const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); }
 static const bool g_use_2cta = env_on("GAN_B200_2CTA");
 static const bool g_epi_stats = env_on("GAN_B200_EPI_STATS");
+// smallest MMA N the CTA-pair kernel takes (measured: below N = 256 one CTA pair per TPC loses to two independent CTAs
+// per SM, whose k-block round trips overlap)
+static const int g_2cta_min_bn = [] { const char* e = getenv("GAN_B200_2CTA_MIN_N"); return e ? atoi(e) : 256; }();
 // CTA pairs that can be co-resident (cudaOccupancyMaxActiveClusters, filled by umma_init): a B200 has 148 of the die's
 // SMs enabled, and a TPC with one fused-off SM cannot host a pair, so this can be below 74.  The persistent grid must
 // not exceed it: a pair that waits for a free TPC would run its whole share of tiles after everybody else.
@@ -735,6 +738,7 @@ static bool launch_conv_fwd_umma2(Launch L, const ConvOp& op, int* stat_parts) {
   if (op.Kc % 64 != 0 || op.Nc % 64 != 0 || op.out == nullptr) return false;
   if (op.epi != EPI_NONE || op.out_f32 != nullptr || op.out_rows_f32 != nullptr) return false;
   const int BN = (op.Nc % 256 == 0) ? 256 : (op.Nc % 128 == 0 ? 128 : 64);
+  if (BN < g_2cta_min_bn) return false;
   UmmaFwdParams P;
   fill_fwd_params(P, op, BN / 2, 64);                 // each CTA of the pair loads half of the weight tile's rows
   const int mtiles = P.tiles_w * P.tiles_h * P.tiles_n;
@@ -1001,9 +1005,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
 
 // Second stage of the deterministic weight-gradient reduction: one block per output tile sums the `splits` slab tiles
 // in a fixed order and scatters the result into the master (TF) weight layout, storing (first contribution of the
-// step) or adding (later contributions: the second discriminator call, CycleGAN's three generator calls).  The tile
-// goes through shared memory so that the global writes are coalesced along whichever index the master layout has
-// contiguous (output channel for Conv2D kernels, input channel for Conv2DTranspose kernels).
+// step) or adding (later contributions: the second discriminator call, CycleGAN's three generator calls).
 struct WgradReduceParams {
   const float* slab; float* dW;
   int splits, bn, mblocks, ntiles, ncls, accumulate;
@@ -1012,32 +1014,33 @@ struct WgradReduceParams {
   int ntaps[4]; int8_t widx[4][16];
 };
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p) {
-  extern __shared__ float tile[];                       // [128][bn + 1]
-  const int bn = p.bn, pitch = bn + 1;
-  int b = blockIdx.x;
+  // grid = (output tiles) x (bn/8 sub-tiles of 1024 elements): one float4 per thread.  Sub-tiles are row strips
+  // (1024/bn rows x bn columns) when the master layout is contiguous along the output channel, column strips
+  // (128 rows x 8 columns) when it is contiguous along the row index, so that a warp's stores form long runs.
+  const int bn = p.bn;
+  const int sub = blockIdx.x % (bn / 8);
+  int b = blockIdx.x / (bn / 8);
+  const long long tile_idx = b;
   const int ntile = b % p.ntiles; b /= p.ntiles;
   const int mblock = b % p.mblocks; const int cls = b / p.mblocks;
-  const float* base = p.slab + ((long long)blockIdx.x * p.splits) * 128 * bn;
-  const int total = 128 * bn;
-  for (int i = threadIdx.x * 4; i < total; i += 256 * 4) {
-    float4 a = *reinterpret_cast<const float4*>(base + i);
-    for (int sp = 1; sp < p.splits; ++sp) {
-      const float4 v = *reinterpret_cast<const float4*>(base + (long long)sp * total + i);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
-    const int r = i / bn, c = i - r * bn;
-    float* t = tile + r * pitch + c;
-    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
-  }
-  __syncthreads();
   const bool along_n = p.s_n == 1;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    int r, c;
-    if (along_n) { r = i / bn; c = i - r * bn; } else { c = i >> 7; r = i & 127; }
-    const int k = mblock * 128 + r;
-    const int t = k / p.Kc, kc = k - t * p.Kc;
-    if (t >= p.ntaps[cls]) continue;
-    const int nn = ntile * bn + c;
+  int r, c;
+  if (along_n) { const int e = threadIdx.x * 4; const int rt = 1024 / bn; r = sub * rt + e / bn; c = e % bn; }
+  else { r = threadIdx.x >> 1; c = sub * 8 + (threadIdx.x & 1) * 4; }
+  const int total = 128 * bn;
+  const float* base = p.slab + (tile_idx * p.splits) * total + (long long)r * bn + c;
+  float4 a = *reinterpret_cast<const float4*>(base);
+  for (int sp = 1; sp < p.splits; ++sp) {                  // fixed order: deterministic
+    const float4 v = *reinterpret_cast<const float4*>(base + (long long)sp * total);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const int k = mblock * 128 + r;
+  const int t = k / p.Kc, kc = k - t * p.Kc;
+  if (t >= p.ntaps[cls]) return;
+  const float vals[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int nn = ntile * bn + c + e;
     long long off;
     if (p.im2col_c > 0) {
       if ((kc & 3) >= p.im2col_c || nn >= p.Nr) continue;
@@ -1049,8 +1052,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p)
       if (kc >= p.Kr || nn >= p.Nr) continue;
       off = (long long)p.widx[cls][t & 15] * p.s_tap + (long long)kc * p.s_k + (long long)nn * p.s_n;
     }
-    const float v = tile[r * pitch + c];
-    p.dW[off] = p.accumulate ? p.dW[off] + v : v;
+    p.dW[off] = p.accumulate ? p.dW[off] + vals[e] : vals[e];
   }
 }
 
@@ -1134,7 +1136,7 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
     R.accumulate = op.accumulate; R.Kc = op.Kc; R.Kr = op.Kr; R.Nr = op.Nr; R.im2col_c = P.im2col_c; R.n_slot4_c = op.n_slot4_c;
     R.s_tap = op.s_tap; R.s_k = op.s_k; R.s_n = op.s_n;
     for (int c = 0; c < op.ncls; ++c) { R.ntaps[c] = op.cls[c].ntaps; for (int t = 0; t < op.cls[c].ntaps; ++t) R.widx[c][t] = op.cls[c].widx[t]; }
-    k_wgrad_reduce<<<(unsigned)ctas, 256, (size_t)128 * (bn_slab + 1) * 4, L.s>>>(R);
+    k_wgrad_reduce<<<(unsigned)(ctas * (bn_slab / 8)), 256, 0, L.s>>>(R);
     KLAUNCH(L);
   }
 }
@@ -1171,7 +1173,6 @@ void umma_init() {
     SET_SMEM((k_conv_fwd_umma<16, 64>), fwd_smem_bytes(16));
     SET_SMEM((k_conv_fwd_umma<128, 16>), fwd_smem_bytes(128));
     SET_SMEM((k_conv_fwd_umma<64, 16>), fwd_smem_bytes(64));
-    SET_SMEM(k_wgrad_reduce, 128 * 129 * 4);
     SET_SMEM((k_conv_wgrad_umma<128, 64>), wg_smem_bytes(128));
     SET_SMEM((k_conv_wgrad_umma<64, 64>), wg_smem_bytes(64));
     SET_SMEM((k_conv_wgrad_umma<16, 64>), wg_smem_bytes(16));

@@ -276,8 +276,9 @@ static void finish_net(gan_net* n) {
         add_tensor(n, ly.name + ".moving_mean", {ly.Cout}, n->nmov, false);
         add_tensor(n, ly.name + ".moving_variance", {ly.Cout}, n->nmov, false);
       }
-  n->params.ensure((size_t)(n->nparams + 4) * 4);
-  n->grads.ensure((size_t)(n->nparams + 4) * 4);
+  // + slack: data-parallel buckets are padded to a multiple of 4*world floats (zeros, never read back)
+  n->params.ensure((size_t)(n->nparams + 1028) * 4);
+  n->grads.ensure((size_t)(n->nparams + 1028) * 4);
   if (n->nmov > 0) {
     n->mov.ensure((size_t)n->nmov * 4);
     std::vector<float> init((size_t)n->nmov, 0.f);
@@ -565,6 +566,31 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   layer_forward(g, s, 15, in, make_view(s.out_f32.p, B, H, W, C));
 }
 
+// Data parallel: hand the gradient range [from, hi) of a net to the communication stream, hi = the lowest offset
+// already handed over in this step (buckets are issued top-down, in backward-completion order).  Offsets are rounded UP
+// to the bucket quantum 4*world so that every bucket divides evenly over the ranks; the few floats below a rounded
+// boundary travel with the next (later-finishing) bucket, the padding beyond nparams is zeros.  With the sharded
+// optimizer the bucket is reduce-scattered and remembered (rank r then owns sub-range r); otherwise it is all-reduced.
+static void comm_reduce_bucket(gan_net* n, int64_t from) {
+  gan_ctx* ctx = n->ctx;
+  if (ctx->world <= 1) return;
+  const int64_t q = 4LL * ctx->world;
+  GAN_REQUIRE(q <= 1024, "world size above 256 is not supported");
+  const int64_t total = (n->nparams + q - 1) / q * q;
+  const int64_t hi = n->reduced_from < 0 ? total : n->reduced_from;
+  const int64_t lo = from <= 0 ? 0 : (from + q - 1) / q * q;
+  if (lo >= hi) return;
+  float* gr = n->grads.as<float>();
+  if (ctx->shard_optimizer) {
+    comm_reducescatter_async(ctx, gr + lo, hi - lo);
+    n->bucket_off.push_back(lo); n->bucket_len.push_back(hi - lo);
+  } else {
+    comm_allreduce_async(ctx, gr + lo, hi - lo);
+  }
+  n->reduced_from = lo;
+}
+static void comm_step_begin(gan_net* n) { n->bucket_off.clear(); n->bucket_len.clear(); n->reduced_from = -1; }
+
 // Backward through one generator call.  d1/d2: extra gradient sources w.r.t. the tanh output
 // (activation dtype); ref/l1_coef: + l1_coef*sign(out-ref).  Accumulates into g->grads.
 // `final_call`: this is the last contribution to g->grads in the step, so finished gradient ranges
@@ -621,8 +647,8 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
     else { int pp = UP_F[k - 2] + DOWN_F[8 - k]; din = make_view(s.dcat[k - 2].p, B, H >> (9 - k), W >> (9 - k), pp); }
     layer_backward(g, s, 7 + k, src, GradSrc{nullptr, 0, 0}, din, true);
     if (final_call && ctx->world > 1) {
-      if (k == 5) comm_allreduce_async(ctx, gr + g->layers[12].w_off, g->nparams - g->layers[12].w_off);
-      if (k == 1) comm_allreduce_async(ctx, gr + g->layers[8].w_off, g->layers[12].w_off - g->layers[8].w_off);
+      if (k == 5) comm_reduce_bucket(g, g->layers[12].w_off);       // up5 .. last
+      if (k == 1) comm_reduce_bucket(g, g->layers[8].w_off);        // up1 .. up4 (29 M of the 54 M parameters)
     }
   }
   for (int j = 8; j >= 1; --j) {
@@ -643,10 +669,9 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
     }
     layer_backward(g, s, j - 1, a, b, din, true);
     // down5..down8 hold 16.8 M of the down path's 19.5 M parameters: reduce them under down4..down1
-    if (final_call && ctx->world > 1 && j == 5)
-      comm_allreduce_async(ctx, gr + g->layers[4].w_off, g->layers[8].w_off - g->layers[4].w_off);
+    if (final_call && ctx->world > 1 && j == 5) comm_reduce_bucket(g, g->layers[4].w_off);
   }
-  if (final_call && ctx->world > 1) comm_allreduce_async(ctx, gr, g->layers[4].w_off);
+  if (final_call && ctx->world > 1) comm_reduce_bucket(g, 0);
 }
 
 // inp/tar: device fp32 (B,H,W,C); tar may be nullptr when target == false.
@@ -804,16 +829,34 @@ static void build_adam_tables(gan_net* n) {
   n->adam_nent = (int)tab.size(); n->adam_tiles = tiles; n->adam_nranges = (int)ranges.size();
 }
 
-// `reduced`: the gradient buffer has already been all-reduced (overlapped buckets + comm_join).
+// `reduced`: the gradient buckets of this net have already been handed to the communication stream (comm_reduce_bucket)
+// and joined (comm_join).
 static void adam_apply(gan_adam* o, bool reduced = false) {
   gan_net* n = o->net; gan_ctx* ctx = n->ctx;
   if (n->adam_nent == 0) build_adam_tables(n);
-  if (ctx->world > 1 && !reduced) comm_allreduce_sum(ctx, n->grads.as<float>(), n->nparams);
+  if (ctx->world > 1 && !reduced) { comm_step_begin(n); comm_reduce_bucket(n, 0); comm_join(ctx); }
   o->t += 1;
   launch_bump(ctx->L(), o->t_dev.as<long long>(), nullptr, 1);
+  const float gscale = 1.f / ((float)ctx->world * n->grad_scale);     // undo the data-parallel sum and the loss scale
+  if (ctx->world > 1 && ctx->shard_optimizer) {
+    // ZeRO-1 style: every bucket was reduce-scattered, so this rank holds the summed gradient of its
+    // sub-range only; it updates exactly that 1/world of the parameters (and of m, v), the updated master
+    // parameters are all-gathered in place, and the 16-bit weight packs are rebuilt from the gathered master.
+    ProfScope ps(ctx, FAM_ADAM, 28.0 * (double)n->nparams / ctx->world + 4.0 * (double)n->nparams * (ctx->world - 1) / ctx->world);
+    const int nb = (int)n->bucket_off.size();
+    for (int i = 0; i < nb; ++i) {
+      const int64_t cnt = n->bucket_len[i] / ctx->world, off = n->bucket_off[i] + (int64_t)ctx->rank * cnt;
+      launch_adam(ctx->L(), n->params.as<float>() + off, n->grads.as<float>() + off, o->m.as<float>() + off, o->v.as<float>() + off,
+                  cnt, o->t_dev.as<long long>(), o->lr, o->b1, o->b2, (float)o->eps, gscale);
+    }
+    comm_allgather_buckets(ctx, n->params.as<float>(), n->bucket_off.data(), n->bucket_len.data(), nb);
+    n->packed_dirty = true;
+    pack_weights(n);
+    return;
+  }
   AdamArgs a{n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), o->t_dev.as<long long>(),
-             o->lr, o->b1, o->b2, (float)o->eps, 1.f / ((float)ctx->world * n->grad_scale)};   // undo the DP sum and the loss scale
-  // fused update + repack: 28 B/param of optimizer traffic + 4 B/param for the two packed bf16 copies
+             o->lr, o->b1, o->b2, (float)o->eps, gscale};
+  // fused update + repack: 28 B/param of optimizer traffic + 4 B/param for the two packed 16-bit copies
   ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
   launch_adam_pack(ctx->L(), ctx->dtA, ctx->dtG, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
   launch_adam_ranges(ctx->L(), a, (const AdamRange*)n->adam_ranges.p, n->adam_nranges);
@@ -878,7 +921,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
-  if (training) { zero_grads(g); zero_grads(d); }
+  if (training) { zero_grads(g); zero_grads(d); comm_step_begin(g); comm_step_begin(d); }
   const double n_img_d = (double)B * H * W * C, n_log_d = (double)B * (H / 8 - 2) * (W / 8 - 2);
   const float S = pick_grad_scale(ctx, std::max((double)lambda / n_img_d, std::max((double)gan_scale, 0.5) / n_log_d));
   ctx->grad_scale = S; g->grad_scale = S; d->grad_scale = S;
@@ -896,7 +939,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   disc_bce(d, 1, 0.f, 0.5f * S, training, true, 3);
   if (training) {
     discriminator_backward(d, 1, true, false);
-    comm_allreduce_async(ctx, d->grads.as<float>(), d->nparams);          // D gradients final: reduce under G's backward
+    comm_reduce_bucket(d, 0);                                             // D gradients final: reduce under G's backward
   }
   disc_bce(d, 1, 1.f, gan_scale * S, training, false, 0);
   if (training) {
@@ -938,7 +981,10 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
-  if (training) { zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy); }
+  if (training) {
+    zero_grads(g); zero_grads(f); zero_grads(dx); zero_grads(dy);
+    comm_step_begin(g); comm_step_begin(f); comm_step_begin(dx); comm_step_begin(dy);
+  }
   const float S = pick_grad_scale(ctx, std::max((double)lambda / ((double)B * H * W * C), 1.0 / ((double)B * (H / 8 - 2) * (W / 8 - 2))));
   ctx->grad_scale = S; g->grad_scale = S; f->grad_scale = S; dx->grad_scale = S; dy->grad_scale = S;
 
@@ -962,9 +1008,9 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   launch_l1(ctx->L(), y, same_y, n_img, lw, 4);
   launch_l1(ctx->L(), x, same_x, n_img, lw, 5);
   disc_bce(dx, 0, 1.f, 0.5f * S, training, true, 6); if (training) discriminator_backward(dx, 0, true, false);
-  disc_bce(dx, 1, 0.f, 0.5f * S, training, true, 7); if (training) discriminator_backward(dx, 1, true, false);
+  disc_bce(dx, 1, 0.f, 0.5f * S, training, true, 7); if (training) { discriminator_backward(dx, 1, true, false); comm_reduce_bucket(dx, 0); }
   disc_bce(dy, 0, 1.f, 0.5f * S, training, true, 8); if (training) discriminator_backward(dy, 0, true, false);
-  disc_bce(dy, 1, 0.f, 0.5f * S, training, true, 9); if (training) discriminator_backward(dy, 1, true, false);
+  disc_bce(dy, 1, 0.f, 0.5f * S, training, true, 9); if (training) { discriminator_backward(dy, 1, true, false); comm_reduce_bucket(dy, 0); }
   disc_bce(dy, 1, 1.f, S, training, false, 0); if (training) discriminator_backward(dy, 1, false, true);
   disc_bce(dx, 1, 1.f, S, training, false, 1); if (training) discriminator_backward(dx, 1, false, true);
   if (training) {
@@ -974,9 +1020,11 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
     generator_backward(g, 1, none, none, y, lc, true);                                   // cycle y: through G into fake_x
     generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->Cin0_p, 0}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false);
     generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, dx->Cin0_p, 0}, GradSrc{g->slots[1].dxin.p, g->Cp, 0}, nullptr, 0.f, false);
-    generator_backward(f, 2, none, none, x, 0.5f * lc, false);                           // identity x (:244)
-    generator_backward(g, 2, none, none, y, 0.5f * lc, false);                           // identity y (:243)
-    adam_apply(og); adam_apply(of); adam_apply(odx); adam_apply(ody);                    // (:263-273)
+    // the last contribution to each generator's gradients: their buckets go to the communication stream as they close
+    generator_backward(f, 2, none, none, x, 0.5f * lc, false, true);                     // identity x (:244)
+    generator_backward(g, 2, none, none, y, 0.5f * lc, false, true);                     // identity y (:243)
+    comm_join(ctx);
+    adam_apply(og, true); adam_apply(of, true); adam_apply(odx, true); adam_apply(ody, true);     // (:263-273)
   }
   LossMix mix; memset(&mix, 0, sizeof(mix));
   mix.nraw = 10; mix.nout = 7;
@@ -1219,6 +1267,7 @@ int gan_comm_unique_id(void* out128) {
 int gan_ctx_comm_init(gan_ctx* ctx, int rank, int world, const void* unique_id128) {
   API_BEGIN
   CUDA_CHECK(cudaSetDevice(ctx->device));
+  { const char* e = getenv("GAN_B200_SHARD_OPT"); ctx->shard_optimizer = !(e && e[0] == '0'); }    // dev A/B switch
   comm_init(ctx, rank, world, unique_id128);
   API_END
 }
@@ -1429,7 +1478,7 @@ int gan_adam_create(gan_net* net, double lr, double beta1, double beta2, double 
   gan_adam* o = new gan_adam();
   std::unique_ptr<gan_adam> guard(o);
   o->net = net; o->lr = lr; o->b1 = beta1; o->b2 = beta2; o->eps = eps;
-  o->m.ensure((size_t)(net->nparams + 4) * 4); o->v.ensure((size_t)(net->nparams + 4) * 4);
+  o->m.ensure((size_t)(net->nparams + 1028) * 4); o->v.ensure((size_t)(net->nparams + 1028) * 4);
   o->t_dev.ensure(16);
   guard.release(); net->ctx->adams.push_back(o); live_add(o);
   *out = o;

@@ -93,6 +93,7 @@ struct gan_ctx {
   std::vector<cudaEvent_t> comm_events;   // fork/join events (reused round-robin)
   size_t comm_ev_next = 0;
   bool comm_pending = false;
+  int shard_optimizer = 1;                // world > 1: reduce-scatter + 1/world Adam + all-gather (0: all-reduce + full Adam)
   Launch L() { return Launch{stream, &launches}; }
   size_t esize() const { return dt == DT_F32 ? 4 : 2; }
 };
@@ -153,6 +154,10 @@ struct gan_net {
   int64_t nparams = 0, nmov = 0;
   DevBuf params, grads, mov;
   float grad_scale = 1.f;     // loss scale the contents of `grads` carry (removed by Adam / by the gradient getters)
+  // data parallel, sharded optimizer: the gradient buckets reduce-scattered so far in this step (flat offset, length;
+  // lengths are multiples of the world size) — rank r owns sub-range r of every bucket
+  std::vector<int64_t> bucket_off, bucket_len;
+  int64_t reduced_from = -1;  // lowest flat offset already handed to the communication stream (buckets go top-down)
   std::vector<Slot> slots;
   bool packed_dirty = true;
   DevBuf pack_tab;            // device array of PackEntry (all layers x roles), built once
@@ -180,3 +185,5 @@ void comm_allreduce_sum(gan_ctx* ctx, float* buf, int64_t n);
 // compute stream has finished; comm_join makes the compute stream wait for all forked reductions.
 void comm_allreduce_async(gan_ctx* ctx, float* buf, int64_t n);
 void comm_join(gan_ctx* ctx);
+void comm_reducescatter_async(gan_ctx* ctx, float* buf, int64_t n);
+void comm_allgather_buckets(gan_ctx* ctx, float* base, const int64_t* off, const int64_t* len, int nb);
