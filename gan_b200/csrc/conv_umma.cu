@@ -1029,10 +1029,15 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p)
   else { r = threadIdx.x >> 1; c = sub * 8 + (threadIdx.x & 1) * 4; }
   const int total = 128 * bn;
   const float* base = p.slab + (tile_idx * p.splits) * total + (long long)r * bn + c;
-  float4 a = *reinterpret_cast<const float4*>(base);
-  for (int sp = 1; sp < p.splits; ++sp) {                  // fixed order: deterministic
-    const float4 v = *reinterpret_cast<const float4*>(base + (long long)sp * total);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  // the partial tiles are summed in split order (deterministic), eight independent loads in flight per thread
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sp = 0; sp < p.splits; sp += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = sp + u < p.splits ? __ldcs(reinterpret_cast<const float4*>(base + (long long)(sp + u) * total)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
   }
   const int k = mblock * 128 + r;
   const int t = k / p.Kc, kc = k - t * p.Kc;

@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
   }
   block_partial_store(acc, loss_slot + blockIdx.x);
   if (dz != nullptr && dbias != nullptr) {
-    // launched with ONE block in this case (launch_bce): a single, ordered read-modify-write of the bias gradient
+    // per-block partial of the bias gradient; k_sum_partials adds them in block order (deterministic)
     __syncthreads();
     __shared__ float shb[8];
     float v = warp_sum(bacc);
@@ -848,20 +848,23 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < 8; ++w) t += shb[w];
-      *dbias += t;
+      dbias[(size_t)blockIdx.x * 4] = t;
     }
   }
 }
+__global__ void k_sum_partials(const float* __restrict__ part, int nblocks, int C, float* dst);
 void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
-                float* dbias, float* loss_ws, int slot) {
+                float* dbias, float* loss_ws, int slot, float* part_ws) {
   int blocks = grid_for(n, 256, 1);
   if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
-  if (dz != nullptr && dbias != nullptr) blocks = 1;     // deterministic bias gradient (n = B*900 .. B*3844 logits: microseconds)
+  const bool bias = dz != nullptr && dbias != nullptr;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dz_pitch, dbias, loss_ws + slot * LOSS_BLOCKS);
+    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dz_pitch, bias ? part_ws : nullptr,
+                                      loss_ws + slot * LOSS_BLOCKS);
   });
   KLAUNCH(L);
+  if (bias) { k_sum_partials<<<1, 128, 0, L.s>>>(part_ws, blocks, 1, dbias); KLAUNCH(L); }
 }
 
 __global__ void __launch_bounds__(256) k_l1(const float* __restrict__ a, const float* __restrict__ b, int64_t n,

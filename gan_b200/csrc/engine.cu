@@ -183,9 +183,9 @@ struct ProfScope {
   ProfScope(gan_ctx* c, int fam, double work) : ctx(c), on(c->profile != 0) {
     if (!on) return;
     e.fam = fam; e.work = work; e.a = c->ev_get(); e.b = c->ev_get();
-    cudaEventRecord(e.a, c->stream);
+    cudaEventRecord(e.a, c->cs());
   }
-  ~ProfScope() { if (on) { cudaEventRecord(e.b, ctx->stream); ctx->prof.push_back(e); } }
+  ~ProfScope() { if (on) { cudaEventRecord(e.b, ctx->cs()); ctx->prof.push_back(e); } }
 };
 // Algorithmic FLOPs of one launch: 2*M*N*K of the UNPADDED layer — real channel counts
 // Kr/Nr, and for the slot-4 operands of the image-channel ends the real 16*C columns, not the stored 64.
@@ -205,8 +205,8 @@ static double conv_flops(const ConvOp& op) {
 // returns the number of BatchNorm-statistics partials the conv epilogue produced (0: none, run the statistics pass)
 static int run_conv_fwd(gan_ctx* ctx, const ConvOp& op_in) {
   ConvOp op = op_in;
-  ctx->splitk_ws.ensure((size_t)32 << 20);
-  op.splitk_ws = ctx->splitk_ws.as<float>(); op.splitk_ws_bytes = ctx->splitk_ws.bytes;
+  ctx->sc().splitk_ws.ensure((size_t)32 << 20);
+  op.splitk_ws = ctx->sc().splitk_ws.as<float>(); op.splitk_ws_bytes = ctx->sc().splitk_ws.bytes;
   bool can = ctx->dt == DT_BF16 && umma_fwd_supported(op);
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
@@ -222,15 +222,15 @@ static void run_conv_wgrad(gan_ctx* ctx, Layer& ly, const ConvOp& op_in) {
   op.accumulate = ly.wgrad_epoch == ctx->step_epoch ? 1 : 0;
   ly.wgrad_epoch = ctx->step_epoch;
   op.dW_elems = 16LL * ly.Cin * ly.Cout;
-  ctx->wgrad_ws.ensure((size_t)24 << 20);              // <= 296 partial tiles of 128 x 128 fp32 per launch
-  op.wgrad_ws = ctx->wgrad_ws.as<float>(); op.wgrad_ws_bytes = ctx->wgrad_ws.bytes;
+  ctx->sc().wgrad_ws.ensure((size_t)24 << 20);              // <= 296 partial tiles of 128 x 128 fp32 per launch
+  op.wgrad_ws = ctx->sc().wgrad_ws.as<float>(); op.wgrad_ws_bytes = ctx->sc().wgrad_ws.bytes;
   bool can = ctx->dt == DT_BF16 && umma_wgrad_supported(op);
   if (ctx->engine == GAN_ENGINE_UMMA) GAN_REQUIRE(can, "tcgen05 engine forced but op unsupported");
   const bool um = can && ctx->engine != GAN_ENGINE_FFMA;
   ProfScope ps(ctx, um ? FAM_UMMA_WGRAD : FAM_FFMA_WGRAD, conv_flops(op));
   if (um) { launch_conv_wgrad_umma(ctx->L(), op); return; }
   // CUDA-core path (fp32 parity mode, odd shapes): split-M partial sums meet in fp32 atomics, so the tensor is zeroed first
-  if (!op.accumulate) CUDA_CHECK(cudaMemsetAsync(op.dW, 0, (size_t)op.dW_elems * 4, ctx->stream));
+  if (!op.accumulate) CUDA_CHECK(cudaMemsetAsync(op.dW, 0, (size_t)op.dW_elems * 4, ctx->cs()));
   launch_conv_wgrad_ffma(ctx->L(), op.dt_in, op.dt_out, op);
 }
 
@@ -433,11 +433,11 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   const size_t gc = (size_t)G * ly.Cout;
   if (ly.norm != NORM_NONE) {
     size_t need = stats_ws_floats(G, Pg, ly.Cout), epi = (size_t)STATS_MAX_CHUNKS * 2 * ly.Cout;
-    ctx->stats_ws.ensure((need > epi ? need : epi) * 4);
+    ctx->sc().stats_ws.ensure((need > epi ? need : epi) * 4);
   }
   ConvOp cop = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_FWD, s, z) : make_op(ctx, ly, R_FWD, in, z, ly.wp_fwd.p);
   // BatchNorm statistics straight from the fp32 accumulators when the layer runs on the CTA-pair kernel
-  if (ly.norm == NORM_BATCH) cop.stats_ws = ctx->stats_ws.as<float>();
+  if (ly.norm == NORM_BATCH) cop.stats_ws = ctx->sc().stats_ws.as<float>();
   const int stat_parts = run_conv_fwd(ctx, cop);
   DropKey dk = drop_key(ctx, ly, s);
   // SURVEY 8d byte model: forward = read z + write activation = 2*s per element (statistics belong to the conv epilogue)
@@ -453,14 +453,14 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   float* mm = (ly.mov_off >= 0) ? n->mov.as<float>() + ly.mov_off : nullptr;
   const float eps = ly.norm == NORM_BATCH ? BN_EPS : IN_EPS;
   if (stat_parts > 0) {
-    launch_norm_stats_finalize(ctx->L(), ctx->stats_ws.as<float>(), stat_parts, P, ly.Cout, eps, pr + ly.g_off, pr + ly.b_off,
+    launch_norm_stats_finalize(ctx->L(), ctx->sc().stats_ws.as<float>(), stat_parts, P, ly.Cout, eps, pr + ly.g_off, pr + ly.b_off,
                                st, st + gc, st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
   } else {
     if (launch_bn_small_fwd(ctx->L(), ctx->dtA, z.p, P, G, Ho * Wo, ly.Cout, eps, pr + ly.g_off, pr + ly.b_off, st, st + gc,
                             st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM, ly.act, dk, out.p,
                             out.pitch, out.coff))
       return;
-    launch_norm_stats(ctx->L(), ctx->dtA, z.p, G, Pg, ly.Cout, ctx->stats_ws.as<float>(), eps, pr + ly.g_off, pr + ly.b_off, st,
+    launch_norm_stats(ctx->L(), ctx->dtA, z.p, G, Pg, ly.Cout, ctx->sc().stats_ws.as<float>(), eps, pr + ly.g_off, pr + ly.b_off, st,
                       st + gc, st + 2 * gc, st + 3 * gc, mm, mm ? mm + ly.Cout : nullptr, BN_MOMENTUM);
   }
   launch_norm_apply(ctx->L(), ctx->dtA, z.p, P, Pg, G, Ho * Wo, ly.Cout, st, st + 2 * gc, st + 3 * gc, ly.act, dk, out.p,
@@ -480,21 +480,21 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
   if (ly.head) {
     dz = make_view((void*)d1.p, B, Ho, Wo, ly.Cout_p, d1.pitch, d1.coff);
   } else {
-    ctx->dz_scratch.ensure((size_t)P * ly.Cout * ctx->esize());
-    dz = make_view(ctx->dz_scratch.p, B, Ho, Wo, ly.Cout);
+    ctx->sc().dz_scratch.ensure((size_t)P * ly.Cout * ctx->esize());
+    dz = make_view(ctx->sc().dz_scratch.p, B, Ho, Wo, ly.Cout);
     const int G = ly.norm == NORM_BATCH ? 1 : (ly.norm == NORM_INSTANCE ? B : 1);
     const int64_t Pg = P / G;
     const size_t gc = (size_t)G * ly.Cout;
     float* st = ly.norm != NORM_NONE ? s.stats[li].as<float>() : nullptr;
     float* gr = want_wgrad ? n->grads.as<float>() : nullptr;
-    ctx->junk.ensure(2048 * 4);
-    float* dgamma = (gr && ly.norm != NORM_NONE) ? gr + ly.g_off : ctx->junk.as<float>();
-    float* dbeta = (gr && ly.norm != NORM_NONE) ? gr + ly.b_off : ctx->junk.as<float>() + 1024;
-    if (ly.norm != NORM_NONE) ctx->stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
+    ctx->sc().junk.ensure(2048 * 4);
+    float* dgamma = (gr && ly.norm != NORM_NONE) ? gr + ly.g_off : ctx->sc().junk.as<float>();
+    float* dbeta = (gr && ly.norm != NORM_NONE) ? gr + ly.b_off : ctx->sc().junk.as<float>() + 1024;
+    if (ly.norm != NORM_NONE) ctx->sc().stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
     ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 3 : 5));
     launch_norm_bwd(ctx->L(), ctx->dtA, ctx->dtG, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
                     st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
-                    ctx->stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
+                    ctx->sc().stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
   }
   if (want_wgrad) {
     ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_WGRAD, s, dz) : make_op(ctx, ly, R_WGRAD, in, dz, nullptr);
@@ -521,13 +521,16 @@ static void slot_prepare(gan_net* n, Slot& s, int B, int H, int W) {
 }
 
 // x_f32: device fp32 (B,H,W,C).  Output: s.out_f32 (B,H,W,C) fp32.
-static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, int H, int W) {
+// call_off >= 0: position of this call in the step's generator-call sequence (keys the dropout masks) when the host
+// issues the calls in another order than the reference (two-stream CycleGAN step); -1: next in issue order.
+static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, int H, int W, int call_off = -1) {
   gan_ctx* ctx = g->ctx;
   GAN_REQUIRE(H % 256 == 0 && W % 256 == 0 && H >= 256 && W >= 256, "generator needs H,W multiples of 256");
   pack_weights(g);
   Slot& s = g->slots[slot];
   slot_prepare(g, s, B, H, W);
-  s.call_off = ctx->gen_calls_pending++;
+  if (call_off < 0) s.call_off = ctx->gen_calls_pending++;
+  else { s.call_off = (uint32_t)call_off; if (ctx->gen_calls_pending < (uint32_t)call_off + 1) ctx->gen_calls_pending = (uint32_t)call_off + 1; }
   s.call_id = ctx->call_counter + s.call_off;
   s.sample0 = ctx->sample0_set ? ctx->sample0 : (int64_t)ctx->rank * B;
   const size_t es = ctx->esize();
@@ -605,15 +608,15 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   float* gr = g->grads.as<float>();
   // head
   const int Cp = g->Cp;
-  ctx->head_part.ensure((size_t)HEAD_PART_BLOCKS * 4 * 4);
+  ctx->sc().head_part.ensure((size_t)HEAD_PART_BLOCKS * 4 * 4);
   if (s.used_cols) {
     s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
     launch_ghead_bwd_cols(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, B, H, W, C, s.gcols.p,
-                          gr + g->layers[15].bias_off, ctx->head_part.as<float>());
+                          gr + g->layers[15].bias_off, ctx->sc().head_part.as<float>());
   } else {
     s.dlogit.ensure((size_t)B * H * W * Cp * es);
     launch_ghead_bwd(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
-                     gr + g->layers[15].bias_off, ctx->head_part.as<float>());
+                     gr + g->layers[15].bias_off, ctx->sc().head_part.as<float>());
   }
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
@@ -748,9 +751,10 @@ static void disc_bce(gan_net* d, int slot, float label, float coef, bool make_dz
   int64_t n = logits_count(s);
   const int dzp = d->layers[4].Cout_p;
   if (make_dz) s.dlogit.ensure((size_t)n * dzp * ctx->esize());
+  ctx->sc().head_part.ensure((size_t)HEAD_PART_BLOCKS * 4 * 4);
   launch_bce(ctx->L(), ctx->dtG, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr, dzp,
              (make_dz && bias_grad) ? d->grads.as<float>() + d->layers[4].bias_off : nullptr, ctx->loss_ws.as<float>(),
-             loss_slot);
+             loss_slot, ctx->sc().head_part.as<float>());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -893,6 +897,41 @@ static void loss_ws_reset(gan_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------
 // Pix2Pix.train_step (pix2pix.py:190-218)
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Two-stream execution of a step.  The discriminator's pass over the REAL pair (forward, BCE, backward with its weight
+// gradients) depends on nothing the generator computes, and the generator's forward spends a third of its launches in
+// the 1x1..8x8 bottleneck, where a launch occupies 64..256 of the 296 CTA slots.  The side stream runs that
+// discriminator pass meanwhile; the block scheduler fills the idle SMs.  Fork and join are events, so a captured step
+// graph gets two parallel branches.  The first-layer rows of the real images are built before the fork (shared), every
+// other buffer is private to a (net, call) slot or to the stream's Scratch set.
+// ---------------------------------------------------------------------------------------------
+static bool side_begin(gan_ctx* ctx) {
+  if (!ctx->overlap || ctx->profile) return false;
+  if (ctx->side == nullptr) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  ctx->cur = 1;
+  return true;
+}
+static void side_end(gan_ctx* ctx) { ctx->cur = 0; }                       // back to the main stream; the side keeps running
+static void side_join(gan_ctx* ctx) {
+  CUDA_CHECK(cudaEventRecord(ctx->ev_join, ctx->side));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+}
+// intermediate dependency: everything enqueued on the side stream so far (recorded while cur == 1) ...
+static void side_mark_mid(gan_ctx* ctx) { CUDA_CHECK(cudaEventRecord(ctx->ev_mid, ctx->side)); }
+// ... must have finished before what the main stream enqueues next
+static void main_wait_mid(gan_ctx* ctx) { CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_mid, 0)); }
+// first-layer rows of an input that several nets / streams read: built on the main stream before a fork
+static void share_im2col(gan_ctx* ctx, gan_net* n, const float* img, int B, int H, int W) {
+  if (im2col_on(ctx, n->layers[0])) cached_im2col(ctx, img, B, H, W, n->C);
+}
+
 // Static loss scale for fp16 gradient storage: the largest gradient any loss head emits (`g_head`: weight / number of
 // elements of its mean) is brought to ~4 by a power of two.  Measured on this model (scripts/): |dL/dz| over
 // all layers spans 2e-9 .. 16x the head value, i.e. 3e-5 .. 64 after scaling — inside fp16's 6e-8 .. 65504 with three
@@ -919,6 +958,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   const float* x = stage_in(ctx, 0, x_in, img_bytes);
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
   ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
+  ctx->cur = 0;
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) { zero_grads(g); zero_grads(d); comm_step_begin(g); comm_step_begin(d); }
@@ -926,16 +966,20 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   const float S = pick_grad_scale(ctx, std::max((double)lambda / n_img_d, std::max((double)gan_scale, 0.5) / n_log_d));
   ctx->grad_scale = S; g->grad_scale = S; d->grad_scale = S;
 
+  pack_weights(g); pack_weights(d);
+  share_im2col(ctx, g, x, B, H, W); share_im2col(ctx, d, y, B, H, W);
+  const int64_t n_img = (int64_t)B * H * W * C;
+  // raw loss slots: 0 BCE(1,fake)  1 L1  2 BCE(1,real)  3 BCE(0,fake)
+  const bool forked = side_begin(ctx);
+  discriminator_forward(d, 0, x, y, B, H, W);                            // disc_real_output     (:202)
+  disc_bce(d, 0, 1.f, 0.5f * S, training, true, 2);
+  if (training) discriminator_backward(d, 0, true, false);               // first contribution to D's gradients
+  side_end(ctx);
   generator_forward(g, 0, x, B, H, W);                                   // gen_output           (:200)
   const float* gen_out = g->slots[0].out_f32.as<float>();
-  discriminator_forward(d, 0, x, y, B, H, W);                            // disc_real_output     (:202)
+  if (forked) side_join(ctx);
   discriminator_forward(d, 1, x, gen_out, B, H, W);                      // disc_generated_output(:203)
-
-  const int64_t n_img = (int64_t)B * H * W * C;
   launch_l1(ctx->L(), y, gen_out, n_img, ctx->loss_ws.as<float>(), 1);   // gan_loss2 = mean|target-gen_output| (:181)
-  // raw slots: 0 BCE(1,fake)  1 L1  2 BCE(1,real)  3 BCE(0,fake)
-  disc_bce(d, 0, 1.f, 0.5f * S, training, true, 2);
-  if (training) discriminator_backward(d, 0, true, false);
   disc_bce(d, 1, 0.f, 0.5f * S, training, true, 3);
   if (training) {
     discriminator_backward(d, 1, true, false);
@@ -979,6 +1023,7 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   const float* x = stage_in(ctx, 0, x_in, img_bytes);
   const float* y = stage_in(ctx, 1, y_in, img_bytes);
   ctx->prefetch_src[0] = ctx->prefetch_src[1] = nullptr;   // a prefetch this step did not consume must not match later
+  ctx->cur = 0;
   loss_ws_reset(ctx);
   ctx->step_epoch++; ctx->im2col_next = 0;
   if (training) {
@@ -988,41 +1033,53 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
   const float S = pick_grad_scale(ctx, std::max((double)lambda / ((double)B * H * W * C), 1.0 / ((double)B * (H / 8 - 2) * (W / 8 - 2))));
   ctx->grad_scale = S; g->grad_scale = S; f->grad_scale = S; dx->grad_scale = S; dy->grad_scale = S;
 
-  generator_forward(g, 0, x, B, H, W);  const float* fake_y = g->slots[0].out_f32.as<float>();     // (:220)
-  generator_forward(f, 0, fake_y, B, H, W); const float* cycled_x = f->slots[0].out_f32.as<float>(); // (:221)
-  generator_forward(f, 1, y, B, H, W);  const float* fake_x = f->slots[1].out_f32.as<float>();     // (:223)
-  generator_forward(g, 1, fake_x, B, H, W); const float* cycled_y = g->slots[1].out_f32.as<float>(); // (:224)
-  generator_forward(f, 2, x, B, H, W);  const float* same_x = f->slots[2].out_f32.as<float>();     // (:227)
-  generator_forward(g, 2, y, B, H, W);  const float* same_y = g->slots[2].out_f32.as<float>();     // (:228)
-  discriminator_forward(dx, 0, x, nullptr, B, H, W);        // disc_real_x (:230)
-  discriminator_forward(dy, 0, y, nullptr, B, H, W);        // disc_real_y (:231)
-  discriminator_forward(dx, 1, fake_x, nullptr, B, H, W);   // disc_fake_x (:233)
-  discriminator_forward(dy, 1, fake_y, nullptr, B, H, W);   // disc_fake_y (:234)
-
+  pack_weights(g); pack_weights(f); pack_weights(dx); pack_weights(dy);
+  share_im2col(ctx, g, x, B, H, W); share_im2col(ctx, f, y, B, H, W);
   const int64_t n_img = (int64_t)B * H * W * C;
   float* lw = ctx->loss_ws.as<float>();
+  const GradSrc none{nullptr, 0, 0};
+  const float lc = S * lambda / (float)n_img;
   // raw: 0 BCE(1,fake_y) 1 BCE(1,fake_x) 2 L1(x,cyc_x) 3 L1(y,cyc_y) 4 L1(y,same_y) 5 L1(x,same_x)
   //      6 BCE(1,real_x) 7 BCE(0,fake_x) 8 BCE(1,real_y) 9 BCE(0,fake_y)
-  launch_l1(ctx->L(), x, cycled_x, n_img, lw, 2);
-  launch_l1(ctx->L(), y, cycled_y, n_img, lw, 3);
+  // Side stream: everything that depends on the REAL images only — both discriminators' real passes and the whole
+  // identity branch (same_x = F(x), same_y = G(y), their L1 losses and backward sweeps), which therefore become the
+  // FIRST contributions to the four gradient buffers.  The generator calls keep the reference's position in the
+  // dropout-mask sequence (cycle_gan.py:220-228: fake_y 0, cycled_x 1, fake_x 2, cycled_y 3, same_x 4, same_y 5).
+  const bool forked = side_begin(ctx);
+  discriminator_forward(dx, 0, x, nullptr, B, H, W);        // disc_real_x (:230)
+  disc_bce(dx, 0, 1.f, 0.5f * S, training, true, 6); if (training) discriminator_backward(dx, 0, true, false);
+  discriminator_forward(dy, 0, y, nullptr, B, H, W);        // disc_real_y (:231)
+  disc_bce(dy, 0, 1.f, 0.5f * S, training, true, 8); if (training) discriminator_backward(dy, 0, true, false);
+  if (forked) side_mark_mid(ctx);
+  generator_forward(f, 2, x, B, H, W, 4);  const float* same_x = f->slots[2].out_f32.as<float>();     // (:227)
+  generator_forward(g, 2, y, B, H, W, 5);  const float* same_y = g->slots[2].out_f32.as<float>();     // (:228)
   launch_l1(ctx->L(), y, same_y, n_img, lw, 4);
   launch_l1(ctx->L(), x, same_x, n_img, lw, 5);
-  disc_bce(dx, 0, 1.f, 0.5f * S, training, true, 6); if (training) discriminator_backward(dx, 0, true, false);
+  if (training) {
+    generator_backward(f, 2, none, none, x, 0.5f * lc, false);                           // identity x (:244)
+    generator_backward(g, 2, none, none, y, 0.5f * lc, false);                           // identity y (:243)
+  }
+  side_end(ctx);
+  generator_forward(g, 0, x, B, H, W, 0);  const float* fake_y = g->slots[0].out_f32.as<float>();     // (:220)
+  generator_forward(f, 0, fake_y, B, H, W, 1); const float* cycled_x = f->slots[0].out_f32.as<float>(); // (:221)
+  generator_forward(f, 1, y, B, H, W, 2);  const float* fake_x = f->slots[1].out_f32.as<float>();     // (:223)
+  generator_forward(g, 1, fake_x, B, H, W, 3); const float* cycled_y = g->slots[1].out_f32.as<float>(); // (:224)
+  launch_l1(ctx->L(), x, cycled_x, n_img, lw, 2);
+  launch_l1(ctx->L(), y, cycled_y, n_img, lw, 3);
+  if (forked) main_wait_mid(ctx);                           // the real passes precede the fake ones (gradient order, BN statistics)
+  discriminator_forward(dx, 1, fake_x, nullptr, B, H, W);   // disc_fake_x (:233)
+  discriminator_forward(dy, 1, fake_y, nullptr, B, H, W);   // disc_fake_y (:234)
   disc_bce(dx, 1, 0.f, 0.5f * S, training, true, 7); if (training) { discriminator_backward(dx, 1, true, false); comm_reduce_bucket(dx, 0); }
-  disc_bce(dy, 0, 1.f, 0.5f * S, training, true, 8); if (training) discriminator_backward(dy, 0, true, false);
   disc_bce(dy, 1, 0.f, 0.5f * S, training, true, 9); if (training) { discriminator_backward(dy, 1, true, false); comm_reduce_bucket(dy, 0); }
   disc_bce(dy, 1, 1.f, S, training, false, 0); if (training) discriminator_backward(dy, 1, false, true);
   disc_bce(dx, 1, 1.f, S, training, false, 1); if (training) discriminator_backward(dx, 1, false, true);
+  if (forked) side_join(ctx);
   if (training) {
-    const GradSrc none{nullptr, 0, 0};
-    const float lc = S * lambda / (float)n_img;
     generator_backward(f, 0, none, none, x, lc, true);                                   // cycle x: through F into fake_y
     generator_backward(g, 1, none, none, y, lc, true);                                   // cycle y: through G into fake_x
-    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->Cin0_p, 0}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false);
-    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, dx->Cin0_p, 0}, GradSrc{g->slots[1].dxin.p, g->Cp, 0}, nullptr, 0.f, false);
     // the last contribution to each generator's gradients: their buckets go to the communication stream as they close
-    generator_backward(f, 2, none, none, x, 0.5f * lc, false, true);                     // identity x (:244)
-    generator_backward(g, 2, none, none, y, 0.5f * lc, false, true);                     // identity y (:243)
+    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->Cin0_p, 0}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false, true);
+    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, dx->Cin0_p, 0}, GradSrc{g->slots[1].dxin.p, g->Cp, 0}, nullptr, 0.f, false, true);
     comm_join(ctx);
     adam_apply(og, true); adam_apply(of, true); adam_apply(odx, true); adam_apply(ody, true);     // (:263-273)
   }
@@ -1152,6 +1209,7 @@ int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
                                                               std::to_string(prop.minor) + ", this library is sm_100a only");
   gan_ctx* c = new gan_ctx();
   c->device = device; c->dt = precision == GAN_FP32 ? DT_F32 : DT_BF16; c->seed = seed;
+  { const char* e = getenv("GAN_B200_OVERLAP"); c->overlap = !(e && e[0] == '0'); }      // dev A/B switch: two-stream steps
   if (c->dt == DT_F32) { c->dtA = DT_F32; c->dtG = DT_F32; }
   else {
     // 16-bit mode: fp16 storage with a static loss scale (common.cuh).  GAN_B200_ACT=bf16 selects all-bf16 storage
@@ -1187,6 +1245,7 @@ int gan_ctx_destroy(gan_ctx* ctx) {
   comm_destroy(ctx);
   cudaFreeHost(ctx->loss_host);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->prefetch_done); cudaEventDestroy(ctx->prefetch_consumed); }
+  if (ctx->side) { cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_mid); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   API_END

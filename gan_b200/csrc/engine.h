@@ -53,7 +53,17 @@ struct gan_ctx {
   int64_t sample0 = 0;
   bool sample0_set = false;
   uint64_t launches = 0;
-  DevBuf stats_ws, dz_scratch, loss_ws, loss_out, junk, splitk_ws, wgrad_ws, head_part;
+  // Workspaces that layer code writes, one set per stream: the side stream runs a whole discriminator pass while the
+  // main stream runs the generator (engine.cu side_begin / side_join), so they must not share scratch memory.
+  struct Scratch { DevBuf stats_ws, dz_scratch, junk, splitk_ws, wgrad_ws, head_part; };
+  Scratch scr[2];
+  int cur = 0;                                // 0: main stream, 1: side stream (selects L(), cs(), sc())
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
+  int overlap = 1;                            // run independent sub-graphs of a step on the side stream
+  Scratch& sc() { return scr[cur]; }
+  cudaStream_t cs() const { return cur ? side : stream; }
+  DevBuf loss_ws, loss_out;
   DevBuf stage[4];
   // im2col rows of step inputs shared between nets (x feeds G.down1, D(real).down1 and D(fake).down1)
   struct Im2colEntry { const void* src = nullptr; int B = 0, H = 0, W = 0, C = 0; uint64_t epoch = 0; DevBuf buf; };
@@ -94,7 +104,7 @@ struct gan_ctx {
   size_t comm_ev_next = 0;
   bool comm_pending = false;
   int shard_optimizer = 1;                // world > 1: reduce-scatter + 1/world Adam + all-gather (0: all-reduce + full Adam)
-  Launch L() { return Launch{stream, &launches}; }
+  Launch L() { return Launch{cs(), &launches}; }
   size_t esize() const { return dt == DT_F32 ? 4 : 2; }
 };
 

@@ -65,7 +65,7 @@ void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f
                       float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part_ws);
 // BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
 void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
-                float* dbias, float* loss_ws, int slot);
+                float* dbias, float* loss_ws, int slot, float* part_ws);
 void launch_l1(Launch L, const float* a, const float* b, int64_t n, float* loss_ws, int slot);
 // raw[j] = sum(slot j)/denom[j]; out[i] = sum_j mix[i*nraw+j]*raw[j]
 struct LossMix { int nraw, nout; float denom[LOSS_SLOTS]; float mix[8 * LOSS_SLOTS]; };
