@@ -1062,6 +1062,7 @@ __device__ __forceinline__ float adam_update(const AdamArgs& a, long long i, flo
 
 // 64x64 tiles of the master [16][A][B] kernel tensors, 256 threads: thread = (column b, 4 row groups);
 // the 4 x 8 rows of a half-tile are loaded first (32 independent loads per thread), then updated.
+template <> __device__ __forceinline__ uint32_t pack2<float>(float, float) { return 0u; }   // fp32 mode never packs pairs
 #define APT 64
 template <typename TF, typename TD>
 __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEntry* __restrict__ tab, int nent) {
@@ -1086,6 +1087,58 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
   TF* __restrict__ dF = (TF*)E.dstF + E.boffF[cF] + (long long)tF * E.KcF;     // + co*KtotF + ci
   TD* __restrict__ dD = (TD*)E.dstD + E.boffD[cD] + (long long)tD * E.KcD;     // + ci*KtotD + co
   const long long base = E.w_off + (long long)widx * E.A * E.B;
+  if (E.vec) {
+    // full 64x64 tile, 16-byte aligned rows: thread = (4 consecutive b, 4 rows 16 apart); 16 independent 128-bit loads
+    // per thread are in flight before the first dependent instruction
+    const int c4 = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    const int b4 = b0 + 4 * c4;
+    float4 P[4], G[4], M[4], V[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long idx = base + (long long)(a0 + rg + 16 * i) * E.B + b4;
+      P[i] = *reinterpret_cast<const float4*>(a.p + idx); G[i] = *reinterpret_cast<const float4*>(a.g + idx);
+      M[i] = *reinterpret_cast<const float4*>(a.m + idx); V[i] = *reinterpret_cast<const float4*>(a.v + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg + 16 * i, ai = a0 + r;
+      const long long idx = base + (long long)ai * E.B + b4;
+      float* pp = &P[i].x; const float* gg = &G[i].x; float* mm = &M[i].x; float* vv = &V[i].x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gr = gg[e] * a.gscale;
+        mm[e] += (gr - mm[e]) * (1.f - b1);
+        vv[e] += (gr * gr - vv[e]) * (1.f - b2);
+        pp[e] -= lr_t * mm[e] / (sqrtf(vv[e]) + a.eps);
+        tile[r][4 * c4 + e] = pp[e];
+      }
+      *reinterpret_cast<float4*>(a.p + idx) = P[i]; *reinterpret_cast<float4*>(a.m + idx) = M[i];
+      *reinterpret_cast<float4*>(a.v + idx) = V[i];
+      // destination that is contiguous along the master's fast index b: 4 values = one 8-byte store
+      if (E.conv2d) {
+        uint2 o; o.x = pack2<TD>(pp[0], pp[1]); o.y = pack2<TD>(pp[2], pp[3]);
+        *reinterpret_cast<uint2*>(dD + (long long)ai * E.KtotD + b4) = o;             // ci = a, co = b
+      } else {
+        uint2 o; o.x = pack2<TF>(pp[0], pp[1]); o.y = pack2<TF>(pp[2], pp[3]);
+        *reinterpret_cast<uint2*>(dF + (long long)ai * E.KtotF + b4) = o;             // co = a, ci = b
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int bj = b0 + rg + 16 * i, a4 = a0 + 4 * c4;     // row of the transposed tile = b index, 4 consecutive a
+      const float v0 = tile[4 * c4][rg + 16 * i], v1 = tile[4 * c4 + 1][rg + 16 * i], v2 = tile[4 * c4 + 2][rg + 16 * i],
+                  v3 = tile[4 * c4 + 3][rg + 16 * i];
+      if (E.conv2d) {
+        uint2 o; o.x = pack2<TF>(v0, v1); o.y = pack2<TF>(v2, v3);
+        *reinterpret_cast<uint2*>(dF + (long long)bj * E.KtotF + a4) = o;             // co = b, ci = a
+      } else {
+        uint2 o; o.x = pack2<TD>(v0, v1); o.y = pack2<TD>(v2, v3);
+        *reinterpret_cast<uint2*>(dD + (long long)bj * E.KtotD + a4) = o;             // ci = b, co = a
+      }
+    }
+    return;
+  }
   const int bi = b0 + tx;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -1327,7 +1380,14 @@ void launch_im2col(Launch L, int dt_rows, const float* src, int B, int H, int W,
 
 // col2im of the transposed-conv head: one thread per output pixel gathers its 4 contributing taps
 // (one aligned float4 each) from cols[m][tap*4 + co]; taps per output parity as geom_convT4.
-__global__ void __launch_bounds__(256) k_col2im_tanh(const float* __restrict__ cols, const float* __restrict__ bias, int B,
+__device__ __forceinline__ float4 ld_cols4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld_cols4(const f16* p) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename TC>
+__global__ void __launch_bounds__(256) k_col2im_tanh(const TC* __restrict__ cols, const float* __restrict__ bias, int B,
                                                      int Hin, int Win, int C, float* __restrict__ out) {
   const int Ho = 2 * Hin, Wo = 2 * Win;
   const int64_t total = (int64_t)B * Ho * Wo;
@@ -1345,17 +1405,18 @@ __global__ void __launch_bounds__(256) k_col2im_tanh(const float* __restrict__ c
         const int kw = b ? (tw ? 2 : 0) : (tw ? 3 : 1), dw = b ? (tw ? 0 : 1) : (tw ? -1 : 0);
         const int iw = j + dw;
         if (iw < 0 || iw >= Win) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * 4));
+        const float4 v = ld_cols4(cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * 4);
         acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
       }
     }
     for (int c = 0; c < C; ++c) out[q * C + c] = tanhf(acc[c] + __ldg(bias + c));
   }
 }
-void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32) {
+void launch_col2im_tanh(Launch L, int dt_cols, const void* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32) {
   GAN_REQUIRE(C <= 4, "col2im head supports up to 4 channels");
   const int64_t total = (int64_t)B * Hin * Win * 4;
-  k_col2im_tanh<<<grid_for(total, 256, 16), 256, 0, L.s>>>(cols, bias, B, Hin, Win, C, out_f32);
+  if (dt_cols == DT_F16) k_col2im_tanh<f16><<<grid_for(total, 256, 16), 256, 0, L.s>>>((const f16*)cols, bias, B, Hin, Win, C, out_f32);
+  else k_col2im_tanh<float><<<grid_for(total, 256, 16), 256, 0, L.s>>>((const float*)cols, bias, B, Hin, Win, C, out_f32);
   KLAUNCH(L);
 }
 

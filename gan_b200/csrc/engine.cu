@@ -393,13 +393,16 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   s.in_views[li] = in; s.out_views[li] = out;
   if (ly.head && cols_on(ctx, n, ly)) {
     s.used_cols = true;
-    s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);            // fp32 rows: the 4-term col2im sum is not pre-rounded
-    View cols = make_view(nullptr, B, in.H, in.W, 64);
+    // cols rows: fp16 with fp16 storage (rounding 5e-4 of each of the four summed taps; the 268 MB fp32 round trip at
+    // batch 64 was the largest intermediate of the step), fp32 with bf16 storage (a bf16 pre-rounding would cost 4e-3)
+    const bool cols16 = ctx->dtA == DT_F16;
+    s.cols.ensure((size_t)B * in.H * in.W * 64 * 4);
+    View cols = make_view(cols16 ? s.cols.p : nullptr, B, in.H, in.W, 64);
     ConvOp cop = make_op_1tap(in, ly.Cin, cols, 64, 64, ly.wp_cols.p, ctx->dtA, ctx->dtA);
-    cop.out_rows_f32 = s.cols.as<float>();
+    if (!cols16) cop.out_rows_f32 = s.cols.as<float>();
     cop.real_n = 16 * ly.Cout;
     run_conv_fwd(ctx, cop);
-    launch_col2im_tanh(ctx->L(), s.cols.as<float>(), n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
+    launch_col2im_tanh(ctx->L(), cols16 ? DT_F16 : DT_F32, s.cols.p, n->params.as<float>() + ly.bias_off, B, in.H, in.W, ly.Cout, (float*)out.p);
     return;
   }
   if (ly.head && dcols_on(ctx, n, ly)) {
@@ -820,6 +823,8 @@ static void build_adam_tables(gan_net* n) {
       for (int t = 0; t < cd[c].ntaps; ++t) e.invD[cd[c].widx[t]] = (int8_t)((c << 4) | t);
     }
     e.tiles_a = (e.A + 63) / 64; e.tiles_b = (e.B + 63) / 64;
+    // 8-byte packed stores need 16-bit destinations with even strides; fp32 mode keeps the scalar path
+    e.vec = (n->ctx->dt != DT_F32 && e.A % 64 == 0 && e.B % 64 == 0 && ly.w_off % 4 == 0 && e.KtotF % 4 == 0 && e.KtotD % 4 == 0) ? 1 : 0;
     e.tile_begin = tiles;
     tiles += 16 * e.tiles_a * e.tiles_b;
     tab.push_back(e);

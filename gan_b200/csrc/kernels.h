@@ -21,7 +21,8 @@ void launch_im2col(Launch L, int dt_rows, const float* src, int B, int H, int W,
 // Same rows from a bf16 image with pixel pitch `pitch` (generator-head gradient dz): G[m][t*4 + c]
 // Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*4 + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
-void launch_col2im_tanh(Launch L, const float* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
+// cols: fp32 rows, or fp16 rows (dt_cols == DT_F16: half the bytes of the largest intermediate of the step)
+void launch_col2im_tanh(Launch L, int dt_cols, const void* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
 // Discriminator head (ZeroPad + Conv2D 4x4 s1, 512 -> 1, bias; base_gan.py:157-161) in cols form:
 //   cols[m'][tap*4] = a[m',:] . w[tap,:]  (GEMM over the 31x31 activation grid), then
 //   logits[n,oh,ow] = bias + sum_tap cols[(oh+kh-1, ow+kw-1)][tap*4]
@@ -86,7 +87,7 @@ void launch_scale(Launch L, float* p, int64_t n, float s);
 // weights are read once per step (28+4 B/param instead of 28 + 8).  Non-kernel tensors (gamma/beta/
 // bias) are updated by launch_adam_ranges.
 struct AdamPackEntry {
-  long long w_off; int A, B, conv2d, pad0;
+  long long w_off; int A, B, conv2d, vec;   // vec: full 64x64 tiles with 16-byte aligned rows (vectorised path)
   void* dstF; void* dstD;
   int KcF, KtotF, KcD, KtotD;
   long long boffF[4], boffD[4];
