@@ -242,6 +242,23 @@ template <> __device__ __forceinline__ uint32_t pack2<bf16>(float lo, float hi) 
 }
 template <> __device__ __forceinline__ uint32_t pack2<f16>(float lo, float hi) { return pack_f16x2_sat(lo, hi); }
 
+// "Last block" pattern for deterministic cross-block sums without a second launch: every block publishes its partial,
+// fences, and takes a ticket; exactly one block — the last to arrive, whichever that is — sees all partials and adds
+// them up IN INDEX ORDER, so the result does not depend on the arrival order.  The counter resets itself.
+__device__ __forceinline__ bool last_block_arrives(unsigned int* counter, unsigned int expected) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == expected - 1u) ? 1 : 0;
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

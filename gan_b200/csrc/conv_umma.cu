@@ -1116,7 +1116,9 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
   // make any partial second wave pure tail
   int64_t ctas = (int64_t)mblocks * ntiles * op.ncls;
   int splits = (int)((148 * 2) / ctas);
-  if (splits > total_boxes) splits = total_boxes;
+  // at least 16 pipeline stages per CTA: below that the prologue (barriers, TMEM allocation) and the 64 KB partial-tile
+  // epilogue outweigh the main loop (small per-GPU batches)
+  if (splits > total_boxes / 16) splits = total_boxes / 16;
   if (splits < 1) splits = 1;
   const int bn_slab = BN < 32 ? 16 : BN;
   if (splits > 1 && (op.wgrad_ws == nullptr || (size_t)ctas * splits * 128 * bn_slab * 4 > op.wgrad_ws_bytes)) splits = 1;

@@ -417,25 +417,24 @@ __global__ void __launch_bounds__(256) k_bwd_reduce(const TZ* __restrict__ z, Gr
 
 __global__ void __launch_bounds__(32 * FIN_LANES) k_bwd_finalize(const float* __restrict__ ws, int G, int nchunk, int C,
                                                                  double n, float* __restrict__ c1, float* __restrict__ c2,
-                                                                 float* dgamma, float* dbeta) {
+                                                                 float* dgamma, float* dbeta, unsigned int* counters) {
   const int g = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
   double S, Q;
   fin_reduce(ws, g, nchunk, C, c, lane, S, Q);
-  if (lane != 0 || c >= C) return;
-  c1[(size_t)g * C + c] = (float)(S / n); c2[(size_t)g * C + c] = (float)(Q / n);
-  // parameter gradients: BatchNorm has one group, so this is the only writer of the channel in this launch (launches of
-  // a step are ordered by the stream: deterministic).  InstanceNorm sums over its groups in k_group_param_grads.
-  if (G == 1) { dbeta[c] += (float)S; dgamma[c] += (float)Q; }
-}
-
-// InstanceNorm: dbeta[c] += sum_g n*c1[g][c], dgamma[c] += sum_g n*c2[g][c], groups in index order (deterministic)
-__global__ void __launch_bounds__(256) k_group_param_grads(const float* __restrict__ c1, const float* __restrict__ c2, int G, int C,
-                                                           float n, float* dgamma, float* dbeta) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
-  float sb = 0.f, sg = 0.f;
-  for (int g = 0; g < G; ++g) { sb += c1[(size_t)g * C + c] * n; sg += c2[(size_t)g * C + c] * n; }
-  dbeta[c] += sb; dgamma[c] += sg;
+  if (lane == 0 && c < C) {
+    c1[(size_t)g * C + c] = (float)(S / n); c2[(size_t)g * C + c] = (float)(Q / n);
+    // parameter gradients: BatchNorm has one group, so this is the only writer of the channel in this launch (launches
+    // of a step are ordered by the stream: deterministic)
+    if (G == 1) { dbeta[c] += (float)S; dgamma[c] += (float)Q; }
+  }
+  if (G == 1) return;
+  // InstanceNorm: the last block of this channel strip sums the groups in index order
+  if (!last_block_arrives(counters + blockIdx.x, (unsigned int)G)) return;
+  if (lane == 0 && c < C) {
+    float sb = 0.f, sg = 0.f;
+    for (int gg = 0; gg < G; ++gg) { sb += __ldcg(c1 + (size_t)gg * C + c) * (float)n; sg += __ldcg(c2 + (size_t)gg * C + c) * (float)n; }
+    dbeta[c] += sb; dgamma[c] += sg;
+  }
 }
 
 template <typename TZ, typename T, bool DROP>
@@ -595,7 +594,7 @@ template <typename TZ, typename T, bool DROP>
 __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
     const TZ* __restrict__ z_all, GradSrc d1, GradSrc d2, uint32_t P, uint32_t HW, int C, const float* __restrict__ mean,
     const float* __restrict__ inv, const float* __restrict__ scale, const float* __restrict__ shift, int act, DropKey dk,
-    float* __restrict__ c1, float* __restrict__ c2, float* dgamma, float* dbeta, T* __restrict__ dz_all) {
+    float* __restrict__ c1, float* __restrict__ c2, float* dgamma, float* dbeta, T* __restrict__ dz_all, unsigned int* counters) {
   constexpr int V = VecIO<T>::N;
   extern __shared__ uint4 slab[];                       // [narr][P]
   __shared__ double red[BNS_THREADS / 32][2 * V];
@@ -675,6 +674,16 @@ __global__ void __launch_bounds__(BNS_THREADS) k_bn_small_bwd(
     for (int k = 0; k < V; ++k) o[k] = sc[k] * (gg[k] - k1[k] - xc[k] * iv[k] * k2[k]);
     VecIO<T>::store(dz + (size_t)p * C + c0, o);
   }
+  if (gridDim.y > 1) {
+    // InstanceNorm: the last group-block of this channel slab sums the groups in index order (deterministic)
+    if (!last_block_arrives(counters + blockIdx.x, gridDim.y)) return;
+    if (threadIdx.x < V) {
+      const int c = c0 + threadIdx.x;
+      float sb = 0.f, sg = 0.f;
+      for (unsigned int gg = 0; gg < gridDim.y; ++gg) { sb += __ldcg(c1 + (size_t)gg * C + c) * (float)P; sg += __ldcg(c2 + (size_t)gg * C + c) * (float)P; }
+      dbeta[c] += sb; dgamma[c] += sg;
+    }
+  }
 }
 
 static bool g_bn_small = [] { const char* e = getenv("GAN_B200_BN_SMALL"); return !(e && e[0] == '0'); }();   // dev A/B switch
@@ -705,7 +714,8 @@ bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int 
 
 void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
-                     int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz) {
+                     int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz,
+                     unsigned int* counters) {
   int nchunk = stats_chunks(G, Pg);
   dispatch_dt2(dtz, dt, [&](auto* ztag, auto* tag) {
     using TZ = typename std::remove_pointer<decltype(ztag)>::type;
@@ -725,9 +735,8 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
       (void)once2;
       auto kern = dk.enabled ? k_bn_small_bwd<TZ, T, true> : k_bn_small_bwd<TZ, T, false>;
       kern<<<dim3(C / VecIO<T>::N, G), BNS_THREADS, (size_t)Pg * narr * 16, L.s>>>((const TZ*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, mean,
-                                                                         inv, scale, shift, act, dk, c1, c2, dgamma, dbeta, (T*)dz);
+                                                                         inv, scale, shift, act, dk, c1, c2, dgamma, dbeta, (T*)dz, counters);
       KLAUNCH(L);
-      if (G > 1) { k_group_param_grads<<<(C + 255) / 256, 256, 0, L.s>>>(c1, c2, G, C, (float)Pg, dgamma, dbeta); KLAUNCH(L); }
       return;
     }
     if (norm != NORM_NONE) {
@@ -735,9 +744,8 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
       kred<<<dim3(nchunk, G), 256, smem, L.s>>>((const TZ*)z, d1, d2, (uint32_t)Pg, (uint32_t)HW, C, lcv, nchunk, mean, inv,
                                                 scale, shift, act, dk, ws);
       KLAUNCH(L);
-      k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta);
+      k_bwd_finalize<<<dim3((C + 31) / 32, G), 32 * FIN_LANES, 0, L.s>>>(ws, G, nchunk, C, (double)Pg, c1, c2, dgamma, dbeta, counters);
       KLAUNCH(L);
-      if (G > 1) { k_group_param_grads<<<(C + 255) / 256, 256, 0, L.s>>>(c1, c2, G, C, (float)Pg, dgamma, dbeta); KLAUNCH(L); }
     }
     auto kapp = dk.enabled ? k_bwd_apply<TZ, T, true> : k_bwd_apply<TZ, T, false>;
     kapp<<<norm_grid(P, cv, narr == 3 ? 2 : 3), 256, smem, L.s>>>((const TZ*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW,
@@ -749,10 +757,20 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
 // ---------------------------------------------------------------------------------------------
 // Generator head backward (tanh output; L1 term pix2pix.py:181 / cycle_gan.py:167,176).
 // ---------------------------------------------------------------------------------------------
+// dbias[k] += sum over blocks (in index order) of part[block][k], done by the last block to arrive: deterministic
+__device__ __forceinline__ void head_bias_finish(const float* part, int C, float* dbias, unsigned int* counter) {
+  if (!last_block_arrives(counter, gridDim.x)) return;
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (k >= C || k >= 4) return;
+  double s = 0.0;
+  for (unsigned int b = lane; b < gridDim.x; b += 32) s += (double)__ldcg(part + (size_t)b * 4 + k);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dbias[k] += (float)s;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out, const float* __restrict__ ref, GradSrc d1,
                                                    GradSrc d2, float l1_coef, int64_t total, int C, T* __restrict__ dz,
-                                                   int dz_pitch, float* dbias) {
+                                                   int dz_pitch, float* dbias, float* part, unsigned int* counter) {
   __shared__ float sh[8];
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // C <= 4
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -780,31 +798,22 @@ __global__ void __launch_bounds__(256) k_ghead_bwd(const float* __restrict__ out
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-      dbias[(size_t)blockIdx.x * 4 + k] = t;             // per-block partial (summed in block order by k_sum_partials)
+      part[(size_t)blockIdx.x * 4 + k] = t;              // per-block partial
     }
   }
-}
-// dst[k] += sum over blocks (in index order) of part[block][k]: deterministic bias gradient of the generator head
-__global__ void k_sum_partials(const float* __restrict__ part, int nblocks, int C, float* dst) {
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (k >= C) return;
-  double s = 0.0;
-  for (int b = lane; b < nblocks; b += 32) s += (double)part[(size_t)b * 4 + k];
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) dst[k] += (float)s;
+  head_bias_finish(part, C, dbias, counter);
 }
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
-                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part) {
+                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part, unsigned int* counters) {
   GAN_REQUIRE(C <= 4, "generator head supports up to 4 output channels");
   int64_t total = P * C;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     const int grid = grid_for(total, 256, 4);
     GAN_REQUIRE(grid <= HEAD_PART_BLOCKS, "bias partial workspace too small");
-    k_ghead_bwd<T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dz_pitch, part);
-    k_sum_partials<<<1, 128, 0, L.s>>>(part, grid, C, dbias);
+    k_ghead_bwd<T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, total, C, (T*)dz, dz_pitch, dbias, part, counters);
   });
-  KLAUNCH(L); KLAUNCH(L);
+  KLAUNCH(L);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -825,7 +834,8 @@ __device__ __forceinline__ void block_partial_store(float v, float* dst) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_t n, float label, float coef_over_n,
-                                             T* dz, int dz_pitch, float* dbias, float* __restrict__ loss_slot) {
+                                             T* dz, int dz_pitch, float* dbias, float* part, unsigned int* counter,
+                                             float* __restrict__ loss_slot) {
   float acc = 0.f, bacc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -839,7 +849,7 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
   }
   block_partial_store(acc, loss_slot + blockIdx.x);
   if (dz != nullptr && dbias != nullptr) {
-    // per-block partial of the bias gradient; k_sum_partials adds them in block order (deterministic)
+    // per-block partial of the bias gradient; the last block adds them in block order (deterministic)
     __syncthreads();
     __shared__ float shb[8];
     float v = warp_sum(bacc);
@@ -848,23 +858,27 @@ __global__ void __launch_bounds__(256) k_bce(const float* __restrict__ x, int64_
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int w = 0; w < 8; ++w) t += shb[w];
-      dbias[(size_t)blockIdx.x * 4] = t;
+      part[blockIdx.x] = t;
+    }
+    if (!last_block_arrives(counter, gridDim.x)) return;
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(part + b);
+      *dbias += t;
     }
   }
 }
-__global__ void k_sum_partials(const float* __restrict__ part, int nblocks, int C, float* dst);
 void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
-                float* dbias, float* loss_ws, int slot, float* part_ws) {
+                float* dbias, float* loss_ws, int slot, float* part_ws, unsigned int* counters) {
   int blocks = grid_for(n, 256, 1);
   if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
   const bool bias = dz != nullptr && dbias != nullptr;
   dispatch_dt(dt, [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
-    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dz_pitch, bias ? part_ws : nullptr,
+    k_bce<T><<<blocks, 256, 0, L.s>>>(logits, n, label, coef / (float)n, (T*)dz, dz_pitch, bias ? dbias : nullptr, part_ws, counters,
                                       loss_ws + slot * LOSS_BLOCKS);
   });
   KLAUNCH(L);
-  if (bias) { k_sum_partials<<<1, 128, 0, L.s>>>(part_ws, blocks, 1, dbias); KLAUNCH(L); }
 }
 
 __global__ void __launch_bounds__(256) k_l1(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
@@ -1291,7 +1305,7 @@ __global__ void __launch_bounds__(256) k_im2col(const TS* __restrict__ src, int 
 template <int C, typename T>
 __global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict__ out, const float* __restrict__ ref,
                                                         GradSrc d1, GradSrc d2, float l1_coef, int B, int H, int W,
-                                                        T* __restrict__ dst, float* dbias) {
+                                                        T* __restrict__ dst, float* dbias, float* part, unsigned int* counter) {
   __shared__ float sh[8];
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
   const int Ho = H / 2, Wo = W / 2;
@@ -1336,12 +1350,13 @@ __global__ void __launch_bounds__(256) k_ghead_bwd_cols(const float* __restrict_
     if (threadIdx.x == 0) {
       float t = 0.f;
       for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += sh[wi];
-      dbias[(size_t)blockIdx.x * 4 + k] = t;             // per-block partial (k_sum_partials)
+      part[(size_t)blockIdx.x * 4 + k] = t;              // per-block partial
     }
   }
+  head_bias_finish(part, C, dbias, counter);
 }
 void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
-                           int H, int W, int C, void* gcols, float* dbias, float* part) {
+                           int H, int W, int C, void* gcols, float* dbias, float* part, unsigned int* counters) {
   GAN_REQUIRE(C >= 1 && C <= 4, "generator head supports up to 4 output channels");
   GAN_REQUIRE(dt == DT_F16 || dt == DT_BF16, "cols path is 16-bit only");
   const int64_t M = (int64_t)B * (H / 2) * (W / 2);
@@ -1350,14 +1365,12 @@ void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* 
   auto run = [&](auto* tag) {
     using T = typename std::remove_pointer<decltype(tag)>::type;
     T* d = (T*)gcols;
-    if (C == 1) k_ghead_bwd_cols<1, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
-    else if (C == 2) k_ghead_bwd_cols<2, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
-    else if (C == 3) k_ghead_bwd_cols<3, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
-    else k_ghead_bwd_cols<4, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, part);
+    if (C == 1) k_ghead_bwd_cols<1, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias, part, counters);
+    else if (C == 2) k_ghead_bwd_cols<2, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias, part, counters);
+    else if (C == 3) k_ghead_bwd_cols<3, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias, part, counters);
+    else k_ghead_bwd_cols<4, T><<<grid, 256, 0, L.s>>>(out_f32, ref_f32, d1, d2, l1_coef, B, H, W, d, dbias, part, counters);
   };
   if (dt == DT_F16) run((f16*)nullptr); else run((bf16*)nullptr);
-  KLAUNCH(L);
-  k_sum_partials<<<1, 128, 0, L.s>>>(part, grid, C, dbias);
   KLAUNCH(L);
 }
 

@@ -377,6 +377,11 @@ static void pack_weights(gan_net* n) {
 // ---------------------------------------------------------------------------------------------
 // one conv(+norm+act) layer, forward and backward
 // ---------------------------------------------------------------------------------------------
+// zero-initialised ticket counters of the "last block" sums (self-resetting), one set per stream
+static unsigned int* tickets(gan_ctx* ctx) {
+  ctx->sc().counters.ensure(4096);
+  return ctx->sc().counters.as<unsigned int>();
+}
 static DropKey drop_key(gan_ctx* ctx, const Layer& ly, const Slot& s) {
   DropKey k;
   k.seed_lo = (uint32_t)(ctx->seed & 0xffffffffu); k.seed_hi = (uint32_t)(ctx->seed >> 32);
@@ -497,7 +502,8 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
     ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 3 : 5));
     launch_norm_bwd(ctx->L(), ctx->dtA, ctx->dtG, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
                     st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
-                    ctx->sc().stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p);
+                    ctx->sc().stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p,
+                    tickets(ctx));
   }
   if (want_wgrad) {
     ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_WGRAD, s, dz) : make_op(ctx, ly, R_WGRAD, in, dz, nullptr);
@@ -615,11 +621,11 @@ static void generator_backward(gan_net* g, int slot, GradSrc d1, GradSrc d2, con
   if (s.used_cols) {
     s.gcols.ensure((size_t)B * (H / 2) * (W / 2) * 64 * 2);
     launch_ghead_bwd_cols(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, B, H, W, C, s.gcols.p,
-                          gr + g->layers[15].bias_off, ctx->sc().head_part.as<float>());
+                          gr + g->layers[15].bias_off, ctx->sc().head_part.as<float>(), tickets(ctx));
   } else {
     s.dlogit.ensure((size_t)B * H * W * Cp * es);
     launch_ghead_bwd(ctx->L(), ctx->dtG, s.out_f32.as<float>(), ref_f32, d1, d2, l1_coef, (int64_t)B * H * W, C, s.dlogit.p, Cp,
-                     gr + g->layers[15].bias_off, ctx->sc().head_part.as<float>());
+                     gr + g->layers[15].bias_off, ctx->sc().head_part.as<float>(), tickets(ctx));
   }
   for (int k = 1; k <= 7; ++k) {
     int hs = H >> (8 - k), ws = W >> (8 - k);
@@ -757,7 +763,7 @@ static void disc_bce(gan_net* d, int slot, float label, float coef, bool make_dz
   ctx->sc().head_part.ensure((size_t)HEAD_PART_BLOCKS * 4 * 4);
   launch_bce(ctx->L(), ctx->dtG, s.logits.as<float>(), n, label, coef, make_dz ? s.dlogit.p : nullptr, dzp,
              (make_dz && bias_grad) ? d->grads.as<float>() + d->layers[4].bias_off : nullptr, ctx->loss_ws.as<float>(),
-             loss_slot, ctx->sc().head_part.as<float>());
+             loss_slot, ctx->sc().head_part.as<float>(), tickets(ctx));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -55,7 +55,7 @@ struct gan_ctx {
   uint64_t launches = 0;
   // Workspaces that layer code writes, one set per stream: the side stream runs a whole discriminator pass while the
   // main stream runs the generator (engine.cu side_begin / side_join), so they must not share scratch memory.
-  struct Scratch { DevBuf stats_ws, dz_scratch, junk, splitk_ws, wgrad_ws, head_part; };
+  struct Scratch { DevBuf stats_ws, dz_scratch, junk, splitk_ws, wgrad_ws, head_part, counters; };   // counters: zeroed tickets of the last-block sums
   Scratch scr[2];
   int cur = 0;                                // 0: main stream, 1: side stream (selects L(), cs(), sc())
   cudaStream_t side = nullptr;

@@ -57,16 +57,17 @@ struct GradSrc { const void* p; int pitch, coff; };
 // Backward of (norm -> dropout -> activation): dz, plus dgamma/dbeta accumulated into the grad buffer.
 void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
-                     int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz);
+                     int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz,
+                     unsigned int* counters);
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
 // head backward written directly as slot-4 rows of the cols operand (bf16 path; dz is never materialised)
 void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
-                           int H, int W, int C, void* gcols, float* dbias, float* part_ws);
+                           int H, int W, int C, void* gcols, float* dbias, float* part_ws, unsigned int* counters);
 void launch_ghead_bwd(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2,
-                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part_ws);
+                      float l1_coef, int64_t P, int C, void* dz, int dz_pitch, float* dbias, float* part_ws, unsigned int* counters);
 // BCE-from-logits partial sums into loss slot `slot` and (optionally) dz = coef*(sigmoid(x)-label)/n.
 void launch_bce(Launch L, int dt, const float* logits, int64_t n, float label, float coef, void* dz, int dz_pitch,
-                float* dbias, float* loss_ws, int slot, float* part_ws);
+                float* dbias, float* loss_ws, int slot, float* part_ws, unsigned int* counters);
 void launch_l1(Launch L, const float* a, const float* b, int64_t n, float* loss_ws, int slot);
 // raw[j] = sum(slot j)/denom[j]; out[i] = sum_j mix[i*nraw+j]*raw[j]
 struct LossMix { int nraw, nout; float denom[LOSS_SLOTS]; float mix[8 * LOSS_SLOTS]; };
