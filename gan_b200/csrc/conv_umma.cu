@@ -963,10 +963,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
           if (row_ok && vec_ok && n0 + c + 32 <= p.Nr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              float4* d4 = reinterpret_cast<float4*>(dst + c + j);
-              if (acc_dst) { const float4 a = *d4; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-              *d4 = o;
+              // this CTA is the only writer of these elements in this launch and launches are stream-ordered, so a
+              // fire-and-forget reduction is deterministic here (no read latency in the epilogue)
+              if (acc_dst)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + j), "r"(v[j]), "r"(v[j + 1]),
+                             "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+              else
+                *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else if (row_ok) {
 #pragma unroll
@@ -976,7 +979,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
               if (p.n_slot4_c > 0) {      // cols column (tap*4 + slot) -> master row tap*C + slot
                 if ((nn & 3) < p.n_slot4_c) d1 = p.dW + (long long)kc * p.s_k + (long long)((nn >> 2) * p.n_slot4_c + (nn & 3)) * p.s_n;
               } else if (nn < p.Nr) d1 = dst + (long long)(c + j) * p.s_n;
-              if (d1 != nullptr) *d1 = acc_dst ? *d1 + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+              if (d1 != nullptr) { if (acc_dst) atomicAdd(d1, __uint_as_float(v[j])); else *d1 = __uint_as_float(v[j]); }
             }
           }
         }
@@ -986,7 +989,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (j < p.Nr) { float* d1 = dst + (long long)j * p.s_n; *d1 = acc_dst ? *d1 + __uint_as_float(v[j]) : __uint_as_float(v[j]); }
+            if (j < p.Nr) { float* d1 = dst + (long long)j * p.s_n; if (acc_dst) atomicAdd(d1, __uint_as_float(v[j])); else *d1 = __uint_as_float(v[j]); }
         }
       }
     }
@@ -1057,7 +1060,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p)
       if (kc >= p.Kr || nn >= p.Nr) continue;
       off = (long long)p.widx[cls][t & 15] * p.s_tap + (long long)kc * p.s_k + (long long)nn * p.s_n;
     }
-    p.dW[off] = p.accumulate ? p.dW[off] + vals[e] : vals[e];
+    if (p.accumulate) atomicAdd(p.dW + off, vals[e]); else p.dW[off] = vals[e];      // single writer per element: deterministic
   }
 }
 
