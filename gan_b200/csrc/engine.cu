@@ -390,6 +390,15 @@ static DropKey drop_key(gan_ctx* ctx, const Layer& ly, const Slot& s) {
   return k;
 }
 
+// First layers: rows built in shared memory by k_conv_first_fwd (conv_first.cu), activation fused.
+static bool first_kernel_ok(const gan_ctx* ctx, const Layer& ly, const Slot& s, int H, int W) {
+  if (!ly.first || ctx->dt != DT_BF16 || ctx->engine == GAN_ENGINE_FFMA || ly.norm != NORM_NONE || ly.act != ACT_LEAKY) return false;
+  if (ly.Cout != 64 || ly.wp_im2col.p == nullptr || s.src_f32[0] == nullptr) return false;
+  FirstLayerOp op; memset(&op, 0, sizeof(op));
+  op.nsrc = ly.nsrc; op.C = ly.src_c; op.H = H; op.W = W; op.a_pitch = 8; op.a_coff = 0; op.dt = ctx->dtA;
+  return first_fwd_supported(op);
+}
+
 static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   gan_ctx* ctx = n->ctx;
   Layer& ly = n->layers[li];
@@ -436,6 +445,14 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
   int64_t P = (int64_t)B * Ho * Wo;
   s.z[li].ensure((size_t)P * ly.Cout * ctx->esize());
   View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
+  if (li == 0 && s.used_im2col && first_kernel_ok(ctx, ly, s, in.H, in.W) && out.pitch % 8 == 0 && out.coff % 8 == 0) {
+    FirstLayerOp op; memset(&op, 0, sizeof(op));
+    op.src[0] = s.src_f32[0]; op.src[1] = s.src_f32[1]; op.nsrc = ly.nsrc; op.C = ly.src_c; op.B = B; op.H = in.H; op.W = in.W;
+    op.wpack = ly.wp_im2col.p; op.z = z.p; op.a = out.p; op.a_pitch = out.pitch; op.a_coff = out.coff; op.dt = ctx->dtA;
+    ProfScope ps(ctx, FAM_UMMA_FWD, 2.0 * (double)P * 64.0 * 16.0 * ly.Cin);
+    launch_conv_first_fwd(ctx->L(), op);
+    return;
+  }
   const int G = ly.norm == NORM_BATCH ? 1 : B;
   const int64_t Pg = P / G;
   const size_t gc = (size_t)G * ly.Cout;
@@ -506,6 +523,10 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
                     tickets(ctx));
   }
   if (want_wgrad) {
+    if (li == 0 && s.used_im2col) {       // rows of the input image(s) for the weight-gradient GEMM (cached per image and step)
+      for (int k = 0; k < ly.nsrc; ++k)
+        if (s.src_f32[k] != nullptr) s.im2col[k] = cached_im2col(ctx, s.src_f32[k], B, in.H, in.W, ly.src_c);
+    }
     ConvOp op = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_WGRAD, s, dz) : make_op(ctx, ly, R_WGRAD, in, dz, nullptr);
     op.dW = n->grads.as<float>() + ly.w_off;
     run_conv_wgrad(ctx, ly, op);
@@ -547,8 +568,11 @@ static void generator_forward(gan_net* g, int slot, const float* x_f32, int B, i
   const int Cp = g->Cp;
   s.used_im2col = im2col_on(ctx, g->layers[0]);
   s.xin.ensure((size_t)B * H * W * Cp * es);
+  s.src_f32[0] = x_f32; s.src_f32[1] = nullptr;
   if (s.used_im2col) {
-    s.im2col[0] = cached_im2col(ctx, x_f32, B, H, W, C);
+    // rows in HBM only where the first-layer kernel (rows built in shared memory) cannot run; the weight-gradient pass
+    // fetches them lazily
+    if (!first_kernel_ok(ctx, g->layers[0], s, H, W)) s.im2col[0] = cached_im2col(ctx, x_f32, B, H, W, C);
   } else {
     launch_convert(ctx->L(), ctx->dtA, x_f32, (int64_t)B * H * W, C, s.xin.p, Cp, 0);
   }
@@ -698,9 +722,12 @@ static void discriminator_forward(gan_net* d, int slot, const float* inp, const 
   const int C = d->C, C0 = d->Cin0_p;
   s.in0.ensure((size_t)B * H * W * C0 * es);
   s.used_im2col = im2col_on(ctx, d->layers[0]);
+  s.src_f32[0] = inp; s.src_f32[1] = tar;
   if (s.used_im2col) {                                   // one im2col K-block per source of concatenate([inp, tar])
-    s.im2col[0] = cached_im2col(ctx, inp, B, H, W, C);
-    if (tar) s.im2col[1] = cached_im2col(ctx, tar, B, H, W, C);
+    if (!first_kernel_ok(ctx, d->layers[0], s, H, W)) {
+      s.im2col[0] = cached_im2col(ctx, inp, B, H, W, C);
+      if (tar) s.im2col[1] = cached_im2col(ctx, tar, B, H, W, C);
+    }
   } else {
     launch_convert(ctx->L(), ctx->dtA, inp, (int64_t)B * H * W, C, s.in0.p, C0, 0);      // concatenate([inp, tar]) base_gan.py:139
     if (tar) launch_convert(ctx->L(), ctx->dtA, tar, (int64_t)B * H * W, C, s.in0.p, C0, C);
@@ -1233,6 +1260,7 @@ int gan_ctx_create(int device, int precision, uint64_t seed, gan_ctx** out) {
   CUDA_CHECK(cudaMallocHost((void**)&c->loss_host, 16 * 4));
   c->call_dev.ensure(16);
   umma_init();
+  first_init();
   live_add(c);
   *out = c;
   API_END
@@ -1337,7 +1365,9 @@ int gan_comm_unique_id(void* out128) {
 int gan_ctx_comm_init(gan_ctx* ctx, int rank, int world, const void* unique_id128) {
   API_BEGIN
   CUDA_CHECK(cudaSetDevice(ctx->device));
-  { const char* e = getenv("GAN_B200_SHARD_OPT"); ctx->shard_optimizer = !(e && e[0] == '0'); }    // dev A/B switch
+  // Sharded optimizer from 4 ranks up (measured at N=2: the exposed all-gather + separate repack cost more than the
+  // half Adam they save: 5.97 vs 5.62 ms/step); GAN_B200_SHARD_OPT=0/1 forces it
+  { const char* e = getenv("GAN_B200_SHARD_OPT"); ctx->shard_optimizer = e ? (e[0] != '0') : (world >= 4); }
   comm_init(ctx, rank, world, unique_id128);
   API_END
 }

@@ -147,6 +147,7 @@ struct Slot {
   // discriminator
   DevBuf in0, logits, dlogit, din0;
   const void* im2col[2] = {nullptr, nullptr};   // first-layer im2col rows per input source (ctx cache entries)
+  const float* src_f32[2] = {nullptr, nullptr}; // the fp32 input images of this call (first-layer kernel, lazy rows for wgrad)
   DevBuf cols, gcols;        // generator head: cols = x*W (forward), gcols = im2col(dz) (backward)
   bool used_cols = false;
   bool used_im2col = false;

@@ -115,6 +115,18 @@ int launch_conv_fwd_umma(Launch L, const ConvOp& op);
 void launch_conv_wgrad_umma(Launch L, const ConvOp& op);
 void umma_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
 
+// ---- conv_first.cu --------------------------------------------------------------------------
+// First layers (Conv2D 4x4 s2, 1..4 channels per source image, 64 filters, LeakyReLU, no norm) with the im2col rows built
+// in shared memory: src[] fp32 NHWC images, wpack = the layer's im2col-order weight pack [64][nsrc*64], z = raw output
+// (compact, 16-bit), a = LeakyReLU(z) into the consumer view.
+struct FirstLayerOp {
+  const float* src[2]; int nsrc, C, B, H, W;
+  const void* wpack; void* z; void* a; int a_pitch, a_coff; int dt;
+};
+void first_init();
+bool first_fwd_supported(const FirstLayerOp& op);
+void launch_conv_first_fwd(Launch L, const FirstLayerOp& op);
+
 // on-device input pipeline: gan_image_xform (include/gan_b200.h) plus the float32 resize scales in/out of
 // each stage, divided once per image on the host
 struct ImageXformDev {

@@ -107,7 +107,8 @@ def test_two_gpu_data_parallel_step_matches_oracle(model, precision):
     tol = 1e-4 if precision == "fp32" else 1e-2
     for a, r in zip(r0["losses"] + r0["losses2"], r0["ref_losses"] + r0["ref_losses2"]):
         assert abs(a - r) <= tol * max(1.0, abs(r)), (r0["losses"], r0["ref_losses"], r0["losses2"], r0["ref_losses2"])
-    assert all(e <= 2 * 2 * 2e-4 * 1.01 for e in r0["w_err"]), r0["w_err"]
+    # two Keras-Adam steps: |update| <= lr * (1 + small) each, for the device and for the oracle
+    assert all(e <= 2 * 2 * 2e-4 * (1.01 if precision == "fp32" else 1.05) for e in r0["w_err"]), r0["w_err"]
 
 
 # ---------------------------------------------------------------------------------------------------------------
