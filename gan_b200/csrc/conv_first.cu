@@ -10,10 +10,11 @@
 //     16-byte stores), fences the async proxy and signals the MMA warp;
 //   * warp 8 issues 4 (x sources) tcgen05.mma M=128 x N=64 x K=16 against the stationary weight tile (one TMA load per
 //     CTA) into the group's TMEM columns and commits to the group's barrier;
-//   * the same 4 warps drain TMEM: z (raw conv output, kept for the backward pass) and a = LeakyReLU(z) written into
-//     the consumer view (skip-concat buffer), 128 contiguous bytes per thread each.
+//   * the same 4 warps drain TMEM: a = LeakyReLU(z) goes through shared memory into the consumer view (skip-concat
+//     buffer) with 8 lanes per 128-byte row.  z itself is not stored: LeakyReLU keeps the sign, so the backward pass
+//     takes the activation derivative from a (launch_norm_bwd with a strided z view).
 // Two groups per CTA alternate tiles, so the gather / store phases of one overlap the other's.  HBM traffic per image
-// batch: the fp32 image(s) once + z + a — the roofline of this layer is HBM, and the kernel moves nothing else.
+// batch: the fp32 image(s) once + a — the roofline of this layer is HBM, and the kernel moves nothing else.
 #include <cuda.h>
 #include <cstring>
 #include "kernels.h"
@@ -76,23 +77,24 @@ struct alignas(64) FirstFwdParams {
   CUtensorMap bmap;                  // packed weights [64][nsrc*64], K-major
   const float* src[2];               // fp32 NHWC images (B, H, W, C)
   int nsrc, C, B, H, W;              // H, W: input size; output grid H/2 x W/2
-  bf16* z;                           // raw conv output, compact (B, H/2, W/2, 64), 16-bit
-  bf16* a; int a_pitch, a_coff;      // LeakyReLU(z) into the consumer view
+  bf16* a; int a_pitch, a_coff;      // LeakyReLU(z) into the consumer view (16-bit)
   int tiles_w, tiles_h, num_tiles;
   int ab_bf16, out_f16;
 };
+
+constexpr int PATCH_PITCH = PATCH_W * 8;                            // bytes per patch row: 34 pixels x 4 slots x 16 bit
+constexpr int PATCH_BYTES = ((PATCH_H * PATCH_PITCH + 127) / 128) * 128;
 
 template <int NSRC>
 __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_constant__ FirstFwdParams p) {
   constexpr uint32_t A_BYTES = 128 * 128;                         // one source: 128 rows x 64 x 16 bit
   constexpr uint32_t GROUP_A = NSRC * A_BYTES;
-  constexpr int PATCH_FLOATS = PATCH_H * PATCH_W * 4;             // channel slots padded to 4
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* atile = smem;                                          // [2 groups][NSRC][128][128 B]
   uint8_t* wsm = smem + 2 * GROUP_A;                              // [NSRC][64 rows][128 B]
-  float* patch = (float*)(wsm + NSRC * 64 * 128);                 // [2 groups][NSRC][18][34][4]
-  uint64_t* bars = (uint64_t*)(patch + 2 * NSRC * PATCH_FLOATS);  // full[2], done[2], wbar
+  uint8_t* patch = wsm + NSRC * 64 * 128;                         // [2 groups][NSRC][18][34][4 slots] 16-bit
+  uint64_t* bars = (uint64_t*)(patch + 2 * NSRC * PATCH_BYTES);   // full[2], done[2], wbar
   uint32_t* tmem_slot = (uint32_t*)(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
     const int pl = (threadIdx.x & 127);            // output pixel inside the tile == accumulator row
     const int olh = pl / FT_W, olw = pl % FT_W;
-    float* my_patch = patch + g * NSRC * PATCH_FLOATS;
+    uint8_t* my_patch = patch + g * NSRC * PATCH_BYTES;
     uint8_t* my_a = atile + g * GROUP_A;
     const int bar_id = 1 + g;                      // named barrier of the group (128 threads)
     uint32_t n = 0;
@@ -158,71 +160,94 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
       const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
       const int oh0 = th * FT_H, ow0 = tw * FT_W;
       const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-      // 1. input patch -> shared memory (fp32, 4 channel slots per pixel; zero outside the image = 'same' padding)
+      // 1. input patch -> shared memory as 16-bit pixels of 4 channel slots (8 bytes; zero outside the image = 'same'
+      //    padding).  All of a thread's loads (up to 5 pixels x C channels x NSRC images) are issued before the first
+      //    store, so one DRAM round trip covers the whole patch.
+      constexpr int NPX = (PATCH_H * PATCH_W + 127) / 128;
+      float4 pv[NSRC][NPX];
 #pragma unroll
       for (int s = 0; s < NSRC; ++s) {
         const float* img = p.src[s] + (size_t)b * p.H * p.W * p.C;
-        for (int i = pl; i < PATCH_H * PATCH_W; i += 128) {
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+          const int i = pl + j * 128;
           const int r = i / PATCH_W, c = i - r * PATCH_W;
           const int ih = ih0 + r, iw = iw0 + c;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+          if (i < PATCH_H * PATCH_W && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
             const float* px = img + ((size_t)ih * p.W + iw) * p.C;
             v.x = __ldg(px);
             if (p.C > 1) v.y = __ldg(px + 1);
             if (p.C > 2) v.z = __ldg(px + 2);
             if (p.C > 3) v.w = __ldg(px + 3);
           }
-          *reinterpret_cast<float4*>(my_patch + s * PATCH_FLOATS + i * 4) = v;
+          pv[s][j] = v;
         }
       }
+#pragma unroll
+      for (int s = 0; s < NSRC; ++s)
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+          const int i = pl + j * 128;
+          if (i < PATCH_H * PATCH_W) {
+            uint2 o;
+            if (p.ab_bf16) { o.x = pack2<bf16>(pv[s][j].x, pv[s][j].y); o.y = pack2<bf16>(pv[s][j].z, pv[s][j].w); }
+            else { o.x = pack2<f16>(pv[s][j].x, pv[s][j].y); o.y = pack2<f16>(pv[s][j].z, pv[s][j].w); }
+            *reinterpret_cast<uint2*>(my_patch + s * PATCH_BYTES + i * 8) = o;
+          }
+        }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      // 2. this thread's row: 16 taps x 4 slots -> eight 16-byte chunks, chunk j at (j ^ (row & 7)) (SWIZZLE_128B)
+      // 2. this thread's row: chunk j = taps (kh, kw0), (kh, kw0+1) = two ADJACENT patch pixels = 16 contiguous, 16-byte
+      //    aligned bytes of the patch (kw0 is even), copied to chunk (j ^ (row & 7)) of the row (SWIZZLE_128B)
 #pragma unroll
       for (int s = 0; s < NSRC; ++s) {
-        const float* ps = my_patch + s * PATCH_FLOATS;
+        const uint8_t* ps = my_patch + s * PATCH_BYTES;
         uint8_t* row = my_a + s * A_BYTES + pl * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                 // taps 2j, 2j+1: kh = j/2, kw = (j&1)*2 + {0,1}
+        for (int j = 0; j < 8; ++j) {
           const int kh = j >> 1, kw0 = (j & 1) * 2;
-          const float4 v0 = *reinterpret_cast<const float4*>(ps + ((2 * olh + kh) * PATCH_W + 2 * olw + kw0) * 4);
-          const float4 v1 = *reinterpret_cast<const float4*>(ps + ((2 * olh + kh) * PATCH_W + 2 * olw + kw0 + 1) * 4);
-          uint4 o;
-          if (p.ab_bf16) { o.x = pack2<bf16>(v0.x, v0.y); o.y = pack2<bf16>(v0.z, v0.w); o.z = pack2<bf16>(v1.x, v1.y); o.w = pack2<bf16>(v1.z, v1.w); }
-          else { o.x = pack2<f16>(v0.x, v0.y); o.y = pack2<f16>(v0.z, v0.w); o.z = pack2<f16>(v1.x, v1.y); o.w = pack2<f16>(v1.z, v1.w); }
-          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = o;
+          const uint4 v = *reinterpret_cast<const uint4*>(ps + (2 * olh + kh) * PATCH_PITCH + (2 * olw + kw0) * 8);
+          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = v;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (pl == 0) mbar_arrive(&bars[g]);
-      // 3. accumulator -> z and LeakyReLU(z)
+      // 3. accumulator -> LeakyReLU -> consumer view.  A warp-wide store in which every lane writes into its own pixel
+      //    row touches 32 lines = 32 LSU wavefronts (measured: that alone bounded the first version at 182 us per
+      //    launch), so the tile is transposed through the group's A buffer (free once the MMA has committed;
+      //    XOR-swizzled 16-byte chunks, conflict-free both ways) and written with 8 lanes per 128-byte row.
       mbar_wait(&bars[2 + g], n & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int oh = oh0 + olh, ow = ow0 + olw;
-      const size_t pix = ((size_t)b * Ho + oh) * Wo + ow;
-      bf16* zrow = p.z + pix * 64;
-      bf16* arow = p.a + pix * p.a_pitch + p.a_coff;
       const uint32_t taddr = tmem_base + g * 64 + ((uint32_t)(q * 32) << 16);
+      uint4* ast = reinterpret_cast<uint4*>(my_a);                       // [128 rows][8 chunks] (16 KB)
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t zo[4], ao[4];
+          uint32_t ao[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float z0 = __uint_as_float(v[j * 8 + 2 * e]), z1 = __uint_as_float(v[j * 8 + 2 * e + 1]);
             const float a0 = z0 > 0.f ? z0 : LEAKY_SLOPE * z0, a1 = z1 > 0.f ? z1 : LEAKY_SLOPE * z1;
-            if (p.out_f16) { zo[e] = pack2<f16>(z0, z1); ao[e] = pack2<f16>(a0, a1); }
-            else { zo[e] = pack2<bf16>(z0, z1); ao[e] = pack2<bf16>(a0, a1); }
+            ao[e] = p.out_f16 ? pack2<f16>(a0, a1) : pack2<bf16>(a0, a1);
           }
-          *reinterpret_cast<uint4*>(zrow + c + j * 8) = make_uint4(zo[0], zo[1], zo[2], zo[3]);
-          *reinterpret_cast<uint4*>(arow + c + j * 8) = make_uint4(ao[0], ao[1], ao[2], ao[3]);
+          const int ch = (c >> 3) + j;                                   // 16-byte chunk 0..7 of this pixel's row
+          ast[pl * 8 + (ch ^ (pl & 7))] = make_uint4(ao[0], ao[1], ao[2], ao[3]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int qi = it * 128 + pl;                                    // linear 16-byte chunk of the tile
+        const int r = qi >> 3, ch = qi & 7;                              // tile row (output pixel), chunk
+        const int oh = oh0 + r / FT_W, ow = ow0 + r % FT_W;
+        const size_t pix = ((size_t)b * Ho + oh) * Wo + ow;
+        *reinterpret_cast<uint4*>(p.a + pix * p.a_pitch + p.a_coff + ch * 8) = ast[r * 8 + (ch ^ (r & 7))];
+      }
       // the group's patch / A tile / TMEM columns are free again once all 128 threads are here
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
@@ -233,7 +258,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
 }
 
 size_t first_smem_bytes(int nsrc) {
-  return (size_t)2 * nsrc * 128 * 128 + (size_t)nsrc * 64 * 128 + (size_t)2 * nsrc * PATCH_H * PATCH_W * 4 * 4 + 64 + 16 + 1024;
+  return (size_t)2 * nsrc * 128 * 128 + (size_t)nsrc * 64 * 128 + (size_t)2 * nsrc * PATCH_BYTES + 64 + 16 + 1024;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -273,10 +298,10 @@ void launch_conv_first_fwd(Launch L, const FirstLayerOp& op) {
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(first layer) failed: " + std::to_string((int)r));
   P.src[0] = op.src[0]; P.src[1] = op.src[1]; P.nsrc = op.nsrc; P.C = op.C; P.B = op.B; P.H = op.H; P.W = op.W;
-  P.z = (bf16*)op.z; P.a = (bf16*)op.a; P.a_pitch = op.a_pitch; P.a_coff = op.a_coff;
+  P.a = (bf16*)op.a; P.a_pitch = op.a_pitch; P.a_coff = op.a_coff;
   P.tiles_w = (op.W / 2) / FT_W; P.tiles_h = (op.H / 2) / FT_H; P.num_tiles = P.tiles_w * P.tiles_h * op.B;
   P.ab_bf16 = op.dt == DT_F16 ? 0 : 1; P.out_f16 = op.dt == DT_F16 ? 1 : 0;
-  const int per_sm = op.nsrc == 1 ? 3 : 1;                       // shared memory: 61 KB (one source) / 121 KB (two)
+  const int per_sm = 2;                                          // registers (106-118 x 288 threads) allow two CTAs; shared memory 52 / 102 KB
   int grid = (P.num_tiles + 1) / 2;
   if (grid > 148 * per_sm) grid = 148 * per_sm;
   if (op.nsrc == 1) k_conv_first_fwd<1><<<grid, FIRST_THREADS, first_smem_bytes(1), L.s>>>(P);

@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const TZ* __restrict__ z, Gra
                                                    const float* __restrict__ mean, const float* __restrict__ inv,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    const float* __restrict__ c1, const float* __restrict__ c2, int act,
-                                                   DropKey dk, T* __restrict__ dz) {
+                                                   DropKey dk, T* __restrict__ dz, int z_pitch, int z_coff) {
   constexpr int V = VecIO<T>::N;
   extern __shared__ uint4 ring[];
   const uint32_t tid = blockIdx.x * 256u + threadIdx.x;
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256) k_bwd_apply(const TZ* __restrict__ z, Gra
   auto issue = [&](uint32_t it) {
     const bool ok = it < nit;
     const size_t p = (size_t)prow + (size_t)it * pstride;
-    ring_issue3<TZ, T>(ring, it, ok, z, p * C + c0, d1, d2, p, c0);
+    ring_issue3<TZ, T>(ring, it, ok, z, p * z_pitch + z_coff + c0, d1, d2, p, c0);
   };
   for (uint32_t it = 0; it < RING_STAGES - 1; ++it) issue(it);
   for (uint32_t it = 0; it < nit; ++it) {
@@ -715,8 +715,10 @@ bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int 
 void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz,
-                     unsigned int* counters) {
+                     unsigned int* counters, int z_pitch, int z_coff) {
   int nchunk = stats_chunks(G, Pg);
+  if (z_pitch <= 0) { z_pitch = C; z_coff = 0; }
+  GAN_REQUIRE(norm == NORM_NONE || (z_pitch == C && z_coff == 0), "a strided z view is only supported for layers without normalisation");
   dispatch_dt2(dtz, dt, [&](auto* ztag, auto* tag) {
     using TZ = typename std::remove_pointer<decltype(ztag)>::type;
     using T = typename std::remove_pointer<decltype(tag)>::type;
@@ -749,7 +751,7 @@ void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradS
     }
     auto kapp = dk.enabled ? k_bwd_apply<TZ, T, true> : k_bwd_apply<TZ, T, false>;
     kapp<<<norm_grid(P, cv, narr == 3 ? 2 : 3), 256, smem, L.s>>>((const TZ*)z, d1, d2, (uint32_t)P, (uint32_t)Pg, G, (uint32_t)HW,
-                                                                 C, lcv, norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz);
+                                                                 C, lcv, norm, mean, inv, scale, shift, c1, c2, act, dk, (T*)dz, z_pitch, z_coff);
     KLAUNCH(L);
   });
 }

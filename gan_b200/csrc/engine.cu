@@ -443,12 +443,14 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     return;
   }
   int64_t P = (int64_t)B * Ho * Wo;
+  if (li == 0) s.z_is_act0 = false;
   s.z[li].ensure((size_t)P * ly.Cout * ctx->esize());
   View z = make_view(s.z[li].p, B, Ho, Wo, ly.Cout);
   if (li == 0 && s.used_im2col && first_kernel_ok(ctx, ly, s, in.H, in.W) && out.pitch % 8 == 0 && out.coff % 8 == 0) {
     FirstLayerOp op; memset(&op, 0, sizeof(op));
     op.src[0] = s.src_f32[0]; op.src[1] = s.src_f32[1]; op.nsrc = ly.nsrc; op.C = ly.src_c; op.B = B; op.H = in.H; op.W = in.W;
-    op.wpack = ly.wp_im2col.p; op.z = z.p; op.a = out.p; op.a_pitch = out.pitch; op.a_coff = out.coff; op.dt = ctx->dtA;
+    op.wpack = ly.wp_im2col.p; op.a = out.p; op.a_pitch = out.pitch; op.a_coff = out.coff; op.dt = ctx->dtA;
+    s.z_is_act0 = true;                    // z is not stored: the backward pass reads the sign from the activation view
     ProfScope ps(ctx, FAM_UMMA_FWD, 2.0 * (double)P * 64.0 * 16.0 * ly.Cin);
     launch_conv_first_fwd(ctx->L(), op);
     return;
@@ -517,10 +519,12 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
     float* dbeta = (gr && ly.norm != NORM_NONE) ? gr + ly.b_off : ctx->sc().junk.as<float>() + 1024;
     if (ly.norm != NORM_NONE) ctx->sc().stats_ws.ensure(stats_ws_floats(G, Pg, ly.Cout) * 4);
     ProfScope ps(ctx, FAM_NORM, (double)P * ly.Cout * ctx->esize() * (ly.norm == NORM_NONE ? 3 : 5));
-    launch_norm_bwd(ctx->L(), ctx->dtA, ctx->dtG, s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st, st ? st + gc : nullptr,
-                    st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
+    const bool from_act = li == 0 && s.z_is_act0;           // first-layer kernel: sign(z) == sign(LeakyReLU(z))
+    const View av = s.out_views[li];
+    launch_norm_bwd(ctx->L(), ctx->dtA, ctx->dtG, from_act ? av.p : s.z[li].p, d1, d2, P, Pg, G, Ho * Wo, ly.Cout, ly.norm, st,
+                    st ? st + gc : nullptr, st ? st + 2 * gc : nullptr, st ? st + 3 * gc : nullptr, ly.act, drop_key(ctx, ly, s),
                     ctx->sc().stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p,
-                    tickets(ctx));
+                    tickets(ctx), from_act ? av.pitch : 0, from_act ? av.coff : 0);
   }
   if (want_wgrad) {
     if (li == 0 && s.used_im2col) {       // rows of the input image(s) for the weight-gradient GEMM (cached per image and step)
@@ -1524,7 +1528,10 @@ int gan_net_debug_tensor(gan_net* net, int slot, const char* name, float* host_d
     GAN_REQUIRE(li >= 0 && !net->layers[li].head, "unknown layer");
     View ov = s.out_views[li];
     P = ov.pixels(); C = ov.C;
-    if (what == "z") { src = s.z[li].p; pitch = C; coff = 0; }
+    if (what == "z") {
+      GAN_REQUIRE(!(li == 0 && s.z_is_act0), "down1.z is not stored by the first-layer kernel (set GAN_B200_FIRST=0 to inspect it)");
+      src = s.z[li].p; pitch = C; coff = 0;
+    }
     else if (what == "a") { src = ov.p; pitch = ov.pitch; coff = ov.coff; }
     else GAN_REQUIRE(false, "debug tensor kind must be z or a");
   }

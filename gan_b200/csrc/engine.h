@@ -151,6 +151,7 @@ struct Slot {
   DevBuf cols, gcols;        // generator head: cols = x*W (forward), gcols = im2col(dz) (backward)
   bool used_cols = false;
   bool used_im2col = false;
+  bool z_is_act0 = false;     // layer 0 ran on the first-layer kernel: no z stored, the activation view stands in for it
   std::vector<DevBuf> act, dact;
 };
 

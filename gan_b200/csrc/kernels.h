@@ -58,7 +58,8 @@ struct GradSrc { const void* p; int pitch, coff; };
 void launch_norm_bwd(Launch L, int dtz, int dt, const void* z, GradSrc d1, GradSrc d2, int64_t P, int64_t Pg, int G, int HW,
                      int C, int norm, const float* mean, const float* inv, const float* scale, const float* shift,
                      int act, DropKey dk, float* ws, float* c1, float* c2, float* dgamma, float* dbeta, void* dz,
-                     unsigned int* counters);
+                     unsigned int* counters, int z_pitch = 0, int z_coff = 0);   // z_pitch > 0: `z` is a strided view (no-norm layers:
+                                                                                 // the activation stands in for z, same sign)
 // Generator head backward: dz = (d1 + d2 + l1_coef*sign(out-ref)) * (1-out^2); dbias += sum(dz).
 // head backward written directly as slot-4 rows of the cols operand (bf16 path; dz is never materialised)
 void launch_ghead_bwd_cols(Launch L, int dt, const float* out_f32, const float* ref_f32, GradSrc d1, GradSrc d2, float l1_coef, int B,
@@ -117,11 +118,11 @@ void umma_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
 
 // ---- conv_first.cu --------------------------------------------------------------------------
 // First layers (Conv2D 4x4 s2, 1..4 channels per source image, 64 filters, LeakyReLU, no norm) with the im2col rows built
-// in shared memory: src[] fp32 NHWC images, wpack = the layer's im2col-order weight pack [64][nsrc*64], z = raw output
-// (compact, 16-bit), a = LeakyReLU(z) into the consumer view.
+// in shared memory: src[] fp32 NHWC images, wpack = the layer's im2col-order weight pack [64][nsrc*64], a = LeakyReLU(z)
+// into the consumer view (the backward pass takes the activation derivative from the sign of a).
 struct FirstLayerOp {
   const float* src[2]; int nsrc, C, B, H, W;
-  const void* wpack; void* z; void* a; int a_pitch, a_coff; int dt;
+  const void* wpack; void* a; int a_pitch, a_coff; int dt;     // z itself is not stored: LeakyReLU keeps the sign
 };
 void first_init();
 bool first_fwd_supported(const FirstLayerOp& op);
