@@ -7,17 +7,23 @@
 A "step" is one Pix2Pix.train_step (reference pix2pix.py:190-218) over one synthetic batch:
 generator forward, two discriminator forwards, four losses, both backward sweeps, both Keras-Adam
 updates.  Workload: 256x256 RGB, GLOBAL batch 64 split evenly over the N ranks (strong scaling),
-bf16 tcgen05 convolutions with fp32 master weights / statistics / optimizer.
+16-bit (fp16 storage with a static loss scale; GAN_B200_ACT=bf16 for bf16) tcgen05 convolutions with fp32 master
+weights / statistics / optimizer; N>1: bucketed NCCL reduce-scatter + sharded Adam + all-gather (N >= 4) or
+all-reduce + fused Adam (N = 2).
 
   value   images/s with the inputs already resident in HBM (pool of 8 distinct batches, 805 MB,
-          larger than the 126 MB L2), CUDA events on the library's stream, max over ranks.
+          larger than the 126 MB L2), CUDA events on the library's stream, max over ranks; the window of exactly
+          K steps is repeated WINDOWS times and the MEDIAN window is reported (`windows.ms` lists all of them).
   e2e     same metric through the public API with HOST (pinned) inputs: the H2D copy of both
           images and the D2H read of the four losses are inside the timed region every step.
   roofline  dominant kernel family = tcgen05 forward/dgrad implicit-GEMM convolutions, timed live
           with CUDA events around every launch (separate profiled pass over the same steps);
-          achieved = algorithmic FLOPs / duration against the measured sustained bf16 peak.
+          achieved = algorithmic FLOPs of the UNPADDED layers / duration; `frac` is against the measured BURST bf16
+          peak (a kernel timed alone), `frac_sustained` against the sustained one; `traffic` from
+          profiles/r02_traffic.json (one ncu --set full capture of the dominant kernel) when present.
   cpu_baseline  the oracle's torch-CPU fp32 restatement of the same train step on the host cores
-          (TensorFlow, which the reference needs, is not installable here), bounded sample.
+          (TensorFlow, which the reference needs, is not installable here), bounded sample: CPU_SAMPLE_BATCH images,
+          the SAME sample definition as --impl reference.
 """
 import argparse
 import json

@@ -70,40 +70,51 @@ __device__ __forceinline__ uint32_t idesc_f16(int M, int N, int ab_bf16) {
 }
 
 constexpr int FT_W = 16, FT_H = 8;                 // output tile: 8 rows x 16 columns = 128 pixels = the MMA's M
-constexpr int PATCH_H = 2 * FT_H + 2, PATCH_W = 2 * FT_W + 2;      // 18 x 34 input pixels
-constexpr int FIRST_THREADS = 288;                 // 2 groups x 4 warps + MMA warp
+constexpr int PATCH_H = 2 * FT_H + 2;              // 18 input rows
+constexpr int PATCH_LEFT = 4;                      // the staged row starts 4 pixels left of the tile's first input column - 1 ... see below
+constexpr int PATCH_PIX = 37;                      // pixels 2*ow0-4 .. 2*ow0+32 (the 34 needed + 3 to the left for 16-byte alignment)
 
 struct alignas(64) FirstFwdParams {
   CUtensorMap bmap;                  // packed weights [64][nsrc*64], K-major
-  const float* src[2];               // fp32 NHWC images (B, H, W, C)
+  const float* src[2];               // fp32 NHWC images (B, H, W, C), 16-byte aligned
   int nsrc, C, B, H, W;              // H, W: input size; output grid H/2 x W/2
   bf16* a; int a_pitch, a_coff;      // LeakyReLU(z) into the consumer view (16-bit)
   int tiles_w, tiles_h, num_tiles;
   int ab_bf16, out_f16;
 };
 
-constexpr int PATCH_PITCH = PATCH_W * 8;                            // bytes per patch row: 34 pixels x 4 slots x 16 bit
-constexpr int PATCH_BYTES = ((PATCH_H * PATCH_PITCH + 127) / 128) * 128;
+__host__ __device__ constexpr int first_row_chunks(int C) { return (PATCH_PIX * 4 * C + 15) / 16; }      // 16-byte chunks per staged row
+__host__ __device__ constexpr int first_stage_bytes(int C) { return ((PATCH_H * first_row_chunks(C) * 16 + 127) / 128) * 128; }
+__host__ __device__ constexpr int first_threads(int NG) { return NG * 128 + 32; }
+__host__ __device__ constexpr int first_tmem_cols(int NG) { return NG <= 2 ? 128 : 256; }
 
-template <int NSRC>
-__global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_constant__ FirstFwdParams p) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// NSRC source images of C channels each, NG gather/epilogue groups of 4 warps (+ one MMA warp)
+template <int NSRC, int C, int NG>
+__global__ void __launch_bounds__(first_threads(NG)) k_conv_first_fwd(const __grid_constant__ FirstFwdParams p) {
   constexpr uint32_t A_BYTES = 128 * 128;                         // one source: 128 rows x 64 x 16 bit
   constexpr uint32_t GROUP_A = NSRC * A_BYTES;
+  constexpr int CH = first_row_chunks(C), ROW_BYTES = CH * 16, STAGE_SRC = first_stage_bytes(C);
+  constexpr int STAGE = NSRC * STAGE_SRC;                         // one tile's raw fp32 input rows
+  constexpr int MMA_WARP = NG * 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* atile = smem;                                          // [2 groups][NSRC][128][128 B]
-  uint8_t* wsm = smem + 2 * GROUP_A;                              // [NSRC][64 rows][128 B]
-  uint8_t* patch = wsm + NSRC * 64 * 128;                         // [2 groups][NSRC][18][34][4 slots] 16-bit
-  uint64_t* bars = (uint64_t*)(patch + 2 * NSRC * PATCH_BYTES);   // full[2], done[2], wbar
-  uint32_t* tmem_slot = (uint32_t*)(bars + 5);
+  uint8_t* atile = smem;                                          // [NG groups][NSRC][128][128 B]
+  uint8_t* wsm = smem + NG * GROUP_A;                             // [NSRC][64 rows][128 B]
+  uint8_t* stage = wsm + NSRC * 64 * 128;                         // [NG groups][2 stages][NSRC][18 rows][ROW_BYTES] fp32
+  uint64_t* bars = (uint64_t*)(stage + NG * 2 * STAGE);           // full[NG], done[NG], wbar
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NG + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
+    for (int i = 0; i < 2 * NG + 1; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)first_tmem_cols(NG)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -112,20 +123,20 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const int Ho = p.H / 2, Wo = p.W / 2;
 
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     // ---- MMA issuer: stationary weights, then one k-block (NSRC x 4 MMAs) per tile ----
     if (lane == 0) {
-      mbar_expect_tx(&bars[4], NSRC * 64 * 128);
-      for (int s = 0; s < NSRC; ++s) tma_load_2d(wsm + s * 64 * 128, &p.bmap, &bars[4], s * 64, 0);
+      mbar_expect_tx(&bars[2 * NG], NSRC * 64 * 128);
+      for (int s = 0; s < NSRC; ++s) tma_load_2d(wsm + s * 64 * 128, &p.bmap, &bars[2 * NG], s * 64, 0);
     }
-    mbar_wait(&bars[4], 0);
+    mbar_wait(&bars[2 * NG], 0);
     const uint32_t idesc = idesc_f16(128, 64, p.ab_bf16);
-    uint32_t n[2] = {0, 0};
-    for (int t = blockIdx.x * 2; t < p.num_tiles; t += gridDim.x * 2) {
+    uint32_t n = 0;
+    for (int t = blockIdx.x * NG; t < p.num_tiles; t += gridDim.x * NG, ++n) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < NG; ++g) {
         if (t + g >= p.num_tiles) break;
-        mbar_wait(&bars[g], n[g] & 1);                              // the group has built its A tile
+        mbar_wait(&bars[g], n & 1);                                 // the group has built its A tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t sa = smem_u32(atile + g * GROUP_A), sb = smem_u32(wsm);
@@ -138,76 +149,81 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
               asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
                            ::"r"(tmem_base + g * 64), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
             }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 + g])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[NG + g])) : "memory");
         }
         __syncwarp();
-        ++n[g];
       }
     }
   } else {
     // ---- gather / epilogue groups ----
-    const int g = warp >> 2;                       // group 0: warps 0..3, group 1: warps 4..7
+    const int g = warp >> 2;                       // group of this warp
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
     const int pl = (threadIdx.x & 127);            // output pixel inside the tile == accumulator row
     const int olh = pl / FT_W, olw = pl % FT_W;
-    uint8_t* my_patch = patch + g * NSRC * PATCH_BYTES;
+    uint8_t* my_stage = stage + g * 2 * STAGE;
     uint8_t* my_a = atile + g * GROUP_A;
     const int bar_id = 1 + g;                      // named barrier of the group (128 threads)
+    const int row_end = p.W * 4 * C;               // bytes of one image row
+
+    // raw fp32 rows of tile t -> stage buffer `buf`, 16 bytes per cp.async: the staged row starts at input column
+    // 2*ow0 - 4 (byte offset 24*ow0 - 48 for C = 3: 16-byte aligned because ow0 is a multiple of 16), three pixels
+    // left of the first column the tile needs (2*ow0 - 1).  A chunk lies wholly inside or wholly outside the image row
+    // (W*4*C is a multiple of 16); outside chunks and rows are zero-filled (src-size 0) = the 'same' padding.
+    auto prefetch = [&](int t, int buf) {
+      int tt = t;
+      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
+      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
+      const int ih0 = 2 * th * FT_H - 1;
+      const int x0 = (2 * tw * FT_W - PATCH_LEFT) * 4 * C;       // byte offset of the staged row inside the image row
+#pragma unroll
+      for (int s = 0; s < NSRC; ++s) {
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.src[s]) + (size_t)b * p.H * row_end;
+        const uint32_t dst0 = smem_u32(my_stage + buf * STAGE + s * STAGE_SRC);
+        for (int i = pl; i < PATCH_H * CH; i += 128) {
+          const int r = i / CH, ch = i - r * CH;
+          const int ih = ih0 + r, x = x0 + ch * 16;
+          const bool ok = ih >= 0 && ih < p.H && x >= 0 && x < row_end;
+          cp_async16(dst0 + r * ROW_BYTES + ch * 16, ok ? img + (size_t)ih * row_end + x : img, ok ? 16u : 0u);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int t = blockIdx.x * NG + g;
+    if (t < p.num_tiles) prefetch(t, 0);
     uint32_t n = 0;
-    for (int t = blockIdx.x * 2 + g; t < p.num_tiles; t += gridDim.x * 2, ++n) {
+    for (; t < p.num_tiles; t += gridDim.x * NG, ++n) {
       int tt = t;
       const int tw = tt % p.tiles_w; tt /= p.tiles_w;
       const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
       const int oh0 = th * FT_H, ow0 = tw * FT_W;
-      const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-      // 1. input patch -> shared memory as 16-bit pixels of 4 channel slots (8 bytes; zero outside the image = 'same'
-      //    padding).  All of a thread's loads (up to 5 pixels x C channels x NSRC images) are issued before the first
-      //    store, so one DRAM round trip covers the whole patch.
-      constexpr int NPX = (PATCH_H * PATCH_W + 127) / 128;
-      float4 pv[NSRC][NPX];
-#pragma unroll
-      for (int s = 0; s < NSRC; ++s) {
-        const float* img = p.src[s] + (size_t)b * p.H * p.W * p.C;
-#pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-          const int i = pl + j * 128;
-          const int r = i / PATCH_W, c = i - r * PATCH_W;
-          const int ih = ih0 + r, iw = iw0 + c;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < PATCH_H * PATCH_W && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
-            const float* px = img + ((size_t)ih * p.W + iw) * p.C;
-            v.x = __ldg(px);
-            if (p.C > 1) v.y = __ldg(px + 1);
-            if (p.C > 2) v.z = __ldg(px + 2);
-            if (p.C > 3) v.w = __ldg(px + 3);
-          }
-          pv[s][j] = v;
-        }
+      // 1. the next tile's rows start their trip from HBM now and land while this tile is assembled, multiplied and
+      //    written out; then wait for this tile's rows (issued one iteration ago)
+      const int tnext = t + gridDim.x * NG;
+      if (tnext < p.num_tiles) {
+        prefetch(tnext, (n + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
-#pragma unroll
-      for (int s = 0; s < NSRC; ++s)
-#pragma unroll
-        for (int j = 0; j < NPX; ++j) {
-          const int i = pl + j * 128;
-          if (i < PATCH_H * PATCH_W) {
-            uint2 o;
-            if (p.ab_bf16) { o.x = pack2<bf16>(pv[s][j].x, pv[s][j].y); o.y = pack2<bf16>(pv[s][j].z, pv[s][j].w); }
-            else { o.x = pack2<f16>(pv[s][j].x, pv[s][j].y); o.y = pack2<f16>(pv[s][j].z, pv[s][j].w); }
-            *reinterpret_cast<uint2*>(my_patch + s * PATCH_BYTES + i * 8) = o;
-          }
-        }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      // 2. this thread's row: chunk j = taps (kh, kw0), (kh, kw0+1) = two ADJACENT patch pixels = 16 contiguous, 16-byte
-      //    aligned bytes of the patch (kw0 is even), copied to chunk (j ^ (row & 7)) of the row (SWIZZLE_128B)
+      // 2. this thread's row: chunk j = taps (kh, kw0), (kh, kw0+1) = two adjacent input pixels = 2*C consecutive
+      //    floats of the staged row -> 2 x 4 channel slots of 16 bit -> chunk (j ^ (row & 7)) of the row (SWIZZLE_128B)
 #pragma unroll
       for (int s = 0; s < NSRC; ++s) {
-        const uint8_t* ps = my_patch + s * PATCH_BYTES;
+        const uint8_t* ps = my_stage + (n & 1) * STAGE + s * STAGE_SRC;
         uint8_t* row = my_a + s * A_BYTES + pl * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int kh = j >> 1, kw0 = (j & 1) * 2;
-          const uint4 v = *reinterpret_cast<const uint4*>(ps + (2 * olh + kh) * PATCH_PITCH + (2 * olw + kw0) * 8);
-          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = v;
+          const float* f = reinterpret_cast<const float*>(ps + (2 * olh + kh) * ROW_BYTES + (2 * olw + kw0 + PATCH_LEFT - 1) * 4 * C);
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < C; ++e) { v[e] = f[e]; v[4 + e] = f[C + e]; }
+          uint4 o;
+          if (p.ab_bf16) { o.x = pack2<bf16>(v[0], v[1]); o.y = pack2<bf16>(v[2], v[3]); o.z = pack2<bf16>(v[4], v[5]); o.w = pack2<bf16>(v[6], v[7]); }
+          else { o.x = pack2<f16>(v[0], v[1]); o.y = pack2<f16>(v[2], v[3]); o.z = pack2<f16>(v[4], v[5]); o.w = pack2<f16>(v[6], v[7]); }
+          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = o;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
       //    row touches 32 lines = 32 LSU wavefronts (measured: that alone bounded the first version at 182 us per
       //    launch), so the tile is transposed through the group's A buffer (free once the MMA has committed;
       //    XOR-swizzled 16-byte chunks, conflict-free both ways) and written with 8 lanes per 128-byte row.
-      mbar_wait(&bars[2 + g], n & 1);
+      mbar_wait(&bars[NG + g], n & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + g * 64 + ((uint32_t)(q * 32) << 16);
       uint4* ast = reinterpret_cast<uint4*>(my_a);                       // [128 rows][8 chunks] (16 KB)
@@ -248,24 +264,213 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_conv_first_fwd(const __grid_c
         const size_t pix = ((size_t)b * Ho + oh) * Wo + ow;
         *reinterpret_cast<uint4*>(p.a + pix * p.a_pitch + p.a_coff + ch * 8) = ast[r * 8 + (ch ^ (r & 7))];
       }
-      // the group's patch / A tile / TMEM columns are free again once all 128 threads are here
+      // the group's stage / A tile / TMEM columns are free again once all 128 threads are here
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)first_tmem_cols(NG)) : "memory");
 }
 
-size_t first_smem_bytes(int nsrc) {
-  return (size_t)2 * nsrc * 128 * 128 + (size_t)nsrc * 64 * 128 + (size_t)2 * nsrc * PATCH_BYTES + 64 + 16 + 1024;
+size_t first_smem_bytes(int nsrc, int C, int ng) {
+  return (size_t)ng * nsrc * 128 * 128 + (size_t)nsrc * 64 * 128 + (size_t)ng * 2 * nsrc * first_stage_bytes(C) + 8 * (2 * ng + 1) + 16 + 1024;
+}
+
+// =============================================================================================
+// weight gradient of the first layers.  D[128 = (source, tap*4+slot)][64 filters] += A^T . dz over the tile's 128 pixels:
+// A = the same shared-memory rows as the forward kernel, read as the MN-major operand (M = the 64 k-values of a pixel
+// row are contiguous, GEMM-K = pixels; both sources side by side = M 128; with one source the upper 64 rows read a
+// zeroed buffer), B = the dz tile [128 pixels][64] brought by TMA, also MN-major.  ONE accumulator per CTA collects
+// every tile the CTA processes (fixed order); the 128 x 64 fp32 partial goes to a slab, k_wgrad_reduce sums the CTAs.
+// =============================================================================================
+struct alignas(64) FirstWgradParams {
+  CUtensorMap dmap;                  // dz (B, Ho, Wo, 64): boxes 64 ch x 16 x 8 x 1, SWIZZLE_128B
+  const float* src[2];
+  int nsrc, C, B, H, W;
+  int tiles_w, tiles_h, num_tiles;
+  int ab_bf16;
+  float* slab;                       // [gridDim.x][128][64]
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// MN-major SWIZZLE_128B descriptor (conv_umma.cu): 128 bytes of MN per k-row, 8 k-rows per atom (SBO = 1024),
+// LBO = byte distance between consecutive 64-element MN blocks
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+template <int NSRC, int C, int NG>
+__global__ void __launch_bounds__(first_threads(NG)) k_conv_first_wgrad(const __grid_constant__ FirstWgradParams p) {
+  constexpr uint32_t A_BYTES = 128 * 128;
+  constexpr uint32_t GROUP_A = NSRC * A_BYTES;
+  constexpr int CH = first_row_chunks(C), ROW_BYTES = CH * 16, STAGE_SRC = first_stage_bytes(C);
+  constexpr int STAGE = NSRC * STAGE_SRC;
+  constexpr int MMA_WARP = NG * 4;
+  constexpr int ZBUF = NSRC == 1 ? 1 : 0;                        // one source: 16 KB of zeros stand in for the second
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* atile = smem;                                          // [NG][NSRC][128 pixels][128 B]
+  uint8_t* zero = atile + NG * GROUP_A;                           // [ZBUF][16 KB]
+  uint8_t* btile = zero + ZBUF * A_BYTES;                        // [NG][128 pixels][128 B] dz
+  uint8_t* stage = btile + NG * A_BYTES;                          // [NG][2][NSRC][18 rows][ROW_BYTES] fp32
+  uint64_t* bars = (uint64_t*)(stage + NG * 2 * STAGE);           // full[NG], dzfull[NG], done[NG], accfull
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NG + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3 * NG + 1; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (ZBUF) {
+    for (int i = threadIdx.x; i < (int)(A_BYTES / 16); i += first_threads(NG)) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == MMA_WARP) {
+    // M = 128 (k-values of both sources), N = 64 (filters), both operands MN-major
+    const uint32_t idesc = idesc_f16(128, 64, p.ab_bf16) | (1u << 15) | (1u << 16);
+    uint32_t n = 0;
+    bool first = true;
+    for (int t = blockIdx.x * NG; t < p.num_tiles; t += gridDim.x * NG, ++n) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (t + g >= p.num_tiles) break;
+        mbar_wait(&bars[g], n & 1);                                 // rows built
+        mbar_wait(&bars[NG + g], n & 1);                            // dz tile landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(atile + g * GROUP_A), sb = smem_u32(btile + g * A_BYTES);
+          const uint32_t lbo = NSRC == 2 ? A_BYTES : (uint32_t)(NG - g) * A_BYTES;     // second M block: source 1, or the zeros
+          const uint64_t ad = desc_mn128(sa, lbo), bd = desc_mn128(sb, A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {                             // 16 pixels (two 8-row atoms) per MMA
+            const uint32_t acc = !(first && k == 0);
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
+                         ::"r"(tmem_base), "l"(ad + (uint64_t)(k * 128)), "l"(bd + (uint64_t)(k * 128)), "r"(idesc), "r"(acc) : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 * NG + g])) : "memory");
+        }
+        __syncwarp();
+        first = false;
+      }
+    }
+    if (elect_one())
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[3 * NG])) : "memory");
+    __syncwarp();
+  } else {
+    const int g = warp >> 2, q = warp & 3;
+    const int pl = (threadIdx.x & 127);
+    const int olh = pl / FT_W, olw = pl % FT_W;
+    uint8_t* my_stage = stage + g * 2 * STAGE;
+    uint8_t* my_a = atile + g * GROUP_A;
+    uint8_t* my_b = btile + g * A_BYTES;
+    const int bar_id = 1 + g;
+    const int row_end = p.W * 4 * C;
+
+    auto prefetch = [&](int t, int buf) {          // as in k_conv_first_fwd
+      int tt = t;
+      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
+      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
+      const int ih0 = 2 * th * FT_H - 1;
+      const int x0 = (2 * tw * FT_W - PATCH_LEFT) * 4 * C;
+#pragma unroll
+      for (int s = 0; s < NSRC; ++s) {
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.src[s]) + (size_t)b * p.H * row_end;
+        const uint32_t dst0 = smem_u32(my_stage + buf * STAGE + s * STAGE_SRC);
+        for (int i = pl; i < PATCH_H * CH; i += 128) {
+          const int r = i / CH, ch = i - r * CH;
+          const int ih = ih0 + r, x = x0 + ch * 16;
+          const bool ok = ih >= 0 && ih < p.H && x >= 0 && x < row_end;
+          cp_async16(dst0 + r * ROW_BYTES + ch * 16, ok ? img + (size_t)ih * row_end + x : img, ok ? 16u : 0u);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int t = blockIdx.x * NG + g;
+    if (t < p.num_tiles) prefetch(t, 0);
+    uint32_t n = 0;
+    for (; t < p.num_tiles; t += gridDim.x * NG, ++n) {
+      int tt = t;
+      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
+      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
+      const int tnext = t + gridDim.x * NG;
+      if (tnext < p.num_tiles) {
+        prefetch(tnext, (n + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      if (n > 0) mbar_wait(&bars[2 * NG + g], (n - 1) & 1);         // the previous tile's MMAs have read the rows and dz
+      if (pl == 0) {
+        mbar_expect_tx(&bars[NG + g], A_BYTES);
+        tma_load_4d(my_b, &p.dmap, &bars[NG + g], 0, tw * FT_W, th * FT_H, b);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+      for (int s = 0; s < NSRC; ++s) {
+        const uint8_t* ps = my_stage + (n & 1) * STAGE + s * STAGE_SRC;
+        uint8_t* row = my_a + s * A_BYTES + pl * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kh = j >> 1, kw0 = (j & 1) * 2;
+          const float* f = reinterpret_cast<const float*>(ps + (2 * olh + kh) * ROW_BYTES + (2 * olw + kw0 + PATCH_LEFT - 1) * 4 * C);
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < C; ++e) { v[e] = f[e]; v[4 + e] = f[C + e]; }
+          uint4 o;
+          if (p.ab_bf16) { o.x = pack2<bf16>(v[0], v[1]); o.y = pack2<bf16>(v[2], v[3]); o.z = pack2<bf16>(v[4], v[5]); o.w = pack2<bf16>(v[6], v[7]); }
+          else { o.x = pack2<f16>(v[0], v[1]); o.y = pack2<f16>(v[2], v[3]); o.z = pack2<f16>(v[4], v[5]); o.w = pack2<f16>(v[6], v[7]); }
+          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = o;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (pl == 0) mbar_arrive(&bars[g]);
+    }
+    if (g == 0) {
+      // the CTA's partial tile -> slab (once per CTA: 32 KB)
+      mbar_wait(&bars[3 * NG], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int r = q * 32 + lane;
+      float* sl = p.slab + ((size_t)blockIdx.x * 128 + r) * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(sl + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+}
+
+size_t first_wgrad_smem_bytes(int nsrc, int C, int ng) {
+  return (size_t)ng * nsrc * 128 * 128 + (nsrc == 1 ? 128 * 128 : 0) + (size_t)ng * 128 * 128 + (size_t)ng * 2 * nsrc * first_stage_bytes(C) +
+         8 * (3 * ng + 1) + 16 + 1024;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled g_encode = nullptr;
-bool g_first_on = true;
+bool g_first_on = true, g_first_wgrad_on = true;
 
 }  // namespace
 
@@ -278,14 +483,23 @@ void first_init() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     g_encode = (PFN_encodeTiled)fn;
   else cudaGetLastError();
-  cudaFuncSetAttribute(k_conv_first_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(1));
-  cudaFuncSetAttribute(k_conv_first_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(2));
+  cudaFuncSetAttribute(k_conv_first_fwd<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(1, 1, 2));
+  cudaFuncSetAttribute(k_conv_first_fwd<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(1, 3, 2));
+  cudaFuncSetAttribute(k_conv_first_fwd<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(2, 1, 3));
+  cudaFuncSetAttribute(k_conv_first_fwd<2, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(2, 3, 3));
+  cudaFuncSetAttribute(k_conv_first_wgrad<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(1, 1, 2));
+  cudaFuncSetAttribute(k_conv_first_wgrad<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(1, 3, 2));
+  cudaFuncSetAttribute(k_conv_first_wgrad<2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(2, 1, 2));
+  cudaFuncSetAttribute(k_conv_first_wgrad<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(2, 3, 2));
   const char* e = getenv("GAN_B200_FIRST");          // dev A/B switch: 0 = im2col rows in HBM (round 1)
   g_first_on = !(e && e[0] == '0');
+  g_first_wgrad_on = !(e && e[0] == '1');            // 1 = forward kernel only (weight gradient on im2col rows)
 }
 
 bool first_fwd_supported(const FirstLayerOp& op) {
-  return g_first_on && g_encode != nullptr && op.nsrc >= 1 && op.nsrc <= 2 && op.C >= 1 && op.C <= 4 && op.H % (2 * FT_H) == 0 &&
+  for (int s = 0; s < op.nsrc && s < 2; ++s)
+    if (((uintptr_t)op.src[s] & 15) != 0) return false;           // 16-byte cp.async from the image rows
+  return g_first_on && g_encode != nullptr && op.nsrc >= 1 && op.nsrc <= 2 && (op.C == 1 || op.C == 3) && op.H % (2 * FT_H) == 0 &&
          op.W % (2 * FT_W) == 0 && op.a_pitch % 8 == 0 && op.a_coff % 8 == 0 && (op.dt == DT_F16 || op.dt == DT_BF16);
 }
 
@@ -301,10 +515,54 @@ void launch_conv_first_fwd(Launch L, const FirstLayerOp& op) {
   P.a = (bf16*)op.a; P.a_pitch = op.a_pitch; P.a_coff = op.a_coff;
   P.tiles_w = (op.W / 2) / FT_W; P.tiles_h = (op.H / 2) / FT_H; P.num_tiles = P.tiles_w * P.tiles_h * op.B;
   P.ab_bf16 = op.dt == DT_F16 ? 0 : 1; P.out_f16 = op.dt == DT_F16 ? 1 : 0;
-  const int per_sm = 2;                                          // registers (106-118 x 288 threads) allow two CTAs; shared memory 52 / 102 KB
-  int grid = (P.num_tiles + 1) / 2;
+  // one source: 2 groups, 72 KB of shared memory -> two CTAs per SM; two sources: 3 groups, 209 KB -> one CTA per SM
+  const int ng = op.nsrc == 1 ? 2 : 3, per_sm = op.nsrc == 1 ? 2 : 1;
+  int grid = (P.num_tiles + ng - 1) / ng;
   if (grid > 148 * per_sm) grid = 148 * per_sm;
-  if (op.nsrc == 1) k_conv_first_fwd<1><<<grid, FIRST_THREADS, first_smem_bytes(1), L.s>>>(P);
-  else k_conv_first_fwd<2><<<grid, FIRST_THREADS, first_smem_bytes(2), L.s>>>(P);
+  const size_t sm = first_smem_bytes(op.nsrc, op.C, ng);
+  if (op.nsrc == 1 && op.C == 1) k_conv_first_fwd<1, 1, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  else if (op.nsrc == 1) k_conv_first_fwd<1, 3, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  else if (op.C == 1) k_conv_first_fwd<2, 1, 3><<<grid, first_threads(3), sm, L.s>>>(P);
+  else k_conv_first_fwd<2, 3, 3><<<grid, first_threads(3), sm, L.s>>>(P);
   KLAUNCH(L);
+}
+
+bool first_wgrad_supported(const FirstWgradOp& op) {
+  for (int s = 0; s < op.nsrc && s < 2; ++s)
+    if (((uintptr_t)op.src[s] & 15) != 0) return false;
+  return g_first_on && g_first_wgrad_on && g_encode != nullptr && op.nsrc >= 1 && op.nsrc <= 2 && (op.C == 1 || op.C == 3) &&
+         op.H % (2 * FT_H) == 0 && op.W % (2 * FT_W) == 0 && op.dz_pitch % 8 == 0 && op.dz_coff % 8 == 0 &&
+         (op.dt == DT_F16 || op.dt == DT_BF16) && op.ws != nullptr && op.ws_bytes >= (size_t)148 * 2 * 128 * 64 * 4;
+}
+
+void launch_conv_first_wgrad(Launch L, const FirstWgradOp& op) {
+  FirstWgradParams P; memset(&P, 0, sizeof(P));
+  const int Ho = op.H / 2, Wo = op.W / 2;
+  cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)op.B};
+  cuuint64_t strides[3] = {(cuuint64_t)op.dz_pitch * 2, (cuuint64_t)Wo * op.dz_pitch * 2, (cuuint64_t)Ho * Wo * op.dz_pitch * 2};
+  cuuint32_t box[4] = {64, FT_W, FT_H, 1}, es[4] = {1, 1, 1, 1};
+  void* base = (void*)((const uint8_t*)op.dz + (size_t)op.dz_coff * 2);
+  CUresult r = g_encode(&P.dmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(first-layer dz) failed: " + std::to_string((int)r));
+  P.src[0] = op.src[0]; P.src[1] = op.src[1]; P.nsrc = op.nsrc; P.C = op.C; P.B = op.B; P.H = op.H; P.W = op.W;
+  P.tiles_w = Wo / FT_W; P.tiles_h = Ho / FT_H; P.num_tiles = P.tiles_w * P.tiles_h * op.B;
+  P.ab_bf16 = op.dt == DT_F16 ? 0 : 1;
+  P.slab = op.ws;
+  // one source: 113 KB of shared memory -> two CTAs per SM; two sources: 160 KB -> one
+  const int ng = 2, per_sm = op.nsrc == 1 ? 2 : 1;
+  int grid = (P.num_tiles + ng - 1) / ng;
+  if (grid > 148 * per_sm) grid = 148 * per_sm;
+  const size_t sm = first_wgrad_smem_bytes(op.nsrc, op.C, ng);
+  if (op.nsrc == 1 && op.C == 1) k_conv_first_wgrad<1, 1, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  else if (op.nsrc == 1) k_conv_first_wgrad<1, 3, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  else if (op.C == 1) k_conv_first_wgrad<2, 1, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  else k_conv_first_wgrad<2, 3, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  KLAUNCH(L);
+  // CTA partials -> master layout (kh, kw, source*C + c, co), summed in CTA order
+  WgradReduceParams R; memset(&R, 0, sizeof(R));
+  R.slab = op.ws; R.dW = op.dW; R.splits = grid; R.bn = 64; R.mblocks = 1; R.ntiles = 1; R.ncls = 1; R.accumulate = op.accumulate;
+  R.Kc = 64; R.Kr = 64; R.Nr = 64; R.im2col_c = op.C; R.n_slot4_c = 0; R.s_tap = op.s_tap; R.s_k = op.s_k; R.s_n = op.s_n;
+  R.ntaps[0] = op.nsrc; R.widx[0][0] = 0; R.widx[0][1] = 1;
+  launch_wgrad_reduce(L, R, 1);
 }

@@ -1009,13 +1009,6 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_wgrad_umma(const __grid_co
 // Second stage of the deterministic weight-gradient reduction: one block per output tile sums the `splits` slab tiles
 // in a fixed order and scatters the result into the master (TF) weight layout, storing (first contribution of the
 // step) or adding (later contributions: the second discriminator call, CycleGAN's three generator calls).
-struct WgradReduceParams {
-  const float* slab; float* dW;
-  int splits, bn, mblocks, ntiles, ncls, accumulate;
-  int Kc, Kr, Nr, im2col_c, n_slot4_c;
-  long long s_tap, s_k, s_n;
-  int ntaps[4]; int8_t widx[4][16];
-};
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p) {
   // grid = (output tiles) x (bn/8 sub-tiles of 1024 elements): one float4 per thread.  Sub-tiles are row strips
   // (1024/bn rows x bn columns) when the master layout is contiguous along the output channel, column strips
@@ -1062,6 +1055,11 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceParams p)
     }
     if (p.accumulate) atomicAdd(p.dW + off, vals[e]); else p.dW[off] = vals[e];      // single writer per element: deterministic
   }
+}
+
+void launch_wgrad_reduce(Launch L, const WgradReduceParams& R, long long out_tiles) {
+  k_wgrad_reduce<<<(unsigned)(out_tiles * (R.bn / 8)), 256, 0, L.s>>>(R);
+  KLAUNCH(L);
 }
 
 static size_t wg_smem_bytes(int BN) {
@@ -1146,8 +1144,7 @@ void launch_conv_wgrad_umma(Launch L, const ConvOp& op) {
     R.accumulate = op.accumulate; R.Kc = op.Kc; R.Kr = op.Kr; R.Nr = op.Nr; R.im2col_c = P.im2col_c; R.n_slot4_c = op.n_slot4_c;
     R.s_tap = op.s_tap; R.s_k = op.s_k; R.s_n = op.s_n;
     for (int c = 0; c < op.ncls; ++c) { R.ntaps[c] = op.cls[c].ntaps; for (int t = 0; t < op.cls[c].ntaps; ++t) R.widx[c][t] = op.cls[c].widx[t]; }
-    k_wgrad_reduce<<<(unsigned)(ctas * (bn_slab / 8)), 256, 0, L.s>>>(R);
-    KLAUNCH(L);
+    launch_wgrad_reduce(L, R, ctas);
   }
 }
 

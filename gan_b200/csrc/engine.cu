@@ -526,7 +526,24 @@ static void layer_backward(gan_net* n, Slot& s, int li, GradSrc d1, GradSrc d2, 
                     ctx->sc().stats_ws.as<float>(), st ? st + 4 * gc : nullptr, st ? st + 5 * gc : nullptr, dgamma, dbeta, dz.p,
                     tickets(ctx), from_act ? av.pitch : 0, from_act ? av.coff : 0);
   }
-  if (want_wgrad) {
+  bool first_wgrad_done = false;
+  if (want_wgrad && li == 0 && s.used_im2col && first_kernel_ok(ctx, ly, s, in.H, in.W)) {
+    // first layer: the rows are rebuilt in shared memory from the fp32 image(s) (conv_first.cu), no im2col rows in HBM
+    FirstWgradOp fw; memset(&fw, 0, sizeof(fw));
+    fw.src[0] = s.src_f32[0]; fw.src[1] = s.src_f32[1]; fw.nsrc = ly.nsrc; fw.C = ly.src_c; fw.B = B; fw.H = in.H; fw.W = in.W;
+    fw.dz = dz.p; fw.dz_pitch = dz.pitch; fw.dz_coff = dz.coff; fw.dt = ctx->dtG;
+    fw.dW = n->grads.as<float>() + ly.w_off; fw.s_tap = (long long)ly.Cin * ly.Cout; fw.s_k = ly.Cout; fw.s_n = 1;
+    ctx->sc().wgrad_ws.ensure((size_t)24 << 20);
+    fw.ws = ctx->sc().wgrad_ws.as<float>(); fw.ws_bytes = ctx->sc().wgrad_ws.bytes;
+    if (ctx->dtG == ctx->dtA && first_wgrad_supported(fw)) {
+      fw.accumulate = ly.wgrad_epoch == ctx->step_epoch ? 1 : 0;
+      ly.wgrad_epoch = ctx->step_epoch;
+      ProfScope ps(ctx, FAM_UMMA_WGRAD, 2.0 * (double)P * 16.0 * ly.Cin * ly.Cout);
+      launch_conv_first_wgrad(ctx->L(), fw);
+      first_wgrad_done = true;
+    }
+  }
+  if (want_wgrad && !first_wgrad_done) {
     if (li == 0 && s.used_im2col) {       // rows of the input image(s) for the weight-gradient GEMM (cached per image and step)
       for (int k = 0; k < ly.nsrc; ++k)
         if (s.src_f32[k] != nullptr) s.im2col[k] = cached_im2col(ctx, s.src_f32[k], B, in.H, in.W, ly.src_c);

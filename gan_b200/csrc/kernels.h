@@ -127,6 +127,27 @@ struct FirstLayerOp {
 void first_init();
 bool first_fwd_supported(const FirstLayerOp& op);
 void launch_conv_first_fwd(Launch L, const FirstLayerOp& op);
+// ... and their weight gradient dW[(kh,kw), source*C + c, co] = sum over output pixels of row[k] * dz[co]: the same rows
+// rebuilt in shared memory as the MN-major operand (GEMM-K = pixels), dz tiles by TMA, one fp32 partial tile per CTA
+// reduced in CTA order by k_wgrad_reduce (deterministic); no im2col rows in HBM at all.
+struct FirstWgradOp {
+  const float* src[2]; int nsrc, C, B, H, W;
+  const void* dz; int dz_pitch, dz_coff; int dt;               // (B, H/2, W/2, 64) 16-bit
+  float* dW; long long s_tap, s_k, s_n; int accumulate;
+  float* ws; size_t ws_bytes;                                  // partial-tile workspace
+};
+bool first_wgrad_supported(const FirstWgradOp& op);
+void launch_conv_first_wgrad(Launch L, const FirstWgradOp& op);
+
+// second stage of the deterministic weight-gradient reduction (conv_umma.cu)
+struct WgradReduceParams {
+  const float* slab; float* dW;
+  int splits, bn, mblocks, ntiles, ncls, accumulate;
+  int Kc, Kr, Nr, im2col_c, n_slot4_c;
+  long long s_tap, s_k, s_n;
+  int ntaps[4]; int8_t widx[4][16];
+};
+void launch_wgrad_reduce(Launch L, const WgradReduceParams& R, long long out_tiles);
 
 // on-device input pipeline: gan_image_xform (include/gan_b200.h) plus the float32 resize scales in/out of
 // each stage, divided once per image on the host
