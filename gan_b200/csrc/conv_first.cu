@@ -5,9 +5,10 @@
 // 128-byte row k = tap*4 + channel slot (64 x 16 bit, slots >= C zero).  Round 1 materialised those rows in HBM
 // (134 MB per image batch at 64 x 256^2, written by k_im2col, read by the GEMM) and then ran a separate activation pass
 // over z.  Here a CTA builds the rows in SHARED memory, directly in the SWIZZLE_128B K-major layout the MMA reads:
-//   * a group of 4 warps owns one 8 x 16 tile of output pixels: it pulls the 18 x 34 input patch (fp32, coalesced)
-//     into shared memory, every thread assembles the row of its output pixel (16 taps x 4 slots -> eight swizzled
-//     16-byte stores), fences the async proxy and signals the MMA warp;
+//   * a group of 4 warps owns one 8 x 16 tile of output pixels: its 18 x 34 fp32 input patch arrives by ONE TMA load
+//     per source image (out-of-bounds = zero = 'same' padding) through a ring of 2-3 stages per group, so the next
+//     tiles are in flight while this one is processed; every thread assembles the row of its output pixel (16 taps x
+//     4 slots -> eight swizzled 16-byte stores), fences the async proxy and signals the MMA warp;
 //   * warp 8 issues 4 (x sources) tcgen05.mma M=128 x N=64 x K=16 against the stationary weight tile (one TMA load per
 //     CTA) into the group's TMEM columns and commits to the group's barrier;
 //   * the same 4 warps drain TMEM: a = LeakyReLU(z) goes through shared memory into the consumer view (skip-concat
@@ -71,47 +72,99 @@ __device__ __forceinline__ uint32_t idesc_f16(int M, int N, int ab_bf16) {
 
 constexpr int FT_W = 16, FT_H = 8;                 // output tile: 8 rows x 16 columns = 128 pixels = the MMA's M
 constexpr int PATCH_H = 2 * FT_H + 2;              // 18 input rows
-constexpr int PATCH_LEFT = 4;                      // the staged row starts 4 pixels left of the tile's first input column - 1 ... see below
-constexpr int PATCH_PIX = 37;                      // pixels 2*ow0-4 .. 2*ow0+32 (the 34 needed + 3 to the left for 16-byte alignment)
+constexpr int PATCH_W = 2 * FT_W + 2;              // 34 input columns, first = 2*ow0 - 1
+constexpr int PATCH_LEFT = 3;                      // the staged row starts 3 pixels further left, at column 2*ow0 - 4
+
+// One tile's input: a (37*C rounded up to 4 floats) x 18 box of the fp32 image, fetched by ONE TMA load per source
+// (3-D map (W*C, H, B); the box may start at column -4 / row -1 and overhang the right / bottom edge: out-of-bounds
+// elements arrive as zeros = the 'same' padding, rows of the neighbouring image are never touched).  The box starts
+// at column 2*ow0 - 4 rather than 2*ow0 - 1 because the innermost TMA coordinate has to land on a 16-byte boundary
+// ((2*ow0 - 4) * C floats is a multiple of 4 for every C; probed on the device: a box starting at -3 floats raises an
+// illegal-instruction fault).
+__host__ __device__ constexpr int first_row_floats(int C) { return (((PATCH_W + PATCH_LEFT) * C + 3) / 4) * 4; }    // 112 (C=3), 40 (C=1)
+__host__ __device__ constexpr int first_box_bytes(int C) { return PATCH_H * first_row_floats(C) * 4; }
+__host__ __device__ constexpr int first_stage_bytes(int C) { return ((first_box_bytes(C) + 127) / 128) * 128; }
+__host__ __device__ constexpr int first_threads(int NG) { return NG * 128 + 32; }
+__host__ __device__ constexpr int first_tmem_cols(int NG) { return NG <= 2 ? 128 : 256; }
+
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+struct TileCoord { int b, oh0, ow0; };
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_w, int tiles_h) {
+  TileCoord c;
+  const int tw = t % tiles_w; t /= tiles_w;
+  c.ow0 = tw * FT_W; c.oh0 = (t % tiles_h) * FT_H; c.b = t / tiles_h;
+  return c;
+}
+
+// The 128-byte operand row of output pixel `pl` from the staged fp32 box: chunk j = taps (kh, kw0), (kh, kw0+1) = two
+// adjacent input pixels = 2*C consecutive floats -> 2 x 4 channel slots of 16 bit -> 16-byte chunk (j ^ (row & 7)) of the
+// row (SWIZZLE_128B, the layout the MMA descriptor reads).  The floats start at an odd word (column offset 3), so C = 3
+// reads them as 32 + 64 + 64 + 32 bits.
+template <int C>
+__device__ __forceinline__ void build_row(const uint8_t* stage_src, uint8_t* row, int pl, int ab_bf16) {
+  constexpr int ROWF = first_row_floats(C);
+  const int olh = pl / FT_W, olw = pl % FT_W;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kh = j >> 1, kw0 = (j & 1) * 2;
+    const float* f = reinterpret_cast<const float*>(stage_src) + (2 * olh + kh) * ROWF + (2 * olw + kw0 + PATCH_LEFT) * C;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (C == 1) { v[0] = f[0]; v[4] = f[1]; }
+    else {
+      const float a = f[0]; const float2 b = *reinterpret_cast<const float2*>(f + 1), c = *reinterpret_cast<const float2*>(f + 3);
+      const float d = f[5];
+      v[0] = a; v[1] = b.x; v[2] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d;
+    }
+    uint4 o;
+    if (ab_bf16) { o.x = pack2<bf16>(v[0], v[1]); o.y = pack2<bf16>(v[2], v[3]); o.z = pack2<bf16>(v[4], v[5]); o.w = pack2<bf16>(v[6], v[7]); }
+    else { o.x = pack2<f16>(v[0], v[1]); o.y = pack2<f16>(v[2], v[3]); o.z = pack2<f16>(v[4], v[5]); o.w = pack2<f16>(v[6], v[7]); }
+    *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = o;
+  }
+}
 
 struct alignas(64) FirstFwdParams {
   CUtensorMap bmap;                  // packed weights [64][nsrc*64], K-major
-  const float* src[2];               // fp32 NHWC images (B, H, W, C), 16-byte aligned
+  CUtensorMap imap[2];               // fp32 images as (W*C, H, B)
   int nsrc, C, B, H, W;              // H, W: input size; output grid H/2 x W/2
   bf16* a; int a_pitch, a_coff;      // LeakyReLU(z) into the consumer view (16-bit)
   int tiles_w, tiles_h, num_tiles;
   int ab_bf16, out_f16;
 };
 
-__host__ __device__ constexpr int first_row_chunks(int C) { return (PATCH_PIX * 4 * C + 15) / 16; }      // 16-byte chunks per staged row
-__host__ __device__ constexpr int first_stage_bytes(int C) { return ((PATCH_H * first_row_chunks(C) * 16 + 127) / 128) * 128; }
-__host__ __device__ constexpr int first_threads(int NG) { return NG * 128 + 32; }
-__host__ __device__ constexpr int first_tmem_cols(int NG) { return NG <= 2 ? 128 : 256; }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-
-// NSRC source images of C channels each, NG gather/epilogue groups of 4 warps (+ one MMA warp)
-template <int NSRC, int C, int NG>
+// NSRC source images of C channels each; NG gather/epilogue groups of 4 warps (+ one MMA warp); NS input stages per group
+template <int NSRC, int C, int NG, int NS>
 __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_fwd(const __grid_constant__ FirstFwdParams p) {
   constexpr uint32_t A_BYTES = 128 * 128;                         // one source: 128 rows x 64 x 16 bit
   constexpr uint32_t GROUP_A = NSRC * A_BYTES;
-  constexpr int CH = first_row_chunks(C), ROW_BYTES = CH * 16, STAGE_SRC = first_stage_bytes(C);
-  constexpr int STAGE = NSRC * STAGE_SRC;                         // one tile's raw fp32 input rows
+  constexpr int STAGE_SRC = first_stage_bytes(C), STAGE = NSRC * STAGE_SRC;
+  constexpr uint32_t BOX_BYTES = NSRC * first_box_bytes(C);
   constexpr int MMA_WARP = NG * 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* atile = smem;                                          // [NG groups][NSRC][128][128 B]
   uint8_t* wsm = smem + NG * GROUP_A;                             // [NSRC][64 rows][128 B]
-  uint8_t* stage = wsm + NSRC * 64 * 128;                         // [NG groups][2 stages][NSRC][18 rows][ROW_BYTES] fp32
-  uint64_t* bars = (uint64_t*)(stage + NG * 2 * STAGE);           // full[NG], done[NG], wbar
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NG + 1);
+  uint8_t* stage = wsm + NSRC * 64 * 128;                         // [NG groups][NS stages][NSRC][18 rows][ROWF] fp32
+  uint64_t* bars = (uint64_t*)(stage + NG * NS * STAGE);          // full[NG], done[NG], wbar, stfull[NG][NS]
+  uint64_t* stfull = bars + 2 * NG + 1;
+  uint32_t* tmem_slot = (uint32_t*)(stfull + NG * NS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * NG + 1; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 2 * NG + 1 + NG * NS; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&p.bmap);
+    for (int s = 0; s < NSRC; ++s) prefetch_tmap(&p.imap[s]);
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)first_tmem_cols(NG)) : "memory");
@@ -159,76 +212,40 @@ __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_fwd(const __gr
     const int g = warp >> 2;                       // group of this warp
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
     const int pl = (threadIdx.x & 127);            // output pixel inside the tile == accumulator row
-    const int olh = pl / FT_W, olw = pl % FT_W;
-    uint8_t* my_stage = stage + g * 2 * STAGE;
+    uint8_t* my_stage = stage + g * NS * STAGE;
     uint8_t* my_a = atile + g * GROUP_A;
+    uint64_t* my_full = stfull + g * NS;
     const int bar_id = 1 + g;                      // named barrier of the group (128 threads)
-    const int row_end = p.W * 4 * C;               // bytes of one image row
+    const int tstride = gridDim.x * NG;
 
-    // raw fp32 rows of tile t -> stage buffer `buf`, 16 bytes per cp.async: the staged row starts at input column
-    // 2*ow0 - 4 (byte offset 24*ow0 - 48 for C = 3: 16-byte aligned because ow0 is a multiple of 16), three pixels
-    // left of the first column the tile needs (2*ow0 - 1).  A chunk lies wholly inside or wholly outside the image row
-    // (W*4*C is a multiple of 16); outside chunks and rows are zero-filled (src-size 0) = the 'same' padding.
-    auto prefetch = [&](int t, int buf) {
-      int tt = t;
-      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
-      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
-      const int ih0 = 2 * th * FT_H - 1;
-      const int x0 = (2 * tw * FT_W - PATCH_LEFT) * 4 * C;       // byte offset of the staged row inside the image row
+    auto fetch = [&](int t, int st) {              // one thread: the tile's input boxes -> stage st
+      const TileCoord tc = tile_coord(t, p.tiles_w, p.tiles_h);
+      mbar_expect_tx(&my_full[st], BOX_BYTES);
 #pragma unroll
-      for (int s = 0; s < NSRC; ++s) {
-        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.src[s]) + (size_t)b * p.H * row_end;
-        const uint32_t dst0 = smem_u32(my_stage + buf * STAGE + s * STAGE_SRC);
-        for (int i = pl; i < PATCH_H * CH; i += 128) {
-          const int r = i / CH, ch = i - r * CH;
-          const int ih = ih0 + r, x = x0 + ch * 16;
-          const bool ok = ih >= 0 && ih < p.H && x >= 0 && x < row_end;
-          cp_async16(dst0 + r * ROW_BYTES + ch * 16, ok ? img + (size_t)ih * row_end + x : img, ok ? 16u : 0u);
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int s = 0; s < NSRC; ++s)
+        tma_load_3d(my_stage + st * STAGE + s * STAGE_SRC, &p.imap[s], &my_full[st], (2 * tc.ow0 - 1 - PATCH_LEFT) * C, 2 * tc.oh0 - 1, tc.b);
     };
 
     int t = blockIdx.x * NG + g;
-    if (t < p.num_tiles) prefetch(t, 0);
+    if (pl == 0)
+      for (int st = 0; st < NS; ++st)
+        if (t + st * tstride < p.num_tiles) fetch(t + st * tstride, st);
     uint32_t n = 0;
-    for (; t < p.num_tiles; t += gridDim.x * NG, ++n) {
-      int tt = t;
-      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
-      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
-      const int oh0 = th * FT_H, ow0 = tw * FT_W;
-      // 1. the next tile's rows start their trip from HBM now and land while this tile is assembled, multiplied and
-      //    written out; then wait for this tile's rows (issued one iteration ago)
-      const int tnext = t + gridDim.x * NG;
-      if (tnext < p.num_tiles) {
-        prefetch(tnext, (n + 1) & 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      // 2. this thread's row: chunk j = taps (kh, kw0), (kh, kw0+1) = two adjacent input pixels = 2*C consecutive
-      //    floats of the staged row -> 2 x 4 channel slots of 16 bit -> chunk (j ^ (row & 7)) of the row (SWIZZLE_128B)
+    for (; t < p.num_tiles; t += tstride, ++n) {
+      const TileCoord tc = tile_coord(t, p.tiles_w, p.tiles_h);
+      const int st = n % NS;
+      // 1. this tile's rows have landed (issued NS tiles ago)
+      mbar_wait(&my_full[st], (n / NS) & 1);
+      // 2. operand rows
 #pragma unroll
-      for (int s = 0; s < NSRC; ++s) {
-        const uint8_t* ps = my_stage + (n & 1) * STAGE + s * STAGE_SRC;
-        uint8_t* row = my_a + s * A_BYTES + pl * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kh = j >> 1, kw0 = (j & 1) * 2;
-          const float* f = reinterpret_cast<const float*>(ps + (2 * olh + kh) * ROW_BYTES + (2 * olw + kw0 + PATCH_LEFT - 1) * 4 * C);
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int e = 0; e < C; ++e) { v[e] = f[e]; v[4 + e] = f[C + e]; }
-          uint4 o;
-          if (p.ab_bf16) { o.x = pack2<bf16>(v[0], v[1]); o.y = pack2<bf16>(v[2], v[3]); o.z = pack2<bf16>(v[4], v[5]); o.w = pack2<bf16>(v[6], v[7]); }
-          else { o.x = pack2<f16>(v[0], v[1]); o.y = pack2<f16>(v[2], v[3]); o.z = pack2<f16>(v[4], v[5]); o.w = pack2<f16>(v[6], v[7]); }
-          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = o;
-        }
-      }
+      for (int s = 0; s < NSRC; ++s)
+        build_row<C>(my_stage + st * STAGE + s * STAGE_SRC, my_a + s * A_BYTES + pl * 128, pl, p.ab_bf16);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (pl == 0) mbar_arrive(&bars[g]);
+      if (pl == 0) {
+        mbar_arrive(&bars[g]);
+        if (t + NS * tstride < p.num_tiles) fetch(t + NS * tstride, st);     // every thread of the group has read the stage
+      }
       // 3. accumulator -> LeakyReLU -> consumer view.  A warp-wide store in which every lane writes into its own pixel
       //    row touches 32 lines = 32 LSU wavefronts (measured: that alone bounded the first version at 182 us per
       //    launch), so the tile is transposed through the group's A buffer (free once the MMA has committed;
@@ -260,11 +277,11 @@ __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_fwd(const __gr
       for (int it = 0; it < 8; ++it) {
         const int qi = it * 128 + pl;                                    // linear 16-byte chunk of the tile
         const int r = qi >> 3, ch = qi & 7;                              // tile row (output pixel), chunk
-        const int oh = oh0 + r / FT_W, ow = ow0 + r % FT_W;
-        const size_t pix = ((size_t)b * Ho + oh) * Wo + ow;
+        const int oh = tc.oh0 + r / FT_W, ow = tc.ow0 + r % FT_W;
+        const size_t pix = ((size_t)tc.b * Ho + oh) * Wo + ow;
         *reinterpret_cast<uint4*>(p.a + pix * p.a_pitch + p.a_coff + ch * 8) = ast[r * 8 + (ch ^ (r & 7))];
       }
-      // the group's stage / A tile / TMEM columns are free again once all 128 threads are here
+      // the group's A tile / TMEM columns are free again once all 128 threads are here
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
   }
@@ -273,30 +290,27 @@ __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_fwd(const __gr
   if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)first_tmem_cols(NG)) : "memory");
 }
 
-size_t first_smem_bytes(int nsrc, int C, int ng) {
-  return (size_t)ng * nsrc * 128 * 128 + (size_t)nsrc * 64 * 128 + (size_t)ng * 2 * nsrc * first_stage_bytes(C) + 8 * (2 * ng + 1) + 16 + 1024;
+size_t first_smem_bytes(int nsrc, int C, int ng, int ns) {
+  return (size_t)ng * nsrc * 128 * 128 + (size_t)nsrc * 64 * 128 + (size_t)ng * ns * nsrc * first_stage_bytes(C) + 8 * (2 * ng + 1 + ng * ns) + 16 + 1024;
 }
 
 // =============================================================================================
 // weight gradient of the first layers.  D[128 = (source, tap*4+slot)][64 filters] += A^T . dz over the tile's 128 pixels:
 // A = the same shared-memory rows as the forward kernel, read as the MN-major operand (M = the 64 k-values of a pixel
 // row are contiguous, GEMM-K = pixels; both sources side by side = M 128; with one source the upper 64 rows read a
-// zeroed buffer), B = the dz tile [128 pixels][64] brought by TMA, also MN-major.  ONE accumulator per CTA collects
-// every tile the CTA processes (fixed order); the 128 x 64 fp32 partial goes to a slab, k_wgrad_reduce sums the CTAs.
+// zeroed buffer), B = the dz tile [128 pixels][64] brought by TMA (double-buffered, one tile ahead), also MN-major.
+// ONE accumulator per CTA collects every tile the CTA processes (fixed order); the 128 x 64 fp32 partial goes to a
+// slab, k_wgrad_reduce sums the CTAs.
 // =============================================================================================
 struct alignas(64) FirstWgradParams {
   CUtensorMap dmap;                  // dz (B, Ho, Wo, 64): boxes 64 ch x 16 x 8 x 1, SWIZZLE_128B
-  const float* src[2];
+  CUtensorMap imap[2];               // fp32 images as (W*C, H, B)
   int nsrc, C, B, H, W;
   int tiles_w, tiles_h, num_tiles;
   int ab_bf16;
   float* slab;                       // [gridDim.x][128][64]
 };
 
-__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 // MN-major SWIZZLE_128B descriptor (conv_umma.cu): 128 bytes of MN per k-row, 8 k-rows per atom (SBO = 1024),
 // LBO = byte distance between consecutive 64-element MN blocks
 __device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -304,27 +318,31 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo_byte
          (1ull << 46) | (2ull << 61);
 }
 
-template <int NSRC, int C, int NG>
+template <int NSRC, int C, int NG, int NS>
 __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_wgrad(const __grid_constant__ FirstWgradParams p) {
   constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t GROUP_A = NSRC * A_BYTES;
-  constexpr int CH = first_row_chunks(C), ROW_BYTES = CH * 16, STAGE_SRC = first_stage_bytes(C);
-  constexpr int STAGE = NSRC * STAGE_SRC;
+  constexpr int STAGE_SRC = first_stage_bytes(C), STAGE = NSRC * STAGE_SRC;
+  constexpr uint32_t BOX_BYTES = NSRC * first_box_bytes(C);
   constexpr int MMA_WARP = NG * 4;
-  constexpr int ZBUF = NSRC == 1 ? 1 : 0;                        // one source: 16 KB of zeros stand in for the second
+  constexpr int ZBUF = NSRC == 1 ? 1 : 0;                         // one source: 16 KB of zeros stand in for the second
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* atile = smem;                                          // [NG][NSRC][128 pixels][128 B]
   uint8_t* zero = atile + NG * GROUP_A;                           // [ZBUF][16 KB]
-  uint8_t* btile = zero + ZBUF * A_BYTES;                        // [NG][128 pixels][128 B] dz
-  uint8_t* stage = btile + NG * A_BYTES;                          // [NG][2][NSRC][18 rows][ROW_BYTES] fp32
-  uint64_t* bars = (uint64_t*)(stage + NG * 2 * STAGE);           // full[NG], dzfull[NG], done[NG], accfull
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NG + 1);
+  uint8_t* btile = zero + ZBUF * A_BYTES;                         // [NG][2][128 pixels][128 B] dz
+  uint8_t* stage = btile + NG * 2 * A_BYTES;                      // [NG][NS][NSRC][18 rows][ROWF] fp32
+  uint64_t* bars = (uint64_t*)(stage + NG * NS * STAGE);          // full[NG], done[NG], accfull, dzfull[NG][2], stfull[NG][NS]
+  uint64_t* dzfull = bars + 2 * NG + 1;
+  uint64_t* stfull = dzfull + 2 * NG;
+  uint32_t* tmem_slot = (uint32_t*)(stfull + NG * NS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3 * NG + 1; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 2 * NG + 1 + 2 * NG + NG * NS; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&p.dmap);
+    for (int s = 0; s < NSRC; ++s) prefetch_tmap(&p.imap[s]);
   }
   if (ZBUF) {
     for (int i = threadIdx.x; i < (int)(A_BYTES / 16); i += first_threads(NG)) reinterpret_cast<uint4*>(zero)[i] = make_uint4(0, 0, 0, 0);
@@ -349,10 +367,10 @@ __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_wgrad(const __
       for (int g = 0; g < NG; ++g) {
         if (t + g >= p.num_tiles) break;
         mbar_wait(&bars[g], n & 1);                                 // rows built
-        mbar_wait(&bars[NG + g], n & 1);                            // dz tile landed
+        mbar_wait(&dzfull[g * 2 + (n & 1)], (n >> 1) & 1);          // dz tile landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t sa = smem_u32(atile + g * GROUP_A), sb = smem_u32(btile + g * A_BYTES);
+          const uint32_t sa = smem_u32(atile + g * GROUP_A), sb = smem_u32(btile + (g * 2 + (n & 1)) * A_BYTES);
           const uint32_t lbo = NSRC == 2 ? A_BYTES : (uint32_t)(NG - g) * A_BYTES;     // second M block: source 1, or the zeros
           const uint64_t ad = desc_mn128(sa, lbo), bd = desc_mn128(sb, A_BYTES);
 #pragma unroll
@@ -361,89 +379,63 @@ __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_wgrad(const __
             asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
                          ::"r"(tmem_base), "l"(ad + (uint64_t)(k * 128)), "l"(bd + (uint64_t)(k * 128)), "r"(idesc), "r"(acc) : "memory");
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 * NG + g])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[NG + g])) : "memory");
         }
         __syncwarp();
         first = false;
       }
     }
     if (elect_one())
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[3 * NG])) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 * NG])) : "memory");
     __syncwarp();
   } else {
     const int g = warp >> 2, q = warp & 3;
     const int pl = (threadIdx.x & 127);
-    const int olh = pl / FT_W, olw = pl % FT_W;
-    uint8_t* my_stage = stage + g * 2 * STAGE;
+    uint8_t* my_stage = stage + g * NS * STAGE;
     uint8_t* my_a = atile + g * GROUP_A;
-    uint8_t* my_b = btile + g * A_BYTES;
+    uint8_t* my_b = btile + g * 2 * A_BYTES;
+    uint64_t* my_full = stfull + g * NS;
     const int bar_id = 1 + g;
-    const int row_end = p.W * 4 * C;
+    const int tstride = gridDim.x * NG;
 
-    auto prefetch = [&](int t, int buf) {          // as in k_conv_first_fwd
-      int tt = t;
-      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
-      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
-      const int ih0 = 2 * th * FT_H - 1;
-      const int x0 = (2 * tw * FT_W - PATCH_LEFT) * 4 * C;
+    auto fetch = [&](int t, int st) {
+      const TileCoord tc = tile_coord(t, p.tiles_w, p.tiles_h);
+      mbar_expect_tx(&my_full[st], BOX_BYTES);
 #pragma unroll
-      for (int s = 0; s < NSRC; ++s) {
-        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.src[s]) + (size_t)b * p.H * row_end;
-        const uint32_t dst0 = smem_u32(my_stage + buf * STAGE + s * STAGE_SRC);
-        for (int i = pl; i < PATCH_H * CH; i += 128) {
-          const int r = i / CH, ch = i - r * CH;
-          const int ih = ih0 + r, x = x0 + ch * 16;
-          const bool ok = ih >= 0 && ih < p.H && x >= 0 && x < row_end;
-          cp_async16(dst0 + r * ROW_BYTES + ch * 16, ok ? img + (size_t)ih * row_end + x : img, ok ? 16u : 0u);
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int s = 0; s < NSRC; ++s)
+        tma_load_3d(my_stage + st * STAGE + s * STAGE_SRC, &p.imap[s], &my_full[st], (2 * tc.ow0 - 1 - PATCH_LEFT) * C, 2 * tc.oh0 - 1, tc.b);
+    };
+    auto fetch_dz = [&](int t, int buf) {
+      const TileCoord tc = tile_coord(t, p.tiles_w, p.tiles_h);
+      mbar_expect_tx(&dzfull[g * 2 + buf], A_BYTES);
+      tma_load_4d(my_b + buf * A_BYTES, &p.dmap, &dzfull[g * 2 + buf], 0, tc.ow0, tc.oh0, tc.b);
     };
 
     int t = blockIdx.x * NG + g;
-    if (t < p.num_tiles) prefetch(t, 0);
+    if (pl == 0) {
+      for (int st = 0; st < NS; ++st)
+        if (t + st * tstride < p.num_tiles) fetch(t + st * tstride, st);
+      if (t < p.num_tiles) fetch_dz(t, 0);
+    }
     uint32_t n = 0;
-    for (; t < p.num_tiles; t += gridDim.x * NG, ++n) {
-      int tt = t;
-      const int tw = tt % p.tiles_w; tt /= p.tiles_w;
-      const int th = tt % p.tiles_h; const int b = tt / p.tiles_h;
-      const int tnext = t + gridDim.x * NG;
-      if (tnext < p.num_tiles) {
-        prefetch(tnext, (n + 1) & 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      if (n > 0) mbar_wait(&bars[2 * NG + g], (n - 1) & 1);         // the previous tile's MMAs have read the rows and dz
-      if (pl == 0) {
-        mbar_expect_tx(&bars[NG + g], A_BYTES);
-        tma_load_4d(my_b, &p.dmap, &bars[NG + g], 0, tw * FT_W, th * FT_H, b);
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    for (; t < p.num_tiles; t += tstride, ++n) {
+      const int st = n % NS;
+      if (n > 0) mbar_wait(&bars[NG + g], (n - 1) & 1);             // the previous tile's MMAs have read the rows and its dz
+      if (pl == 0 && t + tstride < p.num_tiles) fetch_dz(t + tstride, (n + 1) & 1);      // dz one tile ahead
+      mbar_wait(&my_full[st], (n / NS) & 1);
 #pragma unroll
-      for (int s = 0; s < NSRC; ++s) {
-        const uint8_t* ps = my_stage + (n & 1) * STAGE + s * STAGE_SRC;
-        uint8_t* row = my_a + s * A_BYTES + pl * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kh = j >> 1, kw0 = (j & 1) * 2;
-          const float* f = reinterpret_cast<const float*>(ps + (2 * olh + kh) * ROW_BYTES + (2 * olw + kw0 + PATCH_LEFT - 1) * 4 * C);
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int e = 0; e < C; ++e) { v[e] = f[e]; v[4 + e] = f[C + e]; }
-          uint4 o;
-          if (p.ab_bf16) { o.x = pack2<bf16>(v[0], v[1]); o.y = pack2<bf16>(v[2], v[3]); o.z = pack2<bf16>(v[4], v[5]); o.w = pack2<bf16>(v[6], v[7]); }
-          else { o.x = pack2<f16>(v[0], v[1]); o.y = pack2<f16>(v[2], v[3]); o.z = pack2<f16>(v[4], v[5]); o.w = pack2<f16>(v[6], v[7]); }
-          *reinterpret_cast<uint4*>(row + ((j ^ (pl & 7)) << 4)) = o;
-        }
-      }
+      for (int s = 0; s < NSRC; ++s)
+        build_row<C>(my_stage + st * STAGE + s * STAGE_SRC, my_a + s * A_BYTES + pl * 128, pl, p.ab_bf16);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (pl == 0) mbar_arrive(&bars[g]);
+      if (pl == 0) {
+        mbar_arrive(&bars[g]);
+        if (t + NS * tstride < p.num_tiles) fetch(t + NS * tstride, st);
+      }
     }
     if (g == 0) {
       // the CTA's partial tile -> slab (once per CTA: 32 KB)
-      mbar_wait(&bars[3 * NG], 0);
+      mbar_wait(&bars[2 * NG], 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int r = q * 32 + lane;
       float* sl = p.slab + ((size_t)blockIdx.x * 128 + r) * 64;
@@ -461,9 +453,9 @@ __global__ void __launch_bounds__(first_threads(NG)) k_conv_first_wgrad(const __
   if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
 }
 
-size_t first_wgrad_smem_bytes(int nsrc, int C, int ng) {
-  return (size_t)ng * nsrc * 128 * 128 + (nsrc == 1 ? 128 * 128 : 0) + (size_t)ng * 128 * 128 + (size_t)ng * 2 * nsrc * first_stage_bytes(C) +
-         8 * (3 * ng + 1) + 16 + 1024;
+size_t first_wgrad_smem_bytes(int nsrc, int C, int ng, int ns) {
+  return (size_t)ng * nsrc * 128 * 128 + (nsrc == 1 ? 128 * 128 : 0) + (size_t)ng * 2 * 128 * 128 + (size_t)ng * ns * nsrc * first_stage_bytes(C) +
+         8 * (2 * ng + 1 + 2 * ng + ng * ns) + 16 + 1024;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -474,6 +466,22 @@ bool g_first_on = true, g_first_wgrad_on = true;
 
 }  // namespace
 
+// fp32 NHWC image (B, H, W, C) as the 3-D tensor (W*C, H, B); box = one tile's 18 input rows
+static void make_image_map(CUtensorMap* m, const float* src, int C, int B, int H, int W) {
+  cuuint64_t dims[3] = {(cuuint64_t)W * C, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)first_row_floats(C), PATCH_H, 1}, es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)src, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(first-layer image) failed: " + std::to_string((int)r));
+}
+
+// kernel configurations: (sources, channels) -> groups per CTA, input stages per group, CTAs per SM
+//   forward : one source 2 groups x 3 stages (86 KB, two CTAs per SM); two sources 3 groups x 2 stages (204 KB)
+//   wgrad   : one source 3 groups x 2 stages (205 KB); two sources 2 groups x 3 stages (220 KB)
+#define FIRST_FWD_CASES(X) X(1, 1, 2, 3) X(1, 3, 2, 3) X(2, 1, 3, 2) X(2, 3, 3, 2)
+#define FIRST_WG_CASES(X) X(1, 1, 3, 2) X(1, 3, 3, 2) X(2, 1, 2, 3) X(2, 3, 2, 3)
+
 void first_init() {
   static bool done = false;
   if (done) return;
@@ -483,25 +491,28 @@ void first_init() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
     g_encode = (PFN_encodeTiled)fn;
   else cudaGetLastError();
-  cudaFuncSetAttribute(k_conv_first_fwd<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(1, 1, 2));
-  cudaFuncSetAttribute(k_conv_first_fwd<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(1, 3, 2));
-  cudaFuncSetAttribute(k_conv_first_fwd<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(2, 1, 3));
-  cudaFuncSetAttribute(k_conv_first_fwd<2, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(2, 3, 3));
-  cudaFuncSetAttribute(k_conv_first_wgrad<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(1, 1, 2));
-  cudaFuncSetAttribute(k_conv_first_wgrad<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(1, 3, 2));
-  cudaFuncSetAttribute(k_conv_first_wgrad<2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(2, 1, 2));
-  cudaFuncSetAttribute(k_conv_first_wgrad<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(2, 3, 2));
+#define X(NSRC, C, NG, NS) cudaFuncSetAttribute(k_conv_first_fwd<NSRC, C, NG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_smem_bytes(NSRC, C, NG, NS));
+  FIRST_FWD_CASES(X)
+#undef X
+#define X(NSRC, C, NG, NS) cudaFuncSetAttribute(k_conv_first_wgrad<NSRC, C, NG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_smem_bytes(NSRC, C, NG, NS));
+  FIRST_WG_CASES(X)
+#undef X
   const char* e = getenv("GAN_B200_FIRST");          // dev A/B switch: 0 = im2col rows in HBM (round 1)
   g_first_on = !(e && e[0] == '0');
   g_first_wgrad_on = !(e && e[0] == '1');            // 1 = forward kernel only (weight gradient on im2col rows)
 }
 
-bool first_fwd_supported(const FirstLayerOp& op) {
-  for (int s = 0; s < op.nsrc && s < 2; ++s)
-    if (((uintptr_t)op.src[s] & 15) != 0) return false;           // 16-byte cp.async from the image rows
-  return g_first_on && g_encode != nullptr && op.nsrc >= 1 && op.nsrc <= 2 && (op.C == 1 || op.C == 3) && op.H % (2 * FT_H) == 0 &&
-         op.W % (2 * FT_W) == 0 && op.a_pitch % 8 == 0 && op.a_coff % 8 == 0 && (op.dt == DT_F16 || op.dt == DT_BF16);
+static bool first_geom_ok(const float* const* src, int nsrc, int C, int H, int W) {
+  for (int s = 0; s < nsrc && s < 2; ++s)
+    if (((uintptr_t)src[s] & 15) != 0) return false;              // TMA: 16-byte aligned base (strides are: W % 32 == 0)
+  return g_encode != nullptr && nsrc >= 1 && nsrc <= 2 && (C == 1 || C == 3) && H % (2 * FT_H) == 0 && W % (2 * FT_W) == 0;
 }
+
+bool first_fwd_supported(const FirstLayerOp& op) {
+  return g_first_on && first_geom_ok(op.src, op.nsrc, op.C, op.H, op.W) && op.a_pitch % 8 == 0 && op.a_coff % 8 == 0 &&
+         (op.dt == DT_F16 || op.dt == DT_BF16);
+}
+bool first_wgrad_enabled() { return g_first_on && g_first_wgrad_on; }
 
 void launch_conv_first_fwd(Launch L, const FirstLayerOp& op) {
   FirstFwdParams P; memset(&P, 0, sizeof(P));
@@ -511,27 +522,28 @@ void launch_conv_first_fwd(Launch L, const FirstLayerOp& op) {
   CUresult r = g_encode(&P.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)op.wpack, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(first layer) failed: " + std::to_string((int)r));
-  P.src[0] = op.src[0]; P.src[1] = op.src[1]; P.nsrc = op.nsrc; P.C = op.C; P.B = op.B; P.H = op.H; P.W = op.W;
+  for (int s = 0; s < op.nsrc; ++s) make_image_map(&P.imap[s], op.src[s], op.C, op.B, op.H, op.W);
+  P.nsrc = op.nsrc; P.C = op.C; P.B = op.B; P.H = op.H; P.W = op.W;
   P.a = (bf16*)op.a; P.a_pitch = op.a_pitch; P.a_coff = op.a_coff;
   P.tiles_w = (op.W / 2) / FT_W; P.tiles_h = (op.H / 2) / FT_H; P.num_tiles = P.tiles_w * P.tiles_h * op.B;
   P.ab_bf16 = op.dt == DT_F16 ? 0 : 1; P.out_f16 = op.dt == DT_F16 ? 1 : 0;
-  // one source: 2 groups, 72 KB of shared memory -> two CTAs per SM; two sources: 3 groups, 209 KB -> one CTA per SM
-  const int ng = op.nsrc == 1 ? 2 : 3, per_sm = op.nsrc == 1 ? 2 : 1;
-  int grid = (P.num_tiles + ng - 1) / ng;
-  if (grid > 148 * per_sm) grid = 148 * per_sm;
-  const size_t sm = first_smem_bytes(op.nsrc, op.C, ng);
-  if (op.nsrc == 1 && op.C == 1) k_conv_first_fwd<1, 1, 2><<<grid, first_threads(2), sm, L.s>>>(P);
-  else if (op.nsrc == 1) k_conv_first_fwd<1, 3, 2><<<grid, first_threads(2), sm, L.s>>>(P);
-  else if (op.C == 1) k_conv_first_fwd<2, 1, 3><<<grid, first_threads(3), sm, L.s>>>(P);
-  else k_conv_first_fwd<2, 3, 3><<<grid, first_threads(3), sm, L.s>>>(P);
+  const int per_sm = op.nsrc == 1 ? 2 : 1;
+  bool launched = false;
+#define X(NSRC, C_, NG, NS) \
+  if (!launched && op.nsrc == NSRC && op.C == C_) { \
+    int grid = (P.num_tiles + NG - 1) / NG; \
+    if (grid > 148 * per_sm) grid = 148 * per_sm; \
+    k_conv_first_fwd<NSRC, C_, NG, NS><<<grid, first_threads(NG), first_smem_bytes(NSRC, C_, NG, NS), L.s>>>(P); \
+    launched = true; \
+  }
+  FIRST_FWD_CASES(X)
+#undef X
+  if (!launched) throw GanError(-2, "first-layer kernel: unsupported (sources, channels)");
   KLAUNCH(L);
 }
 
 bool first_wgrad_supported(const FirstWgradOp& op) {
-  for (int s = 0; s < op.nsrc && s < 2; ++s)
-    if (((uintptr_t)op.src[s] & 15) != 0) return false;
-  return g_first_on && g_first_wgrad_on && g_encode != nullptr && op.nsrc >= 1 && op.nsrc <= 2 && (op.C == 1 || op.C == 3) &&
-         op.H % (2 * FT_H) == 0 && op.W % (2 * FT_W) == 0 && op.dz_pitch % 8 == 0 && op.dz_coff % 8 == 0 &&
+  return first_wgrad_enabled() && first_geom_ok(op.src, op.nsrc, op.C, op.H, op.W) && op.dz_pitch % 8 == 0 && op.dz_coff % 8 == 0 &&
          (op.dt == DT_F16 || op.dt == DT_BF16) && op.ws != nullptr && op.ws_bytes >= (size_t)148 * 2 * 128 * 64 * 4;
 }
 
@@ -545,19 +557,21 @@ void launch_conv_first_wgrad(Launch L, const FirstWgradOp& op) {
   CUresult r = g_encode(&P.dmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw GanError(-2, "cuTensorMapEncodeTiled(first-layer dz) failed: " + std::to_string((int)r));
-  P.src[0] = op.src[0]; P.src[1] = op.src[1]; P.nsrc = op.nsrc; P.C = op.C; P.B = op.B; P.H = op.H; P.W = op.W;
+  for (int s = 0; s < op.nsrc; ++s) make_image_map(&P.imap[s], op.src[s], op.C, op.B, op.H, op.W);
+  P.nsrc = op.nsrc; P.C = op.C; P.B = op.B; P.H = op.H; P.W = op.W;
   P.tiles_w = Wo / FT_W; P.tiles_h = Ho / FT_H; P.num_tiles = P.tiles_w * P.tiles_h * op.B;
   P.ab_bf16 = op.dt == DT_F16 ? 0 : 1;
   P.slab = op.ws;
-  // one source: 113 KB of shared memory -> two CTAs per SM; two sources: 160 KB -> one
-  const int ng = 2, per_sm = op.nsrc == 1 ? 2 : 1;
-  int grid = (P.num_tiles + ng - 1) / ng;
-  if (grid > 148 * per_sm) grid = 148 * per_sm;
-  const size_t sm = first_wgrad_smem_bytes(op.nsrc, op.C, ng);
-  if (op.nsrc == 1 && op.C == 1) k_conv_first_wgrad<1, 1, 2><<<grid, first_threads(2), sm, L.s>>>(P);
-  else if (op.nsrc == 1) k_conv_first_wgrad<1, 3, 2><<<grid, first_threads(2), sm, L.s>>>(P);
-  else if (op.C == 1) k_conv_first_wgrad<2, 1, 2><<<grid, first_threads(2), sm, L.s>>>(P);
-  else k_conv_first_wgrad<2, 3, 2><<<grid, first_threads(2), sm, L.s>>>(P);
+  int grid = 0;
+#define X(NSRC, C_, NG, NS) \
+  if (grid == 0 && op.nsrc == NSRC && op.C == C_) { \
+    grid = (P.num_tiles + NG - 1) / NG; \
+    if (grid > 148) grid = 148; \
+    k_conv_first_wgrad<NSRC, C_, NG, NS><<<grid, first_threads(NG), first_wgrad_smem_bytes(NSRC, C_, NG, NS), L.s>>>(P); \
+  }
+  FIRST_WG_CASES(X)
+#undef X
+  if (grid == 0) throw GanError(-2, "first-layer weight gradient: unsupported (sources, channels)");
   KLAUNCH(L);
   // CTA partials -> master layout (kh, kw, source*C + c, co), summed in CTA order
   WgradReduceParams R; memset(&R, 0, sizeof(R));

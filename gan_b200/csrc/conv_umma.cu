@@ -249,6 +249,7 @@ constexpr int FWD_STAGES = 3;         // BN <= 128: 3 x 32 KB, two CTAs per SM
 constexpr int FWD_STAGES_256 = 4;     // BN == 256: 4 x 48 KB, one CTA per SM, all 512 TMEM columns
 __host__ __device__ constexpr int fwd_stages(int BN) { return BN == 256 ? FWD_STAGES_256 : FWD_STAGES; }
 constexpr int FWD_THREADS = 192;     // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int F1_STAT_NC = 256;      // epilogue BatchNorm statistics of the one-CTA kernel: up to 256 output channels (8 KB)
 
 __device__ __forceinline__ float epi_apply(float v, int epi, const float* bias, int n) {
   if (epi != EPI_NONE) v += __ldg(bias + n);
@@ -279,9 +280,11 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
   uint64_t* tmem_full = empty + NSTAGE;          // [2]
   uint64_t* tmem_empty = tmem_full + 2;              // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float2* sacc = (float2*)(tmem_slot + 4);           // [4 quadrants][F1_STAT_NC] BatchNorm statistics (stats_ws != nullptr)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntn = p.Nc / BN;
+  const bool stats = BN >= 32 && p.stats_ws != nullptr;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.bmap);
@@ -292,6 +295,8 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 4); }
     ptx::fence_barrier_init();
   }
+  if (stats)
+    for (int i = threadIdx.x; i < 4 * F1_STAT_NC; i += FWD_THREADS) sacc[i] = make_float2(0.f, 0.f);
   if (warp == 2) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
@@ -412,6 +417,28 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
               *reinterpret_cast<uint4*>(dst + c + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
+          if (stats) {
+            // column sums over the warp's 32 rows without shared-memory traffic: a 5-round butterfly in which every
+            // lane keeps the half of its values whose column bit equals its own lane bit and hands the other half to
+            // lane ^ s; after the last round lane l holds column l (31 shuffles per quantity)
+            float x[32], y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { x[j] = valid ? __uint_as_float(v[j]) : 0.f; y[j] = x[j] * x[j]; }
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool up = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < sft; ++i) {
+                const float kx = up ? x[i + sft] : x[i], sx = up ? x[i] : x[i + sft];
+                const float ky = up ? y[i + sft] : y[i], sy = up ? y[i] : y[i + sft];
+                x[i] = kx + __shfl_xor_sync(0xffffffffu, sx, sft);
+                y[i] = ky + __shfl_xor_sync(0xffffffffu, sy, sft);
+              }
+            }
+            float2 a = sacc[q * F1_STAT_NC + n0 + c + lane];
+            a.x += x[0]; a.y += y[0];
+            sacc[q * F1_STAT_NC + n0 + c + lane] = a;
+          }
         }
       } else {
         // N = 16 tile: channel-padded heads (fp32 output with bias / tanh) and padded data gradients
@@ -437,6 +464,15 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+    }
+    if (stats) {
+      // one partial per CTA (quadrants summed in a fixed order): ws[cta][0][c] = sum, [1][c] = sum of squares
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* o = p.stats_ws + ((size_t)blockIdx.x * 2) * p.Nc;
+      for (int c = threadIdx.x - 64; c < p.Nc; c += 128) {
+        const float2 a0 = sacc[c], a1 = sacc[F1_STAT_NC + c], a2 = sacc[2 * F1_STAT_NC + c], a3 = sacc[3 * F1_STAT_NC + c];
+        o[c] = (a0.x + a1.x) + (a2.x + a3.x); o[p.Nc + c] = (a0.y + a1.y) + (a2.y + a3.y);
+      }
     }
   }
   ptx::tc_fence_before();
@@ -625,14 +661,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F2_THREADS, 1) k_con
       if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_leader[buf]);
     }
     if (stats) {
-      // one partial per (CTA, quadrant): ws[(cta*4 + q)][0][c] = sum, [1][c] = sum of squares
+      // one partial per CTA (the four quadrants summed in a fixed order): ws[cta][0][c] = sum, [1][c] = sum of squares
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int et = threadIdx.x - 64;
-      for (int i = et; i < 4 * p.Nc; i += 256) {
-        const int qq = i / p.Nc, c = i - qq * p.Nc;
-        const float2 a = sacc[qq * F2_STAT_NC + c];
-        float* o = p.stats_ws + ((size_t)(blockIdx.x * 4 + qq) * 2) * p.Nc;
-        o[c] = a.x; o[p.Nc + c] = a.y;
+      float* o = p.stats_ws + ((size_t)blockIdx.x * 2) * p.Nc;
+      for (int c = et; c < p.Nc; c += 256) {
+        const float2 a0 = sacc[c], a1 = sacc[F2_STAT_NC + c], a2 = sacc[2 * F2_STAT_NC + c], a3 = sacc[3 * F2_STAT_NC + c];
+        o[c] = (a0.x + a1.x) + (a2.x + a3.x); o[p.Nc + c] = (a0.y + a1.y) + (a2.y + a3.y);
       }
     }
   }
@@ -646,7 +681,7 @@ static size_t f2_smem_bytes(int BN) {
   return (size_t)f2_stages(BN) * f2_stage_bytes(BN) + 1024 + 256 + (size_t)F2_EPI_WARPS * 32 * 33 * 4 + (size_t)4 * F2_STAT_NC * 8;
 }
 
-static size_t fwd_smem_bytes(int BN) { return (size_t)fwd_stages(BN) * (128 * 128 + BN * 128) + 1024 + 256; }
+static size_t fwd_smem_bytes(int BN) { return (size_t)fwd_stages(BN) * (128 * 128 + BN * 128) + 1024 + 256 + (size_t)4 * F1_STAT_NC * 8; }
 
 static bool view_ok(int pitch, int coff, const void* p) {
   return pitch % 8 == 0 && coff % 8 == 0 && ((uintptr_t)p % 16) == 0;
@@ -755,7 +790,7 @@ static bool launch_conv_fwd_umma2(Launch L, const ConvOp& op, int* stat_parts) {
   else if (BN == 128) k_conv_fwd_umma2<128><<<grid, F2_THREADS, sm, L.s>>>(P);
   else k_conv_fwd_umma2<64><<<grid, F2_THREADS, sm, L.s>>>(P);
   KLAUNCH(L);
-  if (P.stats_ws != nullptr) *stat_parts = (int)grid.x * 4;
+  if (P.stats_ws != nullptr) *stat_parts = (int)grid.x;
   return true;
 }
 
@@ -788,6 +823,9 @@ int launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   }
   const int per_sm = BN == 256 ? 1 : 2;
   dim3 grid(P.num_tiles < per_sm * 148 ? P.num_tiles : per_sm * 148);     // persistent
+  // BatchNorm statistics from the fp32 accumulators (one partial per CTA) when every tile holds complete sums
+  P.stats_ws = (g_epi_stats && op.stats_ws != nullptr && op.Nc <= F1_STAT_NC && BN >= 64 && P.ksplit == 1 && !P.f32out &&
+                op.epi == EPI_NONE && op.out_f32 == nullptr) ? op.stats_ws : nullptr;
   const size_t sm = fwd_smem_bytes(BN);
   if (KC == 64) {
     if (BN == 256) k_conv_fwd_umma<256, 64><<<grid, FWD_THREADS, sm, L.s>>>(P);
@@ -801,7 +839,7 @@ int launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   KLAUNCH(L);
   if (P.ksplit > 1)   // deterministic reduction of the k-split slabs + conversion to bf16
     launch_sum_slabs(L, op.dt_out, op.splitk_ws, P.ksplit, (int64_t)op.N * op.Hout * op.Wout, op.Nc, op.out, op.out_pitch, op.out_coff);
-  return 0;
+  return P.stats_ws != nullptr ? (int)grid.x : 0;
 }
 
 // =============================================================================================

@@ -692,6 +692,8 @@ static inline bool bn_small_fits(int G, int64_t P, int narr) {     // P = all pi
   return g_bn_small && G >= 1 && G <= 65535 && P >= G && (size_t)(P / G) * narr * 16 <= (size_t)BNS_MAX_SMEM;
 }
 
+bool bn_small_fwd_fits(int G, int64_t P) { return bn_small_fits(G, P, 1); }
+
 bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int HW, int C, float eps, const float* gamma,
                          const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
                          float* mov_var, float momentum, int act, DropKey dk, void* out, int out_pitch, int out_coff) {

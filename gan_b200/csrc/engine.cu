@@ -395,7 +395,9 @@ static bool first_kernel_ok(const gan_ctx* ctx, const Layer& ly, const Slot& s, 
   if (!ly.first || ctx->dt != DT_BF16 || ctx->engine == GAN_ENGINE_FFMA || ly.norm != NORM_NONE || ly.act != ACT_LEAKY) return false;
   if (ly.Cout != 64 || ly.wp_im2col.p == nullptr || s.src_f32[0] == nullptr) return false;
   FirstLayerOp op; memset(&op, 0, sizeof(op));
+  op.src[0] = s.src_f32[0]; op.src[1] = s.src_f32[1];
   op.nsrc = ly.nsrc; op.C = ly.src_c; op.H = H; op.W = W; op.a_pitch = 8; op.a_coff = 0; op.dt = ctx->dtA;
+  if (ly.nsrc == 2 && s.src_f32[1] == nullptr) return false;
   return first_fwd_supported(op);
 }
 
@@ -463,8 +465,8 @@ static void layer_forward(gan_net* n, Slot& s, int li, View in, View out) {
     ctx->sc().stats_ws.ensure((need > epi ? need : epi) * 4);
   }
   ConvOp cop = (li == 0 && s.used_im2col) ? make_op_im2col(ctx, ly, R_FWD, s, z) : make_op(ctx, ly, R_FWD, in, z, ly.wp_fwd.p);
-  // BatchNorm statistics straight from the fp32 accumulators when the layer runs on the CTA-pair kernel
-  if (ly.norm == NORM_BATCH) cop.stats_ws = ctx->sc().stats_ws.as<float>();
+  // BatchNorm statistics straight from the fp32 accumulators (conv epilogue), unless the whole-layer kernel takes the layer
+  if (ly.norm == NORM_BATCH && !bn_small_fwd_fits(1, P)) cop.stats_ws = ctx->sc().stats_ws.as<float>();
   const int stat_parts = run_conv_fwd(ctx, cop);
   DropKey dk = drop_key(ctx, ly, s);
   // SURVEY 8d byte model: forward = read z + write activation = 2*s per element (statistics belong to the conv epilogue)
@@ -988,7 +990,12 @@ static void side_mark_mid(gan_ctx* ctx) { CUDA_CHECK(cudaEventRecord(ctx->ev_mid
 static void main_wait_mid(gan_ctx* ctx) { CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_mid, 0)); }
 // first-layer rows of an input that several nets / streams read: built on the main stream before a fork
 static void share_im2col(gan_ctx* ctx, gan_net* n, const float* img, int B, int H, int W) {
-  if (im2col_on(ctx, n->layers[0])) cached_im2col(ctx, img, B, H, W, n->C);
+  if (!im2col_on(ctx, n->layers[0])) return;
+  // the first-layer kernels rebuild the rows in shared memory (forward and weight gradient): nothing to share
+  const Layer& ly = n->layers[0];
+  Slot probe; probe.src_f32[0] = img; probe.src_f32[1] = ly.nsrc == 2 ? img : nullptr;
+  if (ctx->dtG == ctx->dtA && first_wgrad_enabled() && first_kernel_ok(ctx, ly, probe, H, W)) return;
+  cached_im2col(ctx, img, B, H, W, n->C);
 }
 
 // Static loss scale for fp16 gradient storage: the largest gradient any loss head emits (`g_head`: weight / number of

@@ -46,6 +46,7 @@ void launch_norm_stats_finalize(Launch L, const float* ws, int nparts, int64_t n
 // out = act(dropout(z*scale+shift)); scale == nullptr => identity affine (no-norm layers).
 // One-kernel BatchNorm / InstanceNorm layer (G groups of P/G pixels) for small groups; returns false (nothing
 // launched) when a group's slab does not fit in shared memory.
+bool bn_small_fwd_fits(int G, int64_t P);     // the whole-layer kernel will take this layer (no separate statistics needed)
 bool launch_bn_small_fwd(Launch L, int dt, const void* z, int64_t P, int G, int HW, int C, float eps, const float* gamma,
                          const float* beta, float* mean, float* inv, float* scale, float* shift, float* mov_mean,
                          float* mov_var, float momentum, int act, DropKey dk, void* out, int out_pitch, int out_coff);
@@ -137,6 +138,7 @@ struct FirstWgradOp {
   float* ws; size_t ws_bytes;                                  // partial-tile workspace
 };
 bool first_wgrad_supported(const FirstWgradOp& op);
+bool first_wgrad_enabled();
 void launch_conv_first_wgrad(Launch L, const FirstWgradOp& op);
 
 // second stage of the deterministic weight-gradient reduction (conv_umma.cu)
