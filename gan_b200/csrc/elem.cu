@@ -1403,6 +1403,47 @@ __device__ __forceinline__ float4 ld_cols4(const f16* p) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
+__device__ __forceinline__ float4 ld_cols4(const bf16* p) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// The same gather as the data gradient of a 4x4 stride-2 'same' Conv2D whose per-tap products are in cols
+// (discriminator first layer, dL/d(input image)): dx[ih, iw, c] = sum over the 4 taps with 2*o - 1 + k = i of
+// cols[o][tap*4 + c]; output = compact 4-channel rows (8 bytes per pixel) in the gradient format.
+template <typename T>
+__global__ void __launch_bounds__(256) k_col2im_grad(const T* __restrict__ cols, int B, int Hin, int Win, T* __restrict__ out) {
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(q % Wo); const int64_t r = q / Wo; const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    const int a = oh & 1, b = ow & 1, i = oh >> 1, j = ow >> 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int th = 0; th < 2; ++th) {
+      const int kh = a ? (th ? 2 : 0) : (th ? 3 : 1), dh = a ? (th ? 0 : 1) : (th ? -1 : 0);
+      const int ih = i + dh;
+      if (ih < 0 || ih >= Hin) continue;
+#pragma unroll
+      for (int tw = 0; tw < 2; ++tw) {
+        const int kw = b ? (tw ? 2 : 0) : (tw ? 3 : 1), dw = b ? (tw ? 0 : 1) : (tw ? -1 : 0);
+        const int iw = j + dw;
+        if (iw < 0 || iw >= Win) continue;
+        const float4 v = ld_cols4(cols + (((int64_t)n * Hin + ih) * Win + iw) * 64 + (kh * 4 + kw) * 4);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
+    }
+    *reinterpret_cast<uint2*>(out + q * 4) = make_uint2(pack2<T>(acc[0], acc[1]), pack2<T>(acc[2], acc[3]));
+  }
+}
+void launch_col2im_grad(Launch L, int dt, const void* cols, int B, int Hin, int Win, void* out) {
+  GAN_REQUIRE(dt == DT_F16 || dt == DT_BF16, "col2im_grad is 16-bit only");
+  const int64_t total = (int64_t)B * Hin * Win * 4;
+  if (dt == DT_F16) k_col2im_grad<f16><<<grid_for(total, 256, 16), 256, 0, L.s>>>((const f16*)cols, B, Hin, Win, (f16*)out);
+  else k_col2im_grad<bf16><<<grid_for(total, 256, 16), 256, 0, L.s>>>((const bf16*)cols, B, Hin, Win, (bf16*)out);
+  KLAUNCH(L);
+}
+
 template <typename TC>
 __global__ void __launch_bounds__(256) k_col2im_tanh(const TC* __restrict__ cols, const float* __restrict__ bias, int B,
                                                      int Hin, int Win, int C, float* __restrict__ out) {

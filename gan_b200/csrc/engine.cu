@@ -342,6 +342,17 @@ static void pack_weights(gan_net* n) {
               idx[(size_t)nn * Kt + sidx * 64 + t * 4 + c] = (int)(l0.w_off + ((int64_t)t * l0.Cin + sidx * C + c) * l0.Cout + nn);
       add_gather(idx, l0.wp_im2col, ctx->dtA);
     }
+    if (!n->is_gen && l0.first && ctx->dt == DT_BF16 && l0.src_c <= 4 && l0.Cout == 64) {
+      // data gradient of the first layer w.r.t. the image the generator produced (the `tar` half when the
+      // discriminator takes (input, target)) as per-tap products: B[n = tap*4 + c][k = co] = W[kh, kw, c0 + c, co]
+      const int C = l0.src_c, c0 = l0.nsrc == 2 ? C : 0;
+      std::vector<int> dc((size_t)64 * 64, -1);
+      for (int t = 0; t < 16; ++t)
+        for (int c = 0; c < C; ++c)
+          for (int co = 0; co < 64; ++co)
+            dc[(size_t)(t * 4 + c) * 64 + co] = (int)(l0.w_off + ((int64_t)t * l0.Cin + c0 + c) * l0.Cout + co);
+      add_gather(dc, l0.wp_dcols, ctx->dtG);
+    }
     Layer& lh = n->layers.back();
     if (n->is_gen && lh.head && ctx->dt == DT_BF16 && lh.Cout <= 4 && lh.Cin % 64 == 0) {
       const int C = lh.Cout, Ci = lh.Cin;           // master (kh,kw,co,ci): row tap*C+co, column ci
@@ -768,6 +779,13 @@ static void discriminator_forward(gan_net* d, int slot, const float* inp, const 
   layer_forward(d, s, 4, in, make_view(s.logits.p, B, h - 1, w - 1, 1));
 }
 
+static bool g_in_cols = [] { const char* e = getenv("GAN_B200_DIN_COLS"); return !(e && e[0] == '0'); }();   // dev A/B switch
+static bool in_cols_on(const gan_ctx* ctx, const gan_net* d) {
+  const Layer& l0 = d->layers[0];
+  return g_in_cols && !d->is_gen && ctx->dt == DT_BF16 && ctx->engine != GAN_ENGINE_FFMA && l0.first && l0.kind == K_CONV_S2 &&
+         l0.src_c <= 4 && l0.Cout == 64 && l0.norm == NORM_NONE && l0.wp_dcols.p != nullptr;
+}
+
 // Backward from s.dlogit (already filled).  want_wgrad: accumulate into d->grads.
 static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool want_input_grad) {
   gan_ctx* ctx = d->ctx;
@@ -795,6 +813,25 @@ static void discriminator_backward(gan_net* d, int slot, bool want_wgrad, bool w
       ConvOp dg = make_op_1tap(G, 64, din, lh.Cin, lh.Cin, lh.wp_dcols.p, ctx->dtG, ctx->dtG);
       dg.real_k = 16;
       run_conv_fwd(ctx, dg);
+      continue;
+    }
+    if (li == 0 && want_input_grad) { s.din0_pitch = d->Cin0_p; s.din0_coff = d->layers[0].nsrc == 2 ? d->C : 0; }
+    if (li == 0 && want_input_grad && in_cols_on(ctx, d)) {
+      // dL/d(generated image) = per-tap products dz . W[tap] (ONE 1x1 GEMM over dz instead of 4 classes x 4 shifted
+      // taps with a 16-channel padded output tile) gathered by k_col2im_grad into compact 4-channel rows
+      Layer& l0 = d->layers[0];
+      din.p = nullptr;
+      layer_backward(d, s, li, src, GradSrc{nullptr, 0, 0}, din, want_wgrad);      // leaves dz in the stream's scratch
+      int Ho, Wo; out_dims(l0.kind, in.H, in.W, Ho, Wo);
+      View dzv = make_view(ctx->sc().dz_scratch.p, B, Ho, Wo, l0.Cout);
+      s.dcols0.ensure((size_t)B * Ho * Wo * 64 * 2);
+      View colsv = make_view(s.dcols0.p, B, Ho, Wo, 64);
+      ConvOp dg = make_op_1tap(dzv, l0.Cout, colsv, 64, 64, l0.wp_dcols.p, ctx->dtG, ctx->dtG);
+      dg.real_n = 16 * l0.src_c;
+      run_conv_fwd(ctx, dg);
+      s.din0.ensure((size_t)B * in.H * in.W * 4 * 2);
+      launch_col2im_grad(ctx->L(), ctx->dtG, s.dcols0.p, B, Ho, Wo, s.din0.p);
+      s.din0_pitch = 4; s.din0_coff = 0;
       continue;
     }
     layer_backward(d, s, li, src, GradSrc{nullptr, 0, 0}, din, want_wgrad);
@@ -1054,7 +1091,7 @@ static void pix2pix_step(gan_net* g, gan_net* d, gan_adam* go, gan_adam* dopt, c
   disc_bce(d, 1, 1.f, gan_scale * S, training, false, 0);
   if (training) {
     discriminator_backward(d, 1, false, true);                           // dL_G/d(gen_output) through D (:210)
-    GradSrc dgan{d->slots[1].din0.p, d->Cin0_p, C};
+    GradSrc dgan{d->slots[1].din0.p, d->slots[1].din0_pitch, d->slots[1].din0_coff};
     generator_backward(g, 0, dgan, GradSrc{nullptr, 0, 0}, y, S * lambda / (float)n_img, false, true);
     comm_join(ctx);
     adam_apply(go, true);                                                // (:213)
@@ -1144,8 +1181,8 @@ static void cyclegan_step(gan_net* g, gan_net* f, gan_net* dx, gan_net* dy, gan_
     generator_backward(f, 0, none, none, x, lc, true);                                   // cycle x: through F into fake_y
     generator_backward(g, 1, none, none, y, lc, true);                                   // cycle y: through G into fake_x
     // the last contribution to each generator's gradients: their buckets go to the communication stream as they close
-    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->Cin0_p, 0}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false, true);
-    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, dx->Cin0_p, 0}, GradSrc{g->slots[1].dxin.p, g->Cp, 0}, nullptr, 0.f, false, true);
+    generator_backward(g, 0, GradSrc{dy->slots[1].din0.p, dy->slots[1].din0_pitch, dy->slots[1].din0_coff}, GradSrc{f->slots[0].dxin.p, f->Cp, 0}, nullptr, 0.f, false, true);
+    generator_backward(f, 1, GradSrc{dx->slots[1].din0.p, dx->slots[1].din0_pitch, dx->slots[1].din0_coff}, GradSrc{g->slots[1].dxin.p, g->Cp, 0}, nullptr, 0.f, false, true);
     comm_join(ctx);
     adam_apply(og, true); adam_apply(of, true); adam_apply(odx, true); adam_apply(ody, true);     // (:263-273)
   }
@@ -1393,9 +1430,11 @@ int gan_comm_unique_id(void* out128) {
 int gan_ctx_comm_init(gan_ctx* ctx, int rank, int world, const void* unique_id128) {
   API_BEGIN
   CUDA_CHECK(cudaSetDevice(ctx->device));
-  // Sharded optimizer from 4 ranks up (measured at N=2: the exposed all-gather + separate repack cost more than the
-  // half Adam they save: 5.97 vs 5.62 ms/step); GAN_B200_SHARD_OPT=0/1 forces it
-  { const char* e = getenv("GAN_B200_SHARD_OPT"); ctx->shard_optimizer = e ? (e[0] != '0') : (world >= 4); }
+  // Sharded optimizer (reduce-scatter -> Adam on 1/world of the parameters -> all-gather of the fp32 master): measured
+  // SLOWER than all-reduce + the fused full Adam at every world size on 8 x B200 (ms/step at global batch 64:
+  // N=2 5.97 vs 5.62, N=4 4.06 vs 3.66, N=8 3.32 vs 3.11): the all-gather of 229 MB sits on the critical path where
+  // the all-reduce hides under the backward sweep.  Off unless GAN_B200_SHARD_OPT=1.
+  { const char* e = getenv("GAN_B200_SHARD_OPT"); ctx->shard_optimizer = e ? (e[0] != '0') : false; }
   comm_init(ctx, rank, world, unique_id128);
   API_END
 }
@@ -1542,7 +1581,10 @@ int gan_net_debug_tensor(gan_net* net, int slot, const char* name, float* host_d
   int src_dt = ctx->dtA;
   if (nm == "out" && net->is_gen) { src = s.out_f32.p; C = net->C; P = (int64_t)s.B * s.H * s.W; pitch = C; is_f32 = true; }
   else if (nm == "logits" && !net->is_gen) { src = s.logits.p; C = 1; P = logits_count(s); pitch = 1; is_f32 = true; }
-  else if (nm == "din0" && !net->is_gen) { src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = net->Cin0_p; src_dt = ctx->dtG; }
+  else if (nm == "din0" && !net->is_gen) {
+    GAN_REQUIRE(s.din0_pitch == net->Cin0_p, "din0 is stored as compact rows of the generated-image channels (GAN_B200_DIN_COLS=0 for the full tensor)");
+    src = s.din0.p; C = net->Cin0; P = (int64_t)s.B * s.H * s.W; pitch = net->Cin0_p; src_dt = ctx->dtG;
+  }
   else {
     size_t dot = nm.rfind('.');
     GAN_REQUIRE(dot != std::string::npos, "debug tensor name must be <layer>.z or <layer>.a");

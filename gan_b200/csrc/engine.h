@@ -145,7 +145,8 @@ struct Slot {
   DevBuf xin, d8, out_f32, dd8, dxin;
   std::vector<DevBuf> cat, dcat, dskip;
   // discriminator
-  DevBuf in0, logits, dlogit, din0;
+  DevBuf in0, logits, dlogit, din0, dcols0;     // dcols0: per-tap products of the first layer's data gradient
+  int din0_pitch = 0, din0_coff = 0;            // layout of din0: (Cin0_p, first wanted channel) or compact (4, 0)
   const void* im2col[2] = {nullptr, nullptr};   // first-layer im2col rows per input source (ctx cache entries)
   const float* src_f32[2] = {nullptr, nullptr}; // the fp32 input images of this call (first-layer kernel, lazy rows for wgrad)
   DevBuf cols, gcols;        // generator head: cols = x*W (forward), gcols = im2col(dz) (backward)

@@ -22,6 +22,7 @@ void launch_im2col(Launch L, int dt_rows, const float* src, int B, int H, int W,
 // Transposed-conv head as GEMM + col2im: cols[m][(kh*4+kw)*4 + co] (fp32, 64 per input-grid point m) ->
 // out[n, 2i+a, 2j+b, co] = tanh(bias[co] + sum of the 4 contributing taps)   (base_gan.py:201-204)
 // cols: fp32 rows, or fp16 rows (dt_cols == DT_F16: half the bytes of the largest intermediate of the step)
+void launch_col2im_grad(Launch L, int dt, const void* cols, int B, int Hin, int Win, void* out_rows4);
 void launch_col2im_tanh(Launch L, int dt_cols, const void* cols, const float* bias, int B, int Hin, int Win, int C, float* out_f32);
 // Discriminator head (ZeroPad + Conv2D 4x4 s1, 512 -> 1, bias; base_gan.py:157-161) in cols form:
 //   cols[m'][tap*4] = a[m',:] . w[tap,:]  (GEMM over the 31x31 activation grid), then

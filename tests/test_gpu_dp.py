@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 SEED = 123
 
 
-def _worker(rank, world, port, q, model, precision):
+def _worker(rank, world, port, q, model, precision, env=None):
+    os.environ.update(env or {})               # communication-mode switches are read when the communicator is created
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -82,17 +83,24 @@ def _worker(rank, world, port, q, model, precision):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model,precision", [("pix2pix", "fp32"), ("pix2pix", "bf16"), ("cyclegan", "fp32")])
-def test_two_gpu_data_parallel_step_matches_oracle(model, precision):
-    """One process per GPU, NCCL reduce-scatter of the gradient buckets, 1/world Adam, all-gather of the updated
-    parameters: both ranks report the same (all-reduced) losses, end with identical weights, and match the oracle's
+@pytest.mark.parametrize("model,precision,env", [
+    ("pix2pix", "fp32", {}),                                  # fp32 parity mode: fp32 gradient all-reduce + fused Adam
+    ("pix2pix", "bf16", {}),                                  # 16-bit mode (default): gradient buckets travel as bf16
+    ("pix2pix", "bf16", {"GAN_B200_COMM16": "0"}),            # 16-bit mode, fp32 on the wire
+    ("pix2pix", "bf16", {"GAN_B200_SHARD_OPT": "1"}),         # reduce-scatter + 1/world Adam + all-gather (opt-in)
+    ("cyclegan", "fp32", {}),
+    ("cyclegan", "fp32", {"GAN_B200_SHARD_OPT": "1"}),
+])
+def test_two_gpu_data_parallel_step_matches_oracle(model, precision, env):
+    """One process per GPU, NCCL all-reduce of the gradient buckets under the backward sweep (or the opt-in sharded
+    optimizer): both ranks report the same (all-reduced) losses, end with identical weights, and match the oracle's
     data-parallel definition for two consecutive steps."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, model, precision)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, model, precision, env)) for r in range(2)]
     for p in procs:
         p.start()
     out = [q.get(timeout=900) for _ in range(2)]
