@@ -98,6 +98,17 @@ void comm_allreduce_async(gan_ctx* ctx, float* buf, int64_t n) {
   ctx->comm_pending = true;
 }
 
+// The same on a bf16 buffer (ncclBfloat16 = 9): half the bytes on NVLink and half the time the NCCL kernels hold SMs.
+void comm_allreduce_bf16_async(gan_ctx* ctx, void* buf, int64_t n) {
+  if (ctx->world <= 1 || n <= 0) return;
+  GAN_REQUIRE(ctx->comm != nullptr, "communicator not initialised");
+  cudaEvent_t e = next_event(ctx);
+  CUDA_CHECK(cudaEventRecord(e, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, e, 0));
+  nccl_check(g_nccl.allreduce(buf, buf, (size_t)n, 9, 0, (ncclComm_t_)ctx->comm, ctx->comm_stream), "ncclAllReduce(bf16)");
+  ctx->comm_pending = true;
+}
+
 // Sharded form (ZeRO-1 style): the bucket [buf, buf+n) (n a multiple of world) is reduce-scattered in
 // place — rank r ends up with the sum of sub-range r, [buf + r*n/world, +n/world) — on the communication stream.
 void comm_reducescatter_async(gan_ctx* ctx, float* buf, int64_t n) {

@@ -1069,8 +1069,32 @@ __device__ __forceinline__ float adam_lr_t(const AdamArgs& a) {
   const double t = (double)(*a.t_dev);
   return (float)(a.lr * sqrt(1.0 - pow(a.b2, t)) / (1.0 - pow(a.b1, t)));
 }
+// gradient loads: fp32 buffer, or the bf16 communication buffer the data-parallel all-reduce ran on
+__device__ __forceinline__ float adam_g1(const AdamArgs& a, long long i) {
+  return a.g16 != nullptr ? __uint_as_float((uint32_t)a.g16[i] << 16) : a.g[i];
+}
+__device__ __forceinline__ float4 adam_g4(const AdamArgs& a, long long i) {      // i % 4 == 0
+  if (a.g16 == nullptr) return *reinterpret_cast<const float4*>(a.g + i);
+  const uint2 t = *reinterpret_cast<const uint2*>(a.g16 + i);
+  return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                     __uint_as_float(t.y & 0xffff0000u));
+}
+__global__ void __launch_bounds__(256) k_grad_to_bf16(const float* __restrict__ g, uint16_t* __restrict__ o, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    uint2 w; w.x = pack2<bf16>(v.x, v.y); w.y = pack2<bf16>(v.z, v.w);
+    reinterpret_cast<uint2*>(o)[i] = w;
+  }
+}
+void launch_grad_to_bf16(Launch L, const float* g, uint16_t* g16, int64_t n) {
+  GAN_REQUIRE(n % 4 == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)g16 & 7) == 0, "gradient range must be 4-aligned");
+  if (n <= 0) return;
+  k_grad_to_bf16<<<grid_for(n / 4, 256, 8), 256, 0, L.s>>>(g, g16, n / 4);
+  KLAUNCH(L);
+}
+
 __device__ __forceinline__ float adam_update(const AdamArgs& a, long long i, float lr_t, float b1, float b2) {
-  float gr = a.g[i] * a.gscale, mm = a.m[i], vv = a.v[i], pp = a.p[i];
+  float gr = adam_g1(a, i) * a.gscale, mm = a.m[i], vv = a.v[i], pp = a.p[i];
   mm += (gr - mm) * (1.f - b1);
   vv += (gr * gr - vv) * (1.f - b2);
   pp -= lr_t * mm / (sqrtf(vv) + a.eps);
@@ -1114,7 +1138,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long idx = base + (long long)(a0 + rg + 16 * i) * E.B + b4;
-      P[i] = *reinterpret_cast<const float4*>(a.p + idx); G[i] = *reinterpret_cast<const float4*>(a.g + idx);
+      P[i] = *reinterpret_cast<const float4*>(a.p + idx); G[i] = adam_g4(a, idx);
       M[i] = *reinterpret_cast<const float4*>(a.m + idx); V[i] = *reinterpret_cast<const float4*>(a.v + idx);
     }
 #pragma unroll
@@ -1166,7 +1190,7 @@ __global__ void __launch_bounds__(256) k_adam_pack(AdamArgs a, const AdamPackEnt
       const int ai = a0 + half * 32 + ty + 4 * i;
       if (ai < E.A && bi < E.B) {
         const long long idx = base + (long long)ai * E.B + bi;
-        P[i] = a.p[idx]; G[i] = a.g[idx]; M[i] = a.m[idx]; V[i] = a.v[idx];
+        P[i] = a.p[idx]; G[i] = adam_g1(a, idx); M[i] = a.m[idx]; V[i] = a.v[idx];
       }
     }
 #pragma unroll

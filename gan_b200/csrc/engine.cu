@@ -654,12 +654,20 @@ static void comm_reduce_bucket(gan_net* n, int64_t from) {
   if (ctx->shard_optimizer) {
     comm_reducescatter_async(ctx, gr + lo, hi - lo);
     n->bucket_off.push_back(lo); n->bucket_len.push_back(hi - lo);
+  } else if (ctx->comm16) {
+    // bf16 on the wire: the bucket is rounded once (fp32 range, 8-bit mantissa: below the 16-bit operand noise the
+    // gradient already carries) into the communication buffer, summed there, and Adam reads the sum from it
+    n->grads16.ensure((size_t)total * 2);
+    uint16_t* g16 = n->grads16.as<uint16_t>();
+    launch_grad_to_bf16(ctx->L(), gr + lo, g16 + lo, hi - lo);
+    comm_allreduce_bf16_async(ctx, g16 + lo, hi - lo);
+    if (lo == 0) n->grads16_valid = true;
   } else {
     comm_allreduce_async(ctx, gr + lo, hi - lo);
   }
   n->reduced_from = lo;
 }
-static void comm_step_begin(gan_net* n) { n->bucket_off.clear(); n->bucket_len.clear(); n->reduced_from = -1; }
+static void comm_step_begin(gan_net* n) { n->bucket_off.clear(); n->bucket_len.clear(); n->reduced_from = -1; n->grads16_valid = false; }
 
 // Backward through one generator call.  d1/d2: extra gradient sources w.r.t. the tanh output
 // (activation dtype); ref/l1_coef: + l1_coef*sign(out-ref).  Accumulates into g->grads.
@@ -957,7 +965,8 @@ static void adam_apply(gan_adam* o, bool reduced = false) {
     return;
   }
   AdamArgs a{n->params.as<float>(), n->grads.as<float>(), o->m.as<float>(), o->v.as<float>(), o->t_dev.as<long long>(),
-             o->lr, o->b1, o->b2, (float)o->eps, gscale};
+             o->lr, o->b1, o->b2, (float)o->eps, gscale, nullptr};
+  if (ctx->world > 1 && ctx->comm16 && n->grads16_valid) a.g16 = n->grads16.as<uint16_t>();
   // fused update + repack: 28 B/param of optimizer traffic + 4 B/param for the two packed 16-bit copies
   ProfScope ps(ctx, FAM_ADAM, 32.0 * (double)n->nparams);
   launch_adam_pack(ctx->L(), ctx->dtA, ctx->dtG, a, (const AdamPackEntry*)n->adam_tab.p, n->adam_nent, n->adam_tiles);
@@ -1435,6 +1444,9 @@ int gan_ctx_comm_init(gan_ctx* ctx, int rank, int world, const void* unique_id12
   // N=2 5.97 vs 5.62, N=4 4.06 vs 3.66, N=8 3.32 vs 3.11): the all-gather of 229 MB sits on the critical path where
   // the all-reduce hides under the backward sweep.  Off unless GAN_B200_SHARD_OPT=1.
   { const char* e = getenv("GAN_B200_SHARD_OPT"); ctx->shard_optimizer = e ? (e[0] != '0') : false; }
+  // 16-bit storage mode: gradient buckets are all-reduced as bf16 (GAN_B200_COMM16=0: fp32 on the wire); the fp32
+  // parity mode and the sharded optimizer keep fp32
+  { const char* e = getenv("GAN_B200_COMM16"); ctx->comm16 = (ctx->dt == DT_BF16 && !ctx->shard_optimizer && world > 1) ? (e ? (e[0] != '0') : 1) : 0; }
   comm_init(ctx, rank, world, unique_id128);
   API_END
 }
@@ -1541,11 +1553,21 @@ static void unscale_host(float* p, int64_t n, float s) {
   const float inv = 1.f / s;
   for (int64_t i = 0; i < n; ++i) p[i] *= inv;
 }
+// gradient range -> host fp32.  Data parallel with bf16 communication: the all-reduced (summed) gradient lives in grads16.
+static void grads_to_host(gan_net* net, int64_t off, int64_t numel, float* host_dst) {
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  if (net->ctx->world > 1 && net->ctx->comm16 && net->grads16_valid) {
+    std::vector<uint16_t> tmp((size_t)numel);
+    CUDA_CHECK(cudaMemcpy(tmp.data(), net->grads16.as<uint16_t>() + off, (size_t)numel * 2, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < numel; ++i) { uint32_t b = (uint32_t)tmp[(size_t)i] << 16; memcpy(host_dst + i, &b, 4); }
+  } else {
+    CUDA_CHECK(cudaMemcpy(host_dst, net->grads.as<float>() + off, (size_t)numel * 4, cudaMemcpyDeviceToHost));
+  }
+  unscale_host(host_dst, numel, net->grad_scale);
+}
 int gan_net_get_grad(gan_net* net, int idx, float* host_dst) {
   API_BEGIN
-  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
-  CUDA_CHECK(cudaMemcpy(host_dst, tensor_dev(net, idx, &net->grads), net->tensors[idx].numel * 4, cudaMemcpyDeviceToHost));
-  unscale_host(host_dst, net->tensors[idx].numel, net->grad_scale);
+  grads_to_host(net, tensor_dev(net, idx, &net->grads) - net->grads.as<float>(), net->tensors[idx].numel, host_dst);
   API_END
 }
 int gan_net_num_params(gan_net* net, int64_t* out) { *out = net->nparams; return GAN_OK; }
@@ -1564,9 +1586,7 @@ int gan_net_set_params(gan_net* net, const float* host_src) {
 }
 int gan_net_get_grads(gan_net* net, float* host_dst) {
   API_BEGIN
-  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
-  CUDA_CHECK(cudaMemcpy(host_dst, net->grads.p, net->nparams * 4, cudaMemcpyDeviceToHost));
-  unscale_host(host_dst, net->nparams, net->grad_scale);
+  grads_to_host(net, 0, net->nparams, host_dst);
   API_END
 }
 

@@ -103,6 +103,7 @@ struct gan_ctx {
   std::vector<cudaEvent_t> comm_events;   // fork/join events (reused round-robin)
   size_t comm_ev_next = 0;
   bool comm_pending = false;
+  int comm16 = 0;                         // world > 1, 16-bit mode: gradients travel as bf16 (half the NCCL bytes)
   int shard_optimizer = 1;                // world > 1: reduce-scatter + 1/world Adam + all-gather (0: all-reduce + full Adam)
   Launch L() { return Launch{cs(), &launches}; }
   size_t esize() const { return dt == DT_F32 ? 4 : 2; }
@@ -166,6 +167,8 @@ struct gan_net {
   int ntrain = 0;
   int64_t nparams = 0, nmov = 0;
   DevBuf params, grads, mov;
+  DevBuf grads16;             // data parallel: bf16 copy of the gradient buckets, the buffer NCCL all-reduces (ctx->comm16)
+  bool grads16_valid = false; // grads16 holds the all-reduced gradient of the last step (the getters read it)
   float grad_scale = 1.f;     // loss scale the contents of `grads` carry (removed by Adam / by the gradient getters)
   // data parallel, sharded optimizer: the gradient buckets reduce-scattered so far in this step (flat offset, length;
   // lengths are multiples of the world size) — rank r owns sub-range r of every bucket
@@ -197,6 +200,7 @@ void comm_allreduce_sum(gan_ctx* ctx, float* buf, int64_t n);
 // Fork: all-reduce [buf, buf+n) on the communication stream once everything enqueued so far on the
 // compute stream has finished; comm_join makes the compute stream wait for all forked reductions.
 void comm_allreduce_async(gan_ctx* ctx, float* buf, int64_t n);
+void comm_allreduce_bf16_async(gan_ctx* ctx, void* buf, int64_t n);
 void comm_join(gan_ctx* ctx);
 void comm_reducescatter_async(gan_ctx* ctx, float* buf, int64_t n);
 void comm_allgather_buckets(gan_ctx* ctx, float* base, const int64_t* off, const int64_t* len, int nb);

@@ -99,7 +99,12 @@ struct AdamPackEntry {
   int tiles_a, tiles_b, tile_begin, pad1;
 };
 struct AdamRange { long long off; int n, pad; };
-struct AdamArgs { float* p; const float* g; float* m; float* v; const long long* t_dev; double lr, b1, b2; float eps, gscale; };
+struct AdamArgs {
+  float* p; const float* g; float* m; float* v; const long long* t_dev; double lr, b1, b2; float eps, gscale;
+  const uint16_t* g16;      // != nullptr: the (all-reduced) gradient as bf16 bits, same indexing as g (data parallel)
+};
+// fp32 gradient range -> bf16 communication buffer (round to nearest even), n a multiple of 4
+void launch_grad_to_bf16(Launch L, const float* g, uint16_t* g16, int64_t n);
 void launch_adam_pack(Launch L, int dt_fwd, int dt_dgrad, const AdamArgs& a, const AdamPackEntry* tab_dev, int nent, int total_tiles);
 void launch_adam_ranges(Launch L, const AdamArgs& a, const AdamRange* tab_dev, int nranges);
 // zero the gamma / beta / bias gradient ranges (the kernels that produce them accumulate)

@@ -9,7 +9,7 @@ configs[2]  CycleGAN 256x256x3, global batch 32 on 8 GPUs  -> 4 (x, y) pairs per
 configs[3]  Pix2Pix 512x512 (reference default channels='1', also '3'), global batch 32 on 8 GPUs -> 4 images per rank
 configs[4]  generator-only predict 256x256x3, batch 256 on ONE GPU (rank 0 only)
 Every rank keeps its per-rank batch (weak definition of the shard), gradients go through the library's NCCL path
-(reduce-scatter, sharded Adam, all-gather); time = CUDA events on the library stream, max over ranks.  Prints one JSON
+(bucketed bf16 all-reduce under the backward sweep, fused Adam; GAN_B200_SHARD_OPT=1 for the sharded optimizer); time = CUDA events on the library stream, max over ranks.  Prints one JSON
 object on rank 0 with images/s, conv TFLOP/s per GPU and the fraction of the measured burst bf16 peak."""
 import json
 import os
