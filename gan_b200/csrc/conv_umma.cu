@@ -242,6 +242,7 @@ struct alignas(64) UmmaFwdParams {
   int ab_bf16;                       // operand format of A and B (both: the weights are packed in the input's dtype)
   int out_f16;                       // 16-bit output format: 1 = f16 (activations), 0 = bf16 (gradients)
   float* ws; int ksplit; long long slab;   // split-K: split ks stores fp32 into ws[ks][pix][Nc] (no atomics)
+  int stage_out;                     // one-CTA kernel: 16-bit output rows written through the shared-memory staging (coalesced)
   float* stats_ws;                   // CTA-pair kernel: per-(CTA, quadrant) column sums / sums of squares, or nullptr
 };
 
@@ -393,6 +394,23 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
       const bool valid = nb < p.N && mh < p.Hm && mw < p.Wm && oh < p.Hout && ow < p.Wout;
       const int64_t pix = ((int64_t)nb * p.Hout + oh) * p.Wout + ow;
       bf16* dst = p.out + pix * p.out_pitch + p.out_coff + n0;
+      // Coalesced 16-bit output (launches without epilogue statistics; the 8 KB accumulator region then serves as four
+      // warp-private 2 KB staging buffers): a lane holds one output ROW, so a direct 16-byte store per lane touches 32
+      // different 128-byte lines per instruction = 32 LSU wavefronts (what bounded the first version of the first-layer
+      // kernel).  Staged through shared memory (XOR-swizzled 16-byte slots, conflict-free both ways),
+      // four lanes write the 64 contiguous bytes of a row: 8 lines per instruction.
+      const bool staged = BN >= 32 && p.stage_out != 0 && !stats && p.ksplit == 1 && !p.f32out;
+      bf16* rdst[4]; bool rvalid[4];
+      if (staged) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int src = 8 * i + (lane >> 2);
+          const unsigned long long a = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)dst, src);
+          rdst[i] = reinterpret_cast<bf16*>((uintptr_t)a) + (lane & 3) * 8;
+          rvalid[i] = __shfl_sync(0xffffffffu, valid ? 1 : 0, src) != 0;
+        }
+      }
+      uint4* stg = reinterpret_cast<uint4*>(sacc) + q * 128;
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -401,7 +419,24 @@ __global__ void __launch_bounds__(FWD_THREADS) k_conv_fwd_umma(const __grid_cons
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           ptx::tmem_ld32(acc + c, v);
-          if (valid && (p.ksplit > 1 || p.f32out)) {
+          if (staged) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = cvt_pair(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]), p.out_f16);
+              stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2), j = lane & 3;
+              const uint4 w = stg[r * 4 + (j ^ ((r >> 1) & 3))];
+              if (rvalid[i]) *reinterpret_cast<uint4*>(rdst[i] + c) = w;
+            }
+            __syncwarp();
+          } else if (valid && (p.ksplit > 1 || p.f32out)) {
             float4* wdst = reinterpret_cast<float4*>(p.ws + (long long)(tile % p.ksplit) * p.slab + pix * p.Nc + n0 + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -823,6 +858,8 @@ int launch_conv_fwd_umma(Launch L, const ConvOp& op) {
   }
   const int per_sm = BN == 256 ? 1 : 2;
   dim3 grid(P.num_tiles < per_sm * 148 ? P.num_tiles : per_sm * 148);     // persistent
+  static const bool stage_on = [] { const char* e = getenv("GAN_B200_STAGED_EPI"); return !(e && e[0] == '0'); }();   // dev A/B switch
+  P.stage_out = stage_on ? 1 : 0;
   // BatchNorm statistics from the fp32 accumulators (one partial per CTA) when every tile holds complete sums
   P.stats_ws = (g_epi_stats && op.stats_ws != nullptr && op.Nc <= F1_STAT_NC && BN >= 64 && P.ksplit == 1 && !P.f32out &&
                 op.epi == EPI_NONE && op.out_f32 == nullptr) ? op.stats_ws : nullptr;
