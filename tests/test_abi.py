@@ -57,3 +57,20 @@ def test_image_xform_struct_matches_the_header():
     names = [n.strip() for decl in re.findall(r"int ([^;]+);", body) for n in decl.split(",")]
     assert names == [f[0] for f in _ffi.ImageXform._fields_]
     assert C.sizeof(_ffi.ImageXform) == 4 * len(names)
+
+
+def test_built_library_carries_the_blackwell_instructions():
+    """The hot path must stay on tcgen05 / TMEM / TMA: the SASS of the built library holds the CTA-pair MMA
+    (tcgen05.mma.cta_group::2), TMA tensor loads incl. the 3-D image boxes of the first-layer kernels, TMEM loads, and no
+    legacy HMMA (mma.sync) instruction anywhere.  Skipped when cuobjdump is not installed."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "gan_b200", "csrc", "libgan_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA.2CTA", "UTCHMMA ", "UTMALDG.4D", "UTMALDG.3D", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "LDTM."):
+        assert mnemonic in sass, mnemonic
+    import re
+    assert not re.search(r"\bHMMA\.", sass), "mma.sync tensor-core instructions found: the convolutions must be tcgen05"
