@@ -1,5 +1,5 @@
 // conv_first.cu — the image-channel first layers (G.down1 base_gan.py:180, D.down1 base_gan.py:141: Conv2D 4x4 s2
-// 'same', Cin in {1,2,3,4} per source image, 64 filters, no normalisation, LeakyReLU 0.3) without im2col rows in HBM.
+// 'same', Cin in {1,3} per source image (one or two sources), 64 filters, no normalisation, LeakyReLU 0.3) without im2col rows in HBM.
 //
 // The 4x4 stride-2 window of a 3-channel image is 48 values per output pixel; as a tcgen05 operand it is one
 // 128-byte row k = tap*4 + channel slot (64 x 16 bit, slots >= C zero).  Round 1 materialised those rows in HBM
@@ -9,13 +9,14 @@
 //     per source image (out-of-bounds = zero = 'same' padding) through a ring of 2-3 stages per group, so the next
 //     tiles are in flight while this one is processed; every thread assembles the row of its output pixel (16 taps x
 //     4 slots -> eight swizzled 16-byte stores), fences the async proxy and signals the MMA warp;
-//   * warp 8 issues 4 (x sources) tcgen05.mma M=128 x N=64 x K=16 against the stationary weight tile (one TMA load per
+//   * the last warp issues 4 (x sources) tcgen05.mma M=128 x N=64 x K=16 against the stationary weight tile (one TMA load per
 //     CTA) into the group's TMEM columns and commits to the group's barrier;
 //   * the same 4 warps drain TMEM: a = LeakyReLU(z) goes through shared memory into the consumer view (skip-concat
 //     buffer) with 8 lanes per 128-byte row.  z itself is not stored: LeakyReLU keeps the sign, so the backward pass
 //     takes the activation derivative from a (launch_norm_bwd with a strided z view).
-// Two groups per CTA alternate tiles, so the gather / store phases of one overlap the other's.  HBM traffic per image
-// batch: the fp32 image(s) once + a — the roofline of this layer is HBM, and the kernel moves nothing else.
+// Two or three groups per CTA work on different tiles, so the gather / store phases of one overlap the others'.  HBM
+// traffic per image batch: the fp32 image(s) once + a (ncu: DRAM reads = 1.00 x the image bytes) — the roofline of this
+// layer is HBM, and the kernel moves nothing else.  k_conv_first_wgrad (below) is the weight gradient on the same front end.
 #include <cuda.h>
 #include <cstring>
 #include "kernels.h"
