@@ -166,3 +166,21 @@ def test_cyclegan_single_sweep_equals_four_tape_gradients():
     for a, b in list(zip(sweep_g, g_g)) + list(zip(sweep_f, g_f)):
         den = float(b.abs().max())
         assert float((a - b).abs().max()) <= 1e-12 * max(den, 1e-30) + 1e-18
+
+
+@pytest.mark.parametrize("n,h,w,c,nsrc", [(2, 8, 8, 3, 1), (1, 8, 12, 3, 2), (2, 4, 8, 1, 2)])
+def test_first_layer_operand_layouts_against_autograd(n, h, w, c, nsrc):
+    """The slot-4 row / weight-pack / per-tap-cols index maps the first-layer kernels use (restated in oracle/direct.py)
+    reproduce Conv2D 4x4 s2 'same' of the concatenated sources, its weight gradient and its input gradient."""
+    rng = np.random.default_rng(7)
+    srcs = [rng.normal(size=(n, h, w, c)) for _ in range(nsrc)]
+    k = rng.normal(size=(4, 4, c * nsrc, 64))
+    x = torch.tensor(np.concatenate(srcs, -1)).permute(0, 3, 1, 2).requires_grad_(True)
+    kt = torch.tensor(k, requires_grad=True)
+    y = O.conv2d_s2_same(x, kt)
+    dz = rng.normal(size=(n, h // 2, w // 2, 64))
+    (gx, gk) = torch.autograd.grad((y * _t(dz)).sum(), (x, kt))
+    assert np.abs(D.conv2d_s2_same_via_rows(srcs, k) - _n(y.detach())).max() < 1e-11
+    assert np.abs(D.conv2d_s2_same_wgrad_via_rows(srcs, dz) - gk.numpy()).max() < 1e-10
+    c0 = c * (nsrc - 1)                                   # the generated image is the LAST source of concatenate([inp, tar])
+    assert np.abs(D.conv2d_s2_same_dgrad_via_cols(dz, k, c0, c) - _n(gx)[..., c0:c0 + c]).max() < 1e-10
