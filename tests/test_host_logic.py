@@ -138,3 +138,21 @@ def test_input_pipeline_host_side_descriptions():
     import pytest
     with pytest.raises(ValueError):
         ip.pack_images([np.zeros((4, 4, 3), np.float32)])
+
+
+def test_profile_scripts_parse_the_committed_launch_list(tmp_path):
+    """scripts/summarize_launches.py and scripts/make_traffic.py (the tools behind profiles/*.md and roofline.traffic) read
+    the committed ncu launch list: 200+ launches, the forward-type convolution family present, positive DRAM traffic."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "r02_launches_one_step.csv")
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "summarize_launches.py"), csv_path], capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    first = out.stdout.splitlines()[0]
+    assert int(first.split()[0]) >= 200 and "k_conv_fwd_umma2<256>" in out.stdout and "k_conv_first_fwd" in out.stdout
+    with open(os.path.join(root, "profiles", "r02_traffic.json")) as f:
+        tj = json.load(f)
+    assert tj["launches_captured"] >= 50 and tj["dram_bytes_per_launch_avg"] > 1e7 and tj["wgrad_launches_captured"] >= 20
